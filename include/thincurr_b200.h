@@ -1,0 +1,136 @@
+/* thincurr_b200.h -- C ABI of libthincurr_b200.so
+ *
+ * Drop-in boundary for ThinCurr's dense operator builds.  The first block re-exports, with
+ * identical names / argument lists / ownership and error conventions, the BIND(C) entry
+ * points that the reference's Python layer binds from liboftpy.so for this path
+ * (reference = OpenFUSIONToolkit @ d08f001b; `F:` = src/python/wrappers/thincurr_f.F90,
+ * `P:` = src/python/OpenFUSIONToolkit/ThinCurr/_interface.py).  The second block is the
+ * flat ISO_C_BINDING-style interface a Fortran host (thin_wall.F90) or a multi-GPU
+ * launcher calls: row-block sharded builds into caller-provided device memory.
+ *
+ * Conventions (same as the reference, F:49-61, _core.py:282-288):
+ *   - success <=> error_str[0] == '\0'; error_str has room for THINCURR_ERROR_SLEN chars
+ *   - strings are NUL-terminated C strings; an empty cache_file means "no cache"
+ *   - matrices returned through `void**` are LIBRARY-OWNED host buffers (pinned) in the
+ *     reference's column-major layout, valid until the model is destroyed or rebuilt
+ *   - LOGICAL(c_bool) arguments are 1-byte bool
+ * There is NO CPU fallback: every build routine fails (error_str) if no CUDA device works.
+ */
+#ifndef THINCURR_B200_H
+#define THINCURR_B200_H
+#include <stdbool.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define THINCURR_PATH_SLEN 200  /* OFT_PATH_SLEN  (src/include/local.h) */
+#define THINCURR_ERROR_SLEN 200 /* OFT_ERROR_SLEN */
+
+/* ---------------------------------------------------------------------------------------
+ * Block 1: reference-compatible entry points (names bound by P:17-120)
+ * ------------------------------------------------------------------------------------ */
+
+/* oftpy_init / oftpy_load_xml: src/python/wrappers/oft_base_f.F90:56-110, :117-140.
+ * oftpy_load_xml parses <oft><thincurr>...</thincurr></oft> (eta, icoils, vcoils, sens_mask) */
+void oftpy_init(int nthreads, bool quiet, const char* input_file, int* slens, void* abort_callback);
+void oftpy_load_xml(const char* xml_file, void** oft_node_ptr);
+void oftpy_set_nthreads(int nthreads);
+void oftpy_set_debug(int debug_level);
+
+/* F:49-228  thincurr_setup: mesh from arrays (np>0; r[np][3], lc[nc][3] 1-based, reg or NULL)
+ * or from a native HDF5 mesh file (np<=0).  pmap: periodic map [np] or {-1}.
+ * sizes[9] = np,ne,nc,nreg,np_active,nholes,n_vcoils,nelems,n_icoils */
+void thincurr_setup(const char* mesh_file, int np, const double* r_loc, int nc, const int* lc_loc,
+                    const int* reg_loc, const int* pmap_loc, int jumper_start, void** tw_ptr, int* sizes,
+                    char* error_str, void* xml_ptr);
+
+/* F:545-581  self-inductance.  *Lmat_ptr -> double[nelems*nelems], Fortran Lmat(nelems,nelems).
+ * use_hodlr=true is rejected (compressed path is out of scope). */
+void thincurr_Lmat(void* tw_ptr, bool use_hodlr, void** Lmat_ptr, const char* cache_file, char* error_str);
+
+/* F:585-617  B-field reconstruction operators. *Bmat_ptr -> Bel(nelems,np,3), *Bdr_ptr -> Bdr(np,n_icoils,3) */
+void thincurr_Bmat(void* tw_ptr, void* hodlr_ptr, void** Bmat_ptr, void** Bdr_ptr, const char* cache_file,
+                   char* error_str);
+
+/* F:621-638  element<->Icoil mutuals. *Mc_ptr -> Ael2dr(nelems,n_icoils).  Also builds Ael2coil/Acoil2coil. */
+void thincurr_Mcoil(void* tw_ptr, void** Mc_ptr, const char* cache_file, char* error_str);
+
+/* F:642-690  sensors. *Ms_ptr -> Ael2sen(nsensors,nelems), *Msc_ptr -> Adr2sen(nsensors,n_icoils) */
+void thincurr_Msensor(void* tw_ptr, const char* sensor_file, void** Ms_ptr, void** Msc_ptr, int* nsensors,
+                      int* njumpers, void** sensor_ptr, const char* cache_file, char* error_str);
+/* F:694-703 */
+void thincurr_get_sensor_name(void* sensor_ptr, int sensor_ind, char* sensor_name, char* error_str);
+
+/* F:501-521  mutual inductance between two models into CALLER-owned Mmat, Fortran (nelems2,nelems1) */
+void thincurr_cross_coupling(void* tw_ptr1, void* tw_ptr2, double* Mmat, const char* cache_file, char* error_str);
+
+/* F:906-921  resistance matrix, 1-based CSR, library-owned (CPU: O(N), thin_wall.F90:1690-1930) */
+void thincurr_Rmat(void* tw_ptr, int** kr_ptr, int** lc_ptr, double** mat_ptr, char* error_str);
+
+/* eta accessors used by the reference tests (F:925-1000 region) */
+void thincurr_get_eta(void* tw_ptr, double* eta_surf, char* error_str);
+void thincurr_set_eta(void* tw_ptr, const double* eta_surf, const double* eta_vol, const double* thickness,
+                      char* error_str);
+
+/* ---------------------------------------------------------------------------------------
+ * Block 2: B200-native flat interface (what a Fortran host binds through ISO_C_BINDING;
+ * see include/thincurr_b200_f.F90 and INTEGRATION.md).  All return 0 on success, else an
+ * error code with a message retrievable by thincurr_b200_last_error().
+ * ------------------------------------------------------------------------------------ */
+const char* thincurr_b200_last_error(void);
+int thincurr_b200_device_count(void);
+void thincurr_b200_destroy(void* tw_ptr);
+
+/* Setup from arrays with explicit node/side sets (what the Python host passes after reading
+ * the mesh file itself).  lc 1-based.  nodeset_ptr[nnodesets+1] offsets into nodeset_val (1-based
+ * vertex ids); closures = 1-based cell ids (sideset 1) or NULL. */
+int thincurr_b200_setup(int np, const double* r, int nc, const int* lc, const int* reg, const int* pmap,
+                        int nnodesets, const int* nodeset_ptr, const int* nodeset_val, int nclosures,
+                        const int* closures, void* xml_ptr, void** tw_ptr, int* sizes);
+
+/* Coil sets / sensors from memory (alternative to XML / floops.loc).  kind: 0 = Vcoil, 1 = Icoil.
+ * set_ptr[nsets+1] -> filament ranges; fil_ptr[nfil+1] -> point ranges into pts[][3]. */
+int thincurr_b200_set_coils(void* tw_ptr, int kind, int nsets, const int* set_ptr, const int* fil_ptr,
+                            const double* pts, const double* scales, const double* radius,
+                            const double* res_per_len, const int* sens_mask, int* sizes);
+int thincurr_b200_set_sensors(void* tw_ptr, int nsensors, const int* fil_ptr, const double* pts,
+                              const double* scale_fac, void** sensor_ptr);
+
+/* Sensor mutuals for sensors given in memory: *Ms_ptr -> Ael2sen(nsensors,nelems), *Msc_ptr -> Adr2sen */
+int thincurr_b200_msensor(void* tw_ptr, void* sensor_ptr, void** Ms_ptr, void** Msc_ptr);
+
+/* Row partition of the dense operators.  Rows are grouped in locality-preserving patches
+ * (internal order); a shard is a contiguous patch range balanced by pair count.
+ * row_ids[nrows] returns the reference (0-based) DOF id of every local row. */
+int thincurr_b200_plan(void* tw_ptr, int nshards, int shard, int* nrows);
+int thincurr_b200_shard_rows(void* tw_ptr, int nshards, int shard, int* row_ids);
+
+/* Self-inductance rows of one shard into caller-provided DEVICE memory d_out[nrows][ld]
+ * (row r = full reference row row_ids[r], i.e. Lmat(:,row_ids[r]+1); ld >= nelems), on the
+ * CUDA device that owns d_out, enqueued on `stream` (cudaStream_t as void*), asynchronous.
+ * stats[8] (host, optional): tiles, pairs evaluated, far pairs, near T evaluations, ... */
+int thincurr_b200_Lmat_shard(void* tw_ptr, int nshards, int shard, double* d_out, int64_t ld, void* stream,
+                             int64_t* stats);
+/* Same from HOST mesh each call (uploads model, builds, copies rows back to h_out[nrows][ld]);
+ * the end-to-end path used by bench.py's e2e leg. */
+int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* h_out, int64_t ld,
+                                  int64_t* stats);
+/* B-field operator rows (element index sharded the same way): d_out[3][np][nrows] */
+int thincurr_b200_Bel_shard(void* tw_ptr, int nshards, int shard, double* d_out, void* stream);
+
+/* iquad histogram / visited-pair count of the reference loop computed on the GPU:
+ * hist[19], visited = # ordered pairs not skipped by thin_wall.F90:1034. */
+int thincurr_b200_pair_stats(void* tw_ptr, int64_t* hist, int64_t* visited);
+
+/* FP64 DFMA peak microbenchmark on the current device (TFLOP/s, FMA = 2 flops). */
+double thincurr_b200_dfma_peak(int device, double* sm_clock_mhz);
+
+/* Introspection for tests. */
+int thincurr_b200_get_model(void* tw_ptr, int* pmap, int* lc, int* kfh, int* lfh, double* qbasis, double* ca);
+int thincurr_b200_hashes(void* tw_ptr, int32_t* hash_lc, int32_t* hash_r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,94 @@
+"""ctypes binding of libthincurr_b200.so (mirror of the reference's
+src/python/OpenFUSIONToolkit/_interface.py:38-120 for this path).
+
+The library is built in-tree by `openfusiontoolkit_b200.build`; importing this module fails
+loudly if it cannot be loaded -- there is no alternative compute path.
+"""
+import ctypes
+import os
+from ctypes import c_bool, c_char_p, c_double, c_int, c_int64, c_void_p
+
+import numpy
+from numpy import float64, int32
+
+root_path = os.path.realpath(os.path.dirname(__file__))
+lib_path = os.path.join(root_path, 'libthincurr_b200.so')
+if not os.path.exists(lib_path):
+    try:
+        from .build import build as _build
+        _build()
+    except Exception as exc:  # pragma: no cover
+        raise FileNotFoundError('libthincurr_b200.so is missing and could not be built: %s' % exc)
+try:
+    oftpy_lib = ctypes.CDLL(lib_path)
+except OSError as load_error:  # pragma: no cover
+    raise FileNotFoundError('Unable to load thincurr-b200 shared library') from load_error
+
+c_int_ptr = ctypes.POINTER(c_int)
+c_int_ptr_ptr = ctypes.POINTER(c_int_ptr)
+c_double_ptr = ctypes.POINTER(c_double)
+c_double_ptr_ptr = ctypes.POINTER(c_double_ptr)
+c_void_ptr_ptr = ctypes.POINTER(c_void_p)
+mu0 = numpy.pi * 4.E-7
+
+
+def ctypes_numpy_array(type, ndim):
+    return numpy.ctypeslib.ndpointer(dtype=type, ndim=ndim, flags='C_CONTIGUOUS')
+
+
+def ctypes_subroutine(function, argtypes=None, restype=None):
+    function.restype = restype
+    if argtypes is not None:
+        function.argtypes = argtypes
+    return function
+
+
+# ---- reference-compatible entry points (same argument lists as ThinCurr/_interface.py:17-120)
+oft_init = ctypes_subroutine(oftpy_lib.oftpy_init, [c_int, c_bool, c_char_p, ctypes_numpy_array(int32, 1), c_void_p])
+oftpy_load_xml = ctypes_subroutine(oftpy_lib.oftpy_load_xml, [c_char_p, c_void_ptr_ptr])
+oftpy_set_debug = ctypes_subroutine(oftpy_lib.oftpy_set_debug, [c_int])
+oftpy_set_nthreads = ctypes_subroutine(oftpy_lib.oftpy_set_nthreads, [c_int])
+thincurr_setup = ctypes_subroutine(oftpy_lib.thincurr_setup,
+    [c_char_p, c_int, ctypes_numpy_array(float64, 2), c_int, ctypes_numpy_array(int32, 2), ctypes_numpy_array(int32, 1),
+     ctypes_numpy_array(int32, 1), c_int, c_void_ptr_ptr, ctypes_numpy_array(int32, 1), c_char_p, c_void_p])
+thincurr_Lmat = ctypes_subroutine(oftpy_lib.thincurr_Lmat, [c_void_p, c_bool, c_void_ptr_ptr, c_char_p, c_char_p])
+thincurr_Bmat = ctypes_subroutine(oftpy_lib.thincurr_Bmat, [c_void_p, c_void_p, c_void_ptr_ptr, c_void_ptr_ptr, c_char_p, c_char_p])
+thincurr_Mcoil = ctypes_subroutine(oftpy_lib.thincurr_Mcoil, [c_void_p, c_void_ptr_ptr, c_char_p, c_char_p])
+thincurr_Msensor = ctypes_subroutine(oftpy_lib.thincurr_Msensor,
+    [c_void_p, c_char_p, c_void_ptr_ptr, c_void_ptr_ptr, c_int_ptr, c_int_ptr, c_void_ptr_ptr, c_char_p, c_char_p])
+thincurr_get_sensor_name = ctypes_subroutine(oftpy_lib.thincurr_get_sensor_name, [c_void_p, c_int, c_char_p, c_char_p])
+thincurr_cross_coupling = ctypes_subroutine(oftpy_lib.thincurr_cross_coupling,
+    [c_void_p, c_void_p, ctypes_numpy_array(float64, 2), c_char_p, c_char_p])
+thincurr_Rmat = ctypes_subroutine(oftpy_lib.thincurr_Rmat, [c_void_p, c_int_ptr_ptr, c_int_ptr_ptr, c_double_ptr_ptr, c_char_p])
+thincurr_get_eta = ctypes_subroutine(oftpy_lib.thincurr_get_eta, [c_void_p, ctypes_numpy_array(float64, 1), c_char_p])
+thincurr_set_eta = ctypes_subroutine(oftpy_lib.thincurr_set_eta, [c_void_p, c_void_p, c_void_p, c_void_p, c_char_p])
+
+# ---- B200-native flat interface (include/thincurr_b200.h, block 2)
+b200_last_error = ctypes_subroutine(oftpy_lib.thincurr_b200_last_error, [], c_char_p)
+b200_device_count = ctypes_subroutine(oftpy_lib.thincurr_b200_device_count, [], c_int)
+b200_destroy = ctypes_subroutine(oftpy_lib.thincurr_b200_destroy, [c_void_p])
+b200_setup = ctypes_subroutine(oftpy_lib.thincurr_b200_setup,
+    [c_int, ctypes_numpy_array(float64, 2), c_int, ctypes_numpy_array(int32, 2), c_void_p, c_void_p, c_int,
+     ctypes_numpy_array(int32, 1), ctypes_numpy_array(int32, 1), c_int, ctypes_numpy_array(int32, 1), c_void_p,
+     c_void_ptr_ptr, ctypes_numpy_array(int32, 1)], c_int)
+b200_set_coils = ctypes_subroutine(oftpy_lib.thincurr_b200_set_coils,
+    [c_void_p, c_int, c_int, ctypes_numpy_array(int32, 1), ctypes_numpy_array(int32, 1), ctypes_numpy_array(float64, 2),
+     ctypes_numpy_array(float64, 1), ctypes_numpy_array(float64, 1), ctypes_numpy_array(float64, 1),
+     ctypes_numpy_array(int32, 1), ctypes_numpy_array(int32, 1)], c_int)
+b200_set_sensors = ctypes_subroutine(oftpy_lib.thincurr_b200_set_sensors,
+    [c_void_p, c_int, ctypes_numpy_array(int32, 1), ctypes_numpy_array(float64, 2), ctypes_numpy_array(float64, 1),
+     c_void_ptr_ptr], c_int)
+b200_msensor = ctypes_subroutine(oftpy_lib.thincurr_b200_msensor, [c_void_p, c_void_p, c_void_ptr_ptr, c_void_ptr_ptr], c_int)
+b200_plan = ctypes_subroutine(oftpy_lib.thincurr_b200_plan, [c_void_p, c_int, c_int, c_int_ptr], c_int)
+b200_shard_rows = ctypes_subroutine(oftpy_lib.thincurr_b200_shard_rows, [c_void_p, c_int, c_int, ctypes_numpy_array(int32, 1)], c_int)
+b200_Lmat_shard = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard,
+    [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p], c_int)
+b200_Lmat_shard_host = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard_host,
+    [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p], c_int)
+b200_Bel_shard = ctypes_subroutine(oftpy_lib.thincurr_b200_Bel_shard, [c_void_p, c_int, c_int, c_void_p, c_void_p], c_int)
+b200_pair_stats = ctypes_subroutine(oftpy_lib.thincurr_b200_pair_stats,
+    [c_void_p, numpy.ctypeslib.ndpointer(dtype=numpy.int64, ndim=1, flags='C_CONTIGUOUS'), ctypes.POINTER(c_int64)], c_int)
+b200_dfma_peak = ctypes_subroutine(oftpy_lib.thincurr_b200_dfma_peak, [c_int, c_double_ptr], c_double)
+b200_get_model = ctypes_subroutine(oftpy_lib.thincurr_b200_get_model,
+    [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int)
+b200_hashes = ctypes_subroutine(oftpy_lib.thincurr_b200_hashes, [c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)], c_int)

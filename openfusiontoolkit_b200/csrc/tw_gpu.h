@@ -1,0 +1,41 @@
+// tw_gpu.h -- host-visible interface of the CUDA side (device mirrors + kernel launchers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "tw_host.h"
+#include "tw_plan.h"
+
+namespace tw {
+
+// Device mirror of a PatchSet (replicated on every GPU that builds rows of this model).
+struct DevicePatchSet {
+  ChunkMeta* chunks = nullptr;
+  double* geom = nullptr;
+  int *dmin = nullptr, *dmax = nullptr, *chunk_dof = nullptr, *inc_ptr = nullptr;
+  uint16_t* inc = nullptr;
+  int *patch_chunk_ptr = nullptr, *dof_orig = nullptr;
+  std::string upload_from(const PatchSet& ps);
+  void release();
+  ~DevicePatchSet() { release(); }
+};
+
+struct DeviceState {
+  int device = 0;
+  DevicePatchSet ps;
+};
+
+std::string gpu_init_constants();
+
+// Run the tile kernel: out[row_out[internal row]][ld] += (1/4pi) sum ... ; out must be zeroed.
+// h_stats (optional, 8 x u64) forces a stream sync: far pairs, near T evals, 1/r evals, phipot evals.
+std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, const std::vector<Tile>& tiles,
+                           const std::vector<int>& row_out, bool self, double* d_out, long long ld, cudaStream_t stream,
+                           unsigned long long* h_stats);
+
+// FP64 DFMA peak microbenchmark (TFLOP/s)
+double gpu_dfma_peak(int device, double* sm_clock_mhz);
+
+}  // namespace tw

@@ -1,0 +1,541 @@
+// tw_io.cpp -- input readers for the ThinCurr drop-in: <thincurr> XML, native HDF5 mesh
+// files, floops.loc sensor files, and gfortran unformatted-record framing for cache files.
+//
+// No libhdf5 / FoX is available (or wanted) here: the native mesh format written by
+// OpenFUSIONToolkit/util.py:62-94 (h5py defaults: superblock v0, v1 object headers, symbol
+// table groups, contiguous little-endian datasets) is parsed directly.
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "tw_host.h"
+
+namespace tw {
+
+// ------------------------------------------------------------------ XML
+const XmlNode* XmlNode::child(const std::string& t) const {
+  for (auto& k : kids)
+    if (k->tag == t) return k.get();
+  return nullptr;
+}
+std::vector<const XmlNode*> XmlNode::children(const std::string& t) const {
+  std::vector<const XmlNode*> out;
+  for (auto& k : kids)
+    if (k->tag == t) out.push_back(k.get());
+  return out;
+}
+
+namespace {
+struct XmlParser {
+  const std::string& s;
+  size_t p = 0;
+  std::string err;
+  explicit XmlParser(const std::string& src) : s(src) {}
+  void skip_ws() {
+    while (p < s.size() && std::isspace((unsigned char)s[p])) p++;
+  }
+  bool skip_misc() {  // comments, declarations, processing instructions
+    for (;;) {
+      skip_ws();
+      if (s.compare(p, 4, "<!--") == 0) {
+        size_t e = s.find("-->", p);
+        if (e == std::string::npos) return false;
+        p = e + 3;
+      } else if (s.compare(p, 2, "<?") == 0) {
+        size_t e = s.find("?>", p);
+        if (e == std::string::npos) return false;
+        p = e + 2;
+      } else if (s.compare(p, 2, "<!") == 0) {
+        size_t e = s.find('>', p);
+        if (e == std::string::npos) return false;
+        p = e + 1;
+      } else {
+        return true;
+      }
+    }
+  }
+  std::unique_ptr<XmlNode> element() {
+    if (!skip_misc() || p >= s.size() || s[p] != '<') {
+      err = "expected element";
+      return nullptr;
+    }
+    p++;
+    auto n = std::make_unique<XmlNode>();
+    while (p < s.size() && !std::isspace((unsigned char)s[p]) && s[p] != '>' && s[p] != '/') n->tag += s[p++];
+    for (;;) {
+      skip_ws();
+      if (p >= s.size()) {
+        err = "unterminated tag";
+        return nullptr;
+      }
+      if (s[p] == '/') {
+        p += 2;
+        return n;
+      }
+      if (s[p] == '>') {
+        p++;
+        break;
+      }
+      std::string key, val;
+      while (p < s.size() && s[p] != '=' && !std::isspace((unsigned char)s[p])) key += s[p++];
+      skip_ws();
+      if (p >= s.size() || s[p] != '=') {
+        err = "malformed attribute";
+        return nullptr;
+      }
+      p++;
+      skip_ws();
+      char q = s[p++];
+      while (p < s.size() && s[p] != q) val += s[p++];
+      p++;
+      n->attr[key] = val;
+    }
+    for (;;) {
+      size_t lt = s.find('<', p);
+      if (lt == std::string::npos) {
+        err = "missing closing tag for " + n->tag;
+        return nullptr;
+      }
+      n->text += s.substr(p, lt - p);
+      p = lt;
+      if (s.compare(p, 2, "</") == 0) {
+        size_t e = s.find('>', p);
+        p = e + 1;
+        return n;
+      }
+      if (s.compare(p, 4, "<!--") == 0) {
+        size_t e = s.find("-->", p);
+        p = e + 3;
+        continue;
+      }
+      auto k = element();
+      if (!k) return nullptr;
+      n->kids.push_back(std::move(k));
+    }
+  }
+};
+
+std::vector<double> parse_numbers(const std::string& txt) {
+  std::vector<double> out;
+  std::string t(txt);
+  for (char& c : t)
+    if (c == ',' || c == ';') c = ' ';
+    else if (c == 'd' || c == 'D') c = 'e';  // Fortran exponents
+  std::istringstream is(t);
+  double v;
+  while (is >> v) out.push_back(v);
+  return out;
+}
+bool parse_bool(const std::string& v) {
+  std::string t;
+  for (char c : v)
+    if (!std::isspace((unsigned char)c)) t += (char)std::tolower((unsigned char)c);
+  return t == "1" || t == "t" || t == "true" || t == ".true." || t == "yes";
+}
+}  // namespace
+
+std::unique_ptr<XmlNode> xml_parse_file(const std::string& path, std::string& err) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) {
+    err = "XML file does not exist";
+    return nullptr;
+  }
+  std::stringstream ss;
+  ss << f.rdbuf();
+  std::string src = ss.str();
+  XmlParser ps(src);
+  auto root = ps.element();
+  if (!root) err = "XML parse error: " + ps.err;
+  return root;
+}
+
+std::string Model::load_coils_xml(const XmlNode* group, const char* prefix, std::vector<CoilSet>& out) {
+  // <coil_set name= res_per_len= radius= sens_mask=> <coil scale= npts= path= ...>R, Z | x y z ...</coil>
+  // semantics of tw_load_coils (thin_wall.F90:2353-2566)
+  int iset = 0;
+  for (const XmlNode* cs : group->children("coil_set")) {
+    iset++;
+    CoilSet set;
+    char nm[64];
+    std::snprintf(nm, sizeof nm, "%s_%05d", prefix, iset);
+    set.name = cs->attr.count("name") ? cs->attr.at("name") : std::string(nm);
+    double set_rpl = -1.0, set_rad = -1.0;
+    if (cs->attr.count("res_per_len")) set_rpl = parse_numbers(cs->attr.at("res_per_len")).at(0);
+    if (cs->attr.count("radius")) set_rad = parse_numbers(cs->attr.at("radius")).at(0);
+    if (cs->attr.count("sens_mask")) set.sens_mask = parse_bool(cs->attr.at("sens_mask"));
+    for (const XmlNode* c : cs->children("coil")) {
+      Filament f;
+      f.res_per_len = set_rpl;
+      f.radius = set_rad;
+      if (c->attr.count("path")) {
+        const std::string& pth = c->attr.at("path");
+        size_t k = pth.find(':');
+        if (k == std::string::npos) return "Misformatted \"path\" attribute in coil";
+        std::vector<uint64_t> shape;
+        std::string e = read_h5_dataset_f64(pth.substr(0, k), pth.substr(k + 1), f.pts, shape);
+        if (!e.empty()) return "Failed to read HDF5 data for coil: " + e;
+        if (shape.size() != 2 || shape[1] != 3) return "Incorrect first dimension of HDF5 dataset for coil";
+      } else {
+        std::vector<double> v = parse_numbers(c->text);
+        if (c->attr.count("npts")) {
+          int npts = (int)parse_numbers(c->attr.at("npts")).at(0);
+          if ((int)v.size() != 3 * npts) return "Incorrect second dimension of coil points in coil";
+          f.pts = v;
+        } else {
+          if (v.size() != 2) return "Incorrect size of pts in RZ coil";
+          const int npts = 181;  // default circular discretisation (:2499-2504)
+          f.pts.resize(3 * npts);
+          for (int k = 0; k < npts; k++) {
+            double theta = k * 2.0 * kPi / (double)(npts - 1);
+            f.pts[3 * k] = v[0] * std::cos(theta);
+            f.pts[3 * k + 1] = v[0] * std::sin(theta);
+            f.pts[3 * k + 2] = v[1];
+          }
+        }
+      }
+      if (c->attr.count("scale")) f.scale = parse_numbers(c->attr.at("scale")).at(0);
+      if (c->attr.count("res_per_len")) f.res_per_len = parse_numbers(c->attr.at("res_per_len")).at(0);
+      if (c->attr.count("radius")) f.radius = parse_numbers(c->attr.at("radius")).at(0);
+      set.coils.push_back(std::move(f));
+    }
+    if (set.coils.empty()) continue;
+    out.push_back(std::move(set));
+  }
+  return "";
+}
+
+std::string Model::load_eta_xml(const XmlNode* tc) {
+  // tw_load_eta (thin_wall.F90:2821-2944); resistivities are stored divided by mu0
+  bool has_s = false, has_v = false, has_t = false;
+  const XmlNode* n = tc->child("eta");
+  if (!n) n = tc->child("eta_surf");
+  if (n) {
+    auto v = parse_numbers(n->text);
+    if ((int)v.size() != nreg) return "Eta size mismatch";
+    for (int i = 0; i < nreg; i++) {
+      if (v[i] <= 0.0) return "All \"eta\" values must be > 0";
+      eta_surf[i] = v[i] / kMu0;
+    }
+    has_s = true;
+  }
+  if ((n = tc->child("eta_vol"))) {
+    auto v = parse_numbers(n->text);
+    if ((int)v.size() != nreg) return "Eta_vol size mismatch";
+    for (int i = 0; i < nreg; i++) eta_vol[i] = v[i] / kMu0;
+    has_v = true;
+  }
+  if ((n = tc->child("thickness"))) {
+    auto v = parse_numbers(n->text);
+    if ((int)v.size() != nreg) return "Thickness size mismatch";
+    for (int i = 0; i < nreg; i++) thickness[i] = v[i];
+    has_t = true;
+  }
+  if (has_s) {
+    if (has_v && has_t)
+      for (int i = 0; i < nreg; i++) eta_surf[i] = eta_vol[i] / thickness[i];
+    else if (!has_v && has_t)
+      for (int i = 0; i < nreg; i++) eta_vol[i] = eta_surf[i] * thickness[i];
+  } else if (has_v && has_t) {
+    for (int i = 0; i < nreg; i++) eta_surf[i] = eta_vol[i] / thickness[i];
+  }
+  if ((n = tc->child("sens_mask"))) {
+    std::istringstream is(n->text);
+    std::string tok;
+    std::vector<int> m;
+    std::string t(n->text);
+    for (char& c : t)
+      if (c == ',') c = ' ';
+    std::istringstream is2(t);
+    while (is2 >> tok) m.push_back(parse_bool(tok) ? 1 : 0);
+    if ((int)m.size() != nreg) return "Sensor mask size mismatch";
+    sens_mask = m;
+  }
+  return "";
+}
+
+// ------------------------------------------------------------------ minimal HDF5 reader
+namespace {
+struct H5File {
+  std::vector<uint8_t> b;
+  std::string err;
+  template <class T>
+  T rd(size_t off) const {
+    T v;
+    if (off + sizeof(T) > b.size()) return T(0);
+    std::memcpy(&v, &b[off], sizeof(T));
+    return v;
+  }
+  struct Msg {
+    uint16_t type;
+    size_t off, size;
+  };
+  bool open(const std::string& path) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) {
+      err = "file does not exist or is not accessible";
+      return false;
+    }
+    std::fseek(f, 0, SEEK_END);
+    long n = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    b.resize((size_t)n);
+    size_t got = std::fread(b.data(), 1, (size_t)n, f);
+    std::fclose(f);
+    static const uint8_t sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+    if (got != (size_t)n || n < 96 || std::memcmp(b.data(), sig, 8) != 0) {
+      err = "not an HDF5 file";
+      return false;
+    }
+    if (b[8] != 0 || b[13] != 8 || b[14] != 8) {
+      err = "unsupported HDF5 superblock (need version 0, 8-byte offsets)";
+      return false;
+    }
+    return true;
+  }
+  uint64_t root_header() const { return rd<uint64_t>(56 + 8); }
+  std::vector<Msg> messages(uint64_t addr) const {
+    std::vector<Msg> out;
+    if (rd<uint8_t>(addr) != 1) return out;
+    uint16_t nmsg = rd<uint16_t>(addr + 2);
+    uint32_t hsize = rd<uint32_t>(addr + 8);
+    std::vector<std::pair<size_t, size_t>> blocks{{addr + 16, hsize}};
+    for (size_t bi = 0; bi < blocks.size() && out.size() < nmsg; bi++) {
+      size_t p = blocks[bi].first, end = p + blocks[bi].second;
+      while (p + 8 <= end && out.size() < nmsg) {
+        uint16_t t = rd<uint16_t>(p), ms = rd<uint16_t>(p + 2);
+        if (t == 0x10) blocks.emplace_back(rd<uint64_t>(p + 8), rd<uint64_t>(p + 16));
+        out.push_back({t, p + 8, ms});
+        p += 8 + ms;
+      }
+    }
+    return out;
+  }
+  void walk(uint64_t bt, uint64_t heap_data, std::map<std::string, uint64_t>& out) const {
+    if (std::memcmp(&b[bt], "TREE", 4) != 0) return;
+    uint8_t level = rd<uint8_t>(bt + 5);
+    uint16_t used = rd<uint16_t>(bt + 6);
+    size_t p = bt + 8 + 16;
+    for (int i = 0; i < used; i++) {
+      p += 8;
+      uint64_t child = rd<uint64_t>(p);
+      p += 8;
+      if (level > 0) {
+        walk(child, heap_data, out);
+      } else if (std::memcmp(&b[child], "SNOD", 4) == 0) {
+        uint16_t n = rd<uint16_t>(child + 6);
+        for (int k = 0; k < n; k++) {
+          size_t e = child + 8 + 40 * (size_t)k;
+          uint64_t name_off = rd<uint64_t>(e), ohdr = rd<uint64_t>(e + 8);
+          out[std::string((const char*)&b[heap_data + name_off])] = ohdr;
+        }
+      }
+    }
+  }
+  bool group(uint64_t ohdr, std::map<std::string, uint64_t>& out) const {
+    for (auto& m : messages(ohdr))
+      if (m.type == 0x11) {
+        uint64_t bt = rd<uint64_t>(m.off), heap = rd<uint64_t>(m.off + 8);
+        if (std::memcmp(&b[heap], "HEAP", 4) != 0) return false;
+        walk(bt, rd<uint64_t>(heap + 24), out);
+        return true;
+      }
+    return false;
+  }
+  bool find(const std::string& path, uint64_t& ohdr) const {
+    ohdr = root_header();
+    size_t p = 0;
+    while (p < path.size()) {
+      size_t q = path.find('/', p);
+      std::string part = path.substr(p, q == std::string::npos ? std::string::npos : q - p);
+      p = (q == std::string::npos) ? path.size() : q + 1;
+      if (part.empty()) continue;
+      std::map<std::string, uint64_t> g;
+      if (!group(ohdr, g) || !g.count(part)) return false;
+      ohdr = g[part];
+    }
+    return true;
+  }
+  // read a dataset as double or int32 (converted from stored int/float of size 4/8)
+  template <class T>
+  bool dataset(uint64_t ohdr, std::vector<T>& out, std::vector<uint64_t>& shape) {
+    int cls = -1, size = 0;
+    uint64_t addr = ~0ull;
+    shape.clear();
+    for (auto& m : messages(ohdr)) {
+      if (m.type == 1) {
+        uint8_t ver = b[m.off], rank = b[m.off + 1];
+        size_t o = m.off + (ver == 1 ? 8 : 4);
+        for (int k = 0; k < rank; k++) shape.push_back(rd<uint64_t>(o + 8 * k));
+      } else if (m.type == 3) {
+        cls = b[m.off] & 0xf;
+        size = (int)rd<uint32_t>(m.off + 4);
+      } else if (m.type == 8) {
+        uint8_t ver = b[m.off];
+        if (ver == 3) {
+          if (b[m.off + 1] != 1) {
+            err = "only contiguous datasets are supported";
+            return false;
+          }
+          addr = rd<uint64_t>(m.off + 2);
+        } else {
+          if (b[m.off + 2] != 1) {
+            err = "only contiguous datasets are supported";
+            return false;
+          }
+          addr = rd<uint64_t>(m.off + 8);
+        }
+      }
+    }
+    if (cls < 0 || addr == ~0ull) {
+      err = "dataset header incomplete";
+      return false;
+    }
+    uint64_t n = 1;
+    for (auto s : shape) n *= s;
+    if (addr + n * size > b.size()) {
+      err = "dataset extends past end of file";
+      return false;
+    }
+    out.resize(n);
+    for (uint64_t i = 0; i < n; i++) {
+      size_t o = addr + i * size;
+      if (cls == 1)
+        out[i] = (T)(size == 8 ? rd<double>(o) : (double)rd<float>(o));
+      else
+        out[i] = (T)(size == 8 ? rd<int64_t>(o) : (size == 4 ? (int64_t)rd<int32_t>(o) : (int64_t)rd<int16_t>(o)));
+    }
+    return true;
+  }
+};
+}  // namespace
+
+std::string read_h5_dataset_f64(const std::string& path, const std::string& name, std::vector<double>& out,
+                                std::vector<uint64_t>& shape) {
+  H5File f;
+  if (!f.open(path)) return f.err;
+  uint64_t oh;
+  if (!f.find(name, oh)) return "dataset \"" + name + "\" not found";
+  if (!f.dataset(oh, out, shape)) return f.err;
+  return "";
+}
+
+std::string read_native_mesh(const std::string& path, NativeMesh& out) {
+  H5File f;
+  if (!f.open(path)) return "Mesh file does not exist or is not accesible";
+  uint64_t oh;
+  std::vector<uint64_t> shape;
+  if (!f.find("mesh/R", oh)) return "Point list (\"mesh/R\") not present in mesh file";
+  std::vector<double> rr;
+  if (!f.dataset(oh, rr, shape) || shape.size() != 2) return "Error reading point list from mesh file";
+  out.np = (int)shape[0];
+  int ndim = (int)shape[1];
+  out.r.assign(3 * (size_t)out.np, 0.0);  // 2-D lists are zero padded (thincurr_f.F90:127-136)
+  for (int i = 0; i < out.np; i++)
+    for (int d = 0; d < ndim && d < 3; d++) out.r[3 * (size_t)i + d] = rr[(size_t)i * ndim + d];
+  if (!f.find("mesh/LC", oh)) return "Cell list (\"mesh/LC\") not present in mesh file";
+  if (!f.dataset(oh, out.lc, shape) || shape.size() != 2 || shape[1] != 3) return "Error reading cell list from mesh file";
+  out.nc = (int)shape[0];
+  if (f.find("mesh/REG", oh)) {
+    if (!f.dataset(oh, out.reg, shape)) return "Error reading region ID from mesh file";
+  } else {
+    out.reg.assign(out.nc, 1);
+  }
+  if (f.find("thincurr/periodicity/pmap", oh)) {
+    if (!f.dataset(oh, out.pmap, shape)) return "Error reading periodicity information from mesh file";
+  }
+  for (int kind = 0; kind < 2; kind++) {
+    auto& sets = kind == 0 ? out.nodesets : out.sidesets;
+    for (int k = 1;; k++) {
+      char nm[64];
+      std::snprintf(nm, sizeof nm, "mesh/%s%04d", kind == 0 ? "NODESET" : "SIDESET", k);
+      if (!f.find(nm, oh)) break;
+      std::vector<int> v;
+      if (!f.dataset(oh, v, shape)) return std::string("Error reading ") + nm;
+      sets.push_back(v);
+    }
+  }
+  return "";
+}
+
+// ------------------------------------------------------------------ floops.loc
+std::string read_floops(const std::string& path, Sensors& out) {
+  // count; per loop: blank line, "npts scale name", npts lines "x y z"
+  // (tw_load_sensors, thin_wall.F90:2599-2619; comment lines start with '#')
+  out.floops.clear();
+  std::ifstream f(path);
+  if (!f) return "";  // a missing file means "no flux loops" in the reference (:2601-2602)
+  std::string line;
+  auto next = [&](std::string& l) -> bool {
+    while (std::getline(f, l)) {
+      size_t a = l.find_first_not_of(" \t\r");
+      if (a == std::string::npos) continue;
+      if (l[a] == '#') continue;
+      return true;
+    }
+    return false;
+  };
+  if (!next(line)) return "Error reading sensor file";
+  int n = std::atoi(line.c_str());
+  for (int i = 0; i < n; i++) {
+    if (!next(line)) return "Error reading sensor file";
+    std::istringstream is(line);
+    int npts;
+    FluxLoop fl;
+    if (!(is >> npts >> fl.scale_fac >> fl.name)) return "Error reading sensor header";
+    fl.pts.resize(3 * (size_t)npts);
+    for (int k = 0; k < npts; k++) {
+      if (!next(line)) return "Error reading sensor points";
+      for (char& c : line)
+        if (c == ',') c = ' ';
+      std::istringstream ps(line);
+      if (!(ps >> fl.pts[3 * k] >> fl.pts[3 * k + 1] >> fl.pts[3 * k + 2])) return "Error reading sensor points";
+    }
+    out.floops.push_back(std::move(fl));
+  }
+  return "";
+}
+
+// ------------------------------------------------------------------ Fortran unformatted records
+// gfortran sequential framing: int32 byte count before and after each record; records longer
+// than 2^31-9 bytes are split into sub-records whose markers carry a negative length when a
+// continuation follows/precedes.
+static const int64_t kMaxSub = 2147483639;
+
+bool funf_write_record(FILE* f, const void* data, size_t bytes) {
+  const char* p = (const char*)data;
+  size_t left = bytes;
+  bool first = true;
+  do {
+    int64_t n = (int64_t)std::min<size_t>(left, (size_t)kMaxSub);
+    bool more = left > (size_t)n;
+    int32_t head = (int32_t)(more ? -n : n), tail = (int32_t)(first ? n : -n);
+    if (std::fwrite(&head, 4, 1, f) != 1) return false;
+    if (n && std::fwrite(p, 1, (size_t)n, f) != (size_t)n) return false;
+    if (std::fwrite(&tail, 4, 1, f) != 1) return false;
+    p += n;
+    left -= (size_t)n;
+    first = false;
+  } while (left > 0);
+  return true;
+}
+
+bool funf_read_record(FILE* f, void* data, size_t bytes) {
+  char* p = (char*)data;
+  size_t got = 0;
+  for (;;) {
+    int32_t head, tail;
+    if (std::fread(&head, 4, 1, f) != 1) return false;
+    size_t n = (size_t)std::llabs((long long)head);
+    if (got + n > bytes) return false;
+    if (n && std::fread(p + got, 1, n, f) != n) return false;
+    if (std::fread(&tail, 4, 1, f) != 1) return false;
+    got += n;
+    if (head >= 0) break;
+  }
+  return got == bytes;
+}
+
+}  // namespace tw

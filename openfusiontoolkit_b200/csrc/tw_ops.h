@@ -1,0 +1,46 @@
+// tw_ops.h -- operator-level entry points implemented in tw_capi.cu / tw_ops.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "tw_gpu.h"
+
+namespace tw {
+
+int visible_devices();
+std::string ensure_plan(Model& m);
+std::string ensure_device(Model& m, int device, std::shared_ptr<DeviceState>& out);
+void drop_device_state(Model& m);
+void shard_rows(const Model& m, int nshards, int shard, int& p0, int& p1, std::vector<int>& row_ids);
+std::string lmat_shard_device(Model& m, int nshards, int shard, double* d_out, long long ld, cudaStream_t stream,
+                              unsigned long long* stats);
+
+// V-coil rows/columns of L from Ael2coil / Acoil2coil (thin_wall.F90:1128-1145), scaled by 1/4pi
+std::string gpu_fill_vcoil_block(const Model& m, const std::vector<int>& row_ids, double* d_out, long long ld,
+                                 cudaStream_t stream);
+// element<->coil and coil<->coil mutuals (tw_compute_Ael2dr + tw_compute_Lmat_coils, :567-883)
+std::string gpu_mcoil(Model& m);
+// element->sensor and coil->sensor mutuals (tw_compute_mutuals, :1418-1686)
+std::string gpu_msensor(Model& m, const Sensors& sens);
+// B-field reconstruction operators (tw_compute_Bops, :1989-2169)
+std::string gpu_bmat(Model& m);
+std::string bel_shard_device(Model& m, int nshards, int shard, double* d_out, cudaStream_t stream);
+// mutual inductance between two models (tw_compute_LmatDirect with col_model, :887-1186)
+std::string gpu_cross_coupling(Model& m1, Model& m2, double* Mmat_host);
+// iquad histogram + visited-pair count of the reference loop nest
+std::string gpu_pair_stats(Model& m, int64_t* hist, int64_t* visited);
+
+// operator caches in the reference's on-disk formats (Fortran unformatted sequential)
+bool lmat_cache_read(Model& m, const std::string& path);
+void lmat_cache_write(const Model& m, const std::string& path);
+bool mutual_cache_read(const Model& m1, const Model& m2, double* M, const std::string& path);
+void mutual_cache_write(const Model& m1, const Model& m2, const double* M, const std::string& path);
+bool mcoil_cache_read(Model& m, const std::string& path);
+void mcoil_cache_write(const Model& m, const std::string& path);
+bool msensor_cache_read(Model& m, int nsensors, const std::string& path);
+void msensor_cache_write(const Model& m, int nsensors, const std::string& path);
+
+}  // namespace tw

@@ -1,0 +1,290 @@
+// tw_plan.cpp -- patch / chunk / tile construction (see tw_plan.h).
+#include "tw_plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace tw {
+
+namespace {
+// kd-order of points: recursive median split along the longest bounding-box axis.  Leaves of
+// size <= P become patches; recursion continues below that only to order DOFs inside a patch.
+void rcb(std::vector<int>& idx, int lo, int hi, const std::vector<double>& xyz, int P, std::vector<int>& cuts,
+         bool emitted) {
+  int n = hi - lo;
+  if (!emitted && n <= P) {
+    cuts.push_back(lo);
+    emitted = true;
+  }
+  if (n <= 4) return;
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int i = lo; i < hi; i++)
+    for (int d = 0; d < 3; d++) {
+      double v = xyz[3 * (size_t)idx[i] + d];
+      mn[d] = std::min(mn[d], v);
+      mx[d] = std::max(mx[d], v);
+    }
+  int ax = 0;
+  for (int d = 1; d < 3; d++)
+    if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
+  int mid = lo + n / 2;
+  std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) {
+    double va = xyz[3 * (size_t)a + ax], vb = xyz[3 * (size_t)b + ax];
+    return va < vb || (va == vb && a < b);
+  });
+  rcb(idx, lo, mid, xyz, P, cuts, emitted);
+  rcb(idx, mid, hi, xyz, P, cuts, emitted);
+}
+}  // namespace
+
+std::string build_patches(const Model& m, int P, PatchSet& ps) {
+  const int nv = m.np_active, nh = m.nholes;
+  ps = PatchSet();
+  ps.ndof = nv + nh;
+  if (P <= 0) {
+    // enough tiles to fill 148 SMs several times over, patches as large as possible otherwise
+    P = 256;
+    while (P > 32 && (double)(nv / P) * (nv / P) / 2.0 < 2000.0) P /= 2;
+  }
+  // dof -> vertices (periodic meshes map several vertices to one DOF)
+  std::vector<int> kdv(nv + 1, 0), ldv;
+  for (int v = 0; v < m.np; v++)
+    if (m.pmap[v] > 0) kdv[m.pmap[v]]++;
+  for (int i = 0; i < nv; i++) kdv[i + 1] += kdv[i];
+  ldv.resize(kdv[nv]);
+  {
+    std::vector<int> fill(kdv.begin(), kdv.end() - 1);
+    for (int v = 0; v < m.np; v++)
+      if (m.pmap[v] > 0) ldv[fill[m.pmap[v] - 1]++] = v;
+  }
+  for (int d = 0; d < nv; d++)
+    if (kdv[d + 1] == kdv[d]) return "Invalid periodicity map (unused DOF id)";
+  std::vector<double> xyz(3 * (size_t)std::max(nv, 1));
+  for (int d = 0; d < nv; d++)
+    for (int k = 0; k < 3; k++) xyz[3 * (size_t)d + k] = m.r[3 * (size_t)ldv[kdv[d]] + k];
+  std::vector<int> idx(nv), cuts;
+  std::iota(idx.begin(), idx.end(), 0);
+  if (nv > 0) rcb(idx, 0, nv, xyz, P, cuts, false);
+  cuts.push_back(nv);
+  ps.nvert_patch = (int)cuts.size() - 1;
+  ps.npatch = ps.nvert_patch + nh;
+  ps.dof_orig.resize(ps.ndof);
+  ps.patch_dof_ptr.assign(1, 0);
+  for (int p = 0; p < ps.nvert_patch; p++) {
+    for (int i = cuts[p]; i < cuts[p + 1]; i++) ps.dof_orig[i] = idx[i];
+    ps.patch_dof_ptr.push_back(cuts[p + 1]);
+  }
+  for (int h = 0; h < nh; h++) {
+    ps.dof_orig[nv + h] = nv + h;
+    ps.patch_dof_ptr.push_back(nv + h + 1);
+  }
+  // hole incidences grouped per hole, in cell order
+  std::vector<std::vector<std::pair<int, int>>> hole_inc(nh);  // (cell, k | neg<<2)
+  for (int c = 0; c < m.nc; c++)
+    for (int ii = m.kfh[c]; ii < m.kfh[c + 1]; ii++) {
+      int h = m.lfh[2 * ii];
+      hole_inc[std::abs(h) - 1].emplace_back(c, m.lfh[2 * ii + 1] | (h < 0 ? 4 : 0));
+    }
+  ps.patch_chunk_ptr.assign(1, 0);
+  ps.patch_ncell.clear();
+  std::vector<int> cell_slot(m.nc, -1);
+  struct Inc {
+    int dof_local, cell_slot, code;
+  };
+  std::vector<Inc> incs;
+  std::vector<int> cells;
+  for (int p = 0; p < ps.npatch; p++) {
+    incs.clear();
+    cells.clear();
+    int d0 = ps.patch_dof_ptr[p], d1 = ps.patch_dof_ptr[p + 1];
+    auto add = [&](int dl, int c, int code) {
+      if (cell_slot[c] < 0) {
+        cell_slot[c] = (int)cells.size();
+        cells.push_back(c);
+      }
+      incs.push_back({dl, cell_slot[c], code});
+    };
+    if (p < ps.nvert_patch) {
+      for (int di = d0; di < d1; di++) {
+        int d = ps.dof_orig[di];
+        for (int kv = kdv[d]; kv < kdv[d + 1]; kv++) {
+          int v = ldv[kv];
+          for (int j = m.kpc[v]; j < m.kpc[v + 1]; j++) {
+            int c = m.lpc[j], k = 0;
+            while (k < 3 && m.lc[3 * c + k] != v) k++;
+            add(di - d0, c, k);
+          }
+        }
+      }
+    } else {
+      for (auto& e : hole_inc[p - ps.nvert_patch]) add(0, e.first, e.second);
+    }
+    int ncell = (int)cells.size();
+    ps.patch_ncell.push_back(ncell);
+    int nch = (ncell + kCH - 1) / kCH;
+    // bucket incidences by chunk, keeping (dof, cell) order
+    std::vector<std::vector<Inc>> by_chunk(nch);
+    for (auto& e : incs) by_chunk[e.cell_slot / kCH].push_back(e);
+    for (int ch = 0; ch < nch; ch++) {
+      int chunk_id = (int)ps.chunks.size();
+      ChunkMeta cm;
+      cm.ncell = std::min(kCH, ncell - ch * kCH);
+      cm.dof_off = (int)ps.chunk_dof.size();
+      cm.inc_off = (int)ps.inc.size();
+      size_t g0 = ps.geom.size();
+      ps.geom.resize(g0 + (size_t)kGeomRows * kCH, 0.0);
+      ps.cell_dmin.resize(ps.cell_dmin.size() + kCH, 0x7fffffff);
+      ps.cell_dmax.resize(ps.cell_dmax.size() + kCH, -1);
+      ps.cell_ids.resize(ps.cell_ids.size() + kCH, -1);
+      for (int s = 0; s < cm.ncell; s++) {
+        int c = cells[ch * kCH + s];
+        ps.cell_ids[(size_t)chunk_id * kCH + s] = c;
+        for (int k = 0; k < 3; k++)
+          for (int d = 0; d < 3; d++) {
+            ps.geom[g0 + (size_t)(k * 3 + d) * kCH + s] = m.r[3 * (size_t)m.lc[3 * c + k] + d];
+            ps.geom[g0 + (size_t)(10 + k * 3 + d) * kCH + s] = m.qbasis[9 * (size_t)c + 3 * k + d];
+          }
+        ps.geom[g0 + (size_t)9 * kCH + s] = m.ca[c];
+        for (int d = 0; d < 3; d++) ps.geom[g0 + (size_t)(19 + d) * kCH + s] = m.norm[3 * (size_t)c + d];
+      }
+      auto& L = by_chunk[ch];
+      std::stable_sort(L.begin(), L.end(), [](const Inc& a, const Inc& b) { return a.dof_local < b.dof_local; });
+      std::vector<int> ptr;
+      int prev = -1;
+      for (size_t k = 0; k < L.size(); k++) {
+        if (L[k].dof_local != prev) {
+          ps.chunk_dof.push_back(d0 + L[k].dof_local);
+          ptr.push_back((int)k);
+          prev = L[k].dof_local;
+        }
+        int s = L[k].cell_slot - ch * kCH;
+        ps.inc.push_back((uint16_t)(s | ((L[k].code & 3) << 6) | ((L[k].code & 4) ? 256 : 0)));
+        int od = ps.dof_orig[d0 + L[k].dof_local];
+        int& mn = ps.cell_dmin[(size_t)chunk_id * kCH + s];
+        int& mx = ps.cell_dmax[(size_t)chunk_id * kCH + s];
+        mn = std::min(mn, od);
+        mx = std::max(mx, od);
+      }
+      ptr.push_back((int)L.size());
+      cm.ndof = (int)ptr.size() - 1;
+      if (cm.ndof > kMaxChunkDof || (int)L.size() > kMaxChunkInc) return "Internal error: chunk incidence overflow";
+      // inc_ptr for chunk i lives at [dof_off + chunk_id, dof_off + chunk_id + ndof]
+      for (int v : ptr) ps.chunk_inc_ptr.push_back(v);
+      ps.chunks.push_back(cm);
+    }
+    ps.patch_chunk_ptr.push_back((int)ps.chunks.size());
+    for (int c : cells) cell_slot[c] = -1;
+  }
+  ps.nchunk = (int)ps.chunks.size();
+  return "";
+}
+
+void shard_range(const PatchSet& ps, int nshards, int shard, int& p0, int& p1) {
+  // contiguous patch ranges with (nearly) equal numbers of row cells: the work of a row patch
+  // is ncell(patch) x (all column cells)
+  double total = 0;
+  for (int n : ps.patch_ncell) total += n;
+  auto cut = [&](int s) {
+    if (s <= 0) return 0;
+    if (s >= nshards) return ps.npatch;
+    double target = total * s / nshards, acc = 0;
+    for (int p = 0; p < ps.npatch; p++) {
+      if (acc + 0.5 * ps.patch_ncell[p] >= target) return p;
+      acc += ps.patch_ncell[p];
+    }
+    return ps.npatch;
+  };
+  p0 = cut(shard);
+  p1 = cut(shard + 1);
+}
+
+namespace {
+struct Ball {
+  double c[3], r;
+};
+std::vector<Ball> patch_balls(const PatchSet& ps) {
+  std::vector<Ball> out(ps.npatch);
+  for (int p = 0; p < ps.npatch; p++) {
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int ch = ps.patch_chunk_ptr[p]; ch < ps.patch_chunk_ptr[p + 1]; ch++)
+      for (int s = 0; s < ps.chunks[ch].ncell; s++)
+        for (int k = 0; k < 3; k++)
+          for (int d = 0; d < 3; d++) {
+            double v = ps.geom[((size_t)ch * kGeomRows + k * 3 + d) * kCH + s];
+            mn[d] = std::min(mn[d], v);
+            mx[d] = std::max(mx[d], v);
+          }
+    Ball b;
+    double r2 = 0;
+    for (int d = 0; d < 3; d++) {
+      b.c[d] = 0.5 * (mn[d] + mx[d]);
+      r2 += 0.25 * (mx[d] - mn[d]) * (mx[d] - mn[d]);
+    }
+    b.r = std::sqrt(r2);
+    out[p] = b;
+  }
+  return out;
+}
+double mean_cell_size(const PatchSet& ps) {
+  double a = 0;
+  long n = 0;
+  for (int ch = 0; ch < ps.nchunk; ch++)
+    for (int s = 0; s < ps.chunks[ch].ncell; s++) {
+      a += ps.geom[((size_t)ch * kGeomRows + 9) * kCH + s];
+      n++;
+    }
+  return n ? std::sqrt(2.0 * a / n) : 1.0;
+}
+float tile_cost(const PatchSet& A, const PatchSet& B, const std::vector<Ball>& ba, const std::vector<Ball>& bb, int pa,
+                int pb, double h) {
+  double d = 0;
+  for (int k = 0; k < 3; k++) d += (ba[pa].c[k] - bb[pb].c[k]) * (ba[pa].c[k] - bb[pb].c[k]);
+  d = std::sqrt(d) - ba[pa].r - bb[pb].r;
+  double pairs = (double)A.patch_ncell[pa] * B.patch_ncell[pb];
+  double w = d < 11.0 * h ? 40.0 : (d < 45.0 * h ? 3.0 : 1.0);  // near field / high-order far field / plain
+  return (float)(pairs * w);
+}
+}  // namespace
+
+void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles) {
+  tiles.clear();
+  auto balls = patch_balls(ps);
+  double h = mean_cell_size(ps);
+  std::vector<int> omin(ps.npatch, 0x7fffffff), omax(ps.npatch, -1);
+  for (int p = 0; p < ps.npatch; p++)
+    for (int i = ps.patch_dof_ptr[p]; i < ps.patch_dof_ptr[p + 1]; i++) {
+      omin[p] = std::min(omin[p], ps.dof_orig[i]);
+      omax[p] = std::max(omax[p], ps.dof_orig[i]);
+    }
+  for (int pa = p0; pa < p1; pa++)
+    for (int pb = 0; pb < ps.npatch; pb++) {
+      bool owned = pb >= p0 && pb < p1;
+      if (owned && pb < pa) continue;  // produced by the mirror write of tile (pb,pa)
+      Tile t;
+      t.pa = pa;
+      t.pb = pb;
+      t.flags = 0;
+      if (pa == pb) t.flags |= 1;
+      else if (owned) t.flags |= 2;
+      if (pa != pb && omax[pa] > omin[pb]) t.flags |= 4;
+      t.cost = tile_cost(ps, ps, balls, balls, pa, pb, h) * ((t.flags & 1) ? 0.5f : 1.0f);
+      tiles.push_back(t);
+    }
+  std::stable_sort(tiles.begin(), tiles.end(), [](const Tile& a, const Tile& b) { return a.cost > b.cost; });
+}
+
+void build_mutual_tiles(const PatchSet& rows, const PatchSet& cols, std::vector<Tile>& tiles) {
+  tiles.clear();
+  auto ba = patch_balls(rows), bb = patch_balls(cols);
+  double h = std::max(mean_cell_size(rows), mean_cell_size(cols));
+  for (int pa = 0; pa < rows.npatch; pa++)
+    for (int pb = 0; pb < cols.npatch; pb++) {
+      Tile t{pa, pb, 0, tile_cost(rows, cols, ba, bb, pa, pb, h)};
+      tiles.push_back(t);
+    }
+  std::stable_sort(tiles.begin(), tiles.end(), [](const Tile& a, const Tile& b) { return a.cost > b.cost; });
+}
+
+}  // namespace tw

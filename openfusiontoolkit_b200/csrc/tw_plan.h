@@ -1,0 +1,68 @@
+// tw_plan.h -- owner-computes decomposition of the dense operator builds.
+//
+// DOFs (vertex + hole DOFs of thin_wall.F90:282-342) are grouped into spatially compact
+// PATCHES by recursive coordinate bisection; a patch owns its rows of L.  Every patch carries
+// the list of cells that touch any of its DOFs (a one-ring halo), cut into CHUNKS of <= kCH
+// cells whose geometry is stored SoA and contiguous in HBM so a CTA can stage a chunk in shared
+// memory with bulk copies.  An output TILE = (row patch, column patch) is owned by exactly one
+// CTA: it evaluates the pair integrals T(c1,c2) chunk pair by chunk pair into a shared-memory
+// tile and contracts them onto the 3x3 (+hole) vertex DOFs, so no atomics are ever needed.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "tw_host.h"
+
+namespace tw {
+
+constexpr int kCH = 64;        // cells per chunk
+constexpr int kMaxChunkDof = 3 * kCH;   // DOFs with incidences in one chunk
+constexpr int kMaxChunkInc = 4 * kCH;   // incidences in one chunk
+constexpr int kGeomRows = 24;  // doubles per cell in the SoA chunk record (0-8 verts, 9 area, 10-18 qbasis, 19-21 normal)
+
+struct ChunkMeta {
+  int ncell;    // valid cells in the chunk
+  int ndof;     // DOFs that have an incidence in this chunk
+  int dof_off;  // offset of this chunk's DOF list (chunk_dof / inc_ptr(+chunk id))
+  int inc_off;  // offset of this chunk's incidence list
+};
+
+// Patch decomposition of ONE model (row or column side).
+struct PatchSet {
+  int npatch = 0, nvert_patch = 0, nchunk = 0, ndof = 0;  // ndof = np_active + nholes
+  std::vector<int> patch_dof_ptr;    // [npatch+1] internal DOF index range per patch
+  std::vector<int> dof_orig;         // [ndof] internal index -> reference DOF id (0-based)
+  std::vector<int> patch_chunk_ptr;  // [npatch+1]
+  std::vector<int> patch_ncell;      // [npatch]
+  std::vector<ChunkMeta> chunks;     // [nchunk]
+  std::vector<double> geom;          // [nchunk][kGeomRows][kCH]
+  std::vector<int> cell_dmin, cell_dmax;  // [nchunk][kCH] min/max reference DOF id (in-patch incidences)
+  std::vector<int> chunk_dof;        // internal DOF index per (chunk, local dof)
+  std::vector<int> chunk_inc_ptr;    // per chunk: ndof+1 offsets (relative to inc_off), stored at dof_off+chunk
+  std::vector<uint16_t> inc;         // cell(6b) | local vertex(2b)<<6 | negative<<8
+  std::vector<int> cell_ids;         // [nchunk][kCH] reference cell id (debug / stats)
+};
+
+struct Tile {
+  int pa, pb;   // row patch, column patch
+  int flags;    // bit0: diagonal (pa==pb, only entries a<=b computed, mirrored)
+                // bit1: mirror-write the transposed entries (pb rows are owned too)
+                // bit2: second role (T with the column cell analytic) may be needed
+  float cost;
+};
+
+struct Plan {
+  int patch_size = 0;
+  PatchSet ps;
+};
+
+// Build the patch decomposition of a model; P = target DOFs per patch (0 = choose automatically)
+std::string build_patches(const Model& m, int P, PatchSet& out);
+// Contiguous patch range [p0,p1) of shard `shard` out of `nshards`, balanced by pair count
+void shard_range(const PatchSet& ps, int nshards, int shard, int& p0, int& p1);
+// Tiles of a self-inductance build for row patches [p0,p1)
+void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles);
+// Tiles of a mutual build (all row patches x all column patches)
+void build_mutual_tiles(const PatchSet& rows, const PatchSet& cols, std::vector<Tile>& tiles);
+
+}  // namespace tw
