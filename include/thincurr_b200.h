@@ -126,6 +126,15 @@ int thincurr_b200_pair_stats(void* tw_ptr, int64_t* hist, int64_t* visited);
 /* FP64 DFMA peak microbenchmark on the current device (TFLOP/s, FMA = 2 flops). */
 double thincurr_b200_dfma_peak(int device, double* sm_clock_mhz);
 
+/* Kernel-level probes for the parity tests: the device functions of the operator kernels on
+ * caller-given inputs.  probe_pairs: T(i,j) with cell i the analytic side when near, and the
+ * selected quadrature order (thin_wall.F90:1044-1083); Pi/Pj = [n][3][3] vertices, Ai/Aj areas.
+ * probe_phipot: tw_compute_phipot (thin_wall.F90:1934-1985) for tri[n][3][3], pt[n][3]. */
+int thincurr_b200_probe_pairs(int n, const double* Pi, const double* Ai, const double* Pj, const double* Aj,
+                              double* T, int* iquad);
+int thincurr_b200_probe_phipot(int n, const double* tri, const double* pt, double* out);
+int thincurr_b200_probe_rsqrt(int n, const double* x, double* y);
+
 /* Introspection for tests. */
 int thincurr_b200_get_model(void* tw_ptr, int* pmap, int* lc, int* kfh, int* lfh, double* qbasis, double* ca);
 int thincurr_b200_hashes(void* tw_ptr, int32_t* hash_lc, int32_t* hash_r);

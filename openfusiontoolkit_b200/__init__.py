@@ -6,6 +6,12 @@ build and the coil / sensor / B-field operators, behind the reference's ThinCurr
 compute_Rmat / cross_coupling`).  The compute path is hand-written CUDA for sm_100a reached
 through the C ABI in include/thincurr_b200.h; there is no CPU fallback.
 """
-from ._core import OFT_env  # noqa: F401
-
 __all__ = ['OFT_env']
+
+
+def __getattr__(name):
+    # lazy so that `python -m openfusiontoolkit_b200.build` can run before the library exists
+    if name == 'OFT_env':
+        from ._core import OFT_env
+        return OFT_env
+    raise AttributeError(name)

@@ -92,3 +92,8 @@ b200_dfma_peak = ctypes_subroutine(oftpy_lib.thincurr_b200_dfma_peak, [c_int, c_
 b200_get_model = ctypes_subroutine(oftpy_lib.thincurr_b200_get_model,
     [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int)
 b200_hashes = ctypes_subroutine(oftpy_lib.thincurr_b200_hashes, [c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)], c_int)
+_f64 = numpy.ctypeslib.ndpointer(dtype=numpy.float64, flags='C_CONTIGUOUS')
+_i32 = numpy.ctypeslib.ndpointer(dtype=numpy.int32, flags='C_CONTIGUOUS')
+b200_probe_pairs = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_pairs, [c_int, _f64, _f64, _f64, _f64, _f64, _i32], c_int)
+b200_probe_phipot = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_phipot, [c_int, _f64, _f64, _f64], c_int)
+b200_probe_rsqrt = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_rsqrt, [c_int, _f64, _f64], c_int)

@@ -75,57 +75,73 @@ __device__ __forceinline__ int iquad_fast(double d2min, double d2max) {
 }
 
 // ---- analytic potential of a triangle at a point -----------------------------------------
-// Operation-for-operation the reference formula (same conditioning near edge extensions).
+// The formula is ill-conditioned where the point lies near the extension of an edge
+// (den = |r_i||e| + r_i.e cancels), so rounding differences are amplified by up to ~1e6.  To
+// reproduce the reference's CPU result to 1e-10 the arithmetic is therefore done with
+// non-contracted IEEE operations (no FMA) in exactly the reference's operation order
+// (DOT_PRODUCT / cross_product / magnitude evaluate left to right, thin_wall.F90:1941-1983,
+// oft_local.F90:314-328); sqrt and division are IEEE-rounded, log/atan2 differ by <= 1-2 ulp.
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xdot(double a0, double a1, double a2, double b0, double b1, double b2) {
+  return xadd(xadd(xmul(a0, b0), xmul(a1, b1)), xmul(a2, b2));
+}
+// quadrature point b1*P1 + b2*P2 + b3*P3 as the reference evaluates it (thin_wall.F90:1064-1066)
+__device__ __forceinline__ double xquad(double b0, double b1, double b2, double p0, double p1, double p2) {
+  return xadd(xadd(xmul(b0, p0), xmul(b1, p1)), xmul(b2, p2));
+}
+
 __device__ __forceinline__ double phipot(const double* P /*[3][3]*/, const double* nhat, double x, double y, double z) {
   double r[3][3], rmag[3], c[3][3];
 #pragma unroll
   for (int i = 0; i < 3; i++) {
-    r[i][0] = P[3 * i] - x;
-    r[i][1] = P[3 * i + 1] - y;
-    r[i][2] = P[3 * i + 2] - z;
-    rmag[i] = sqrt(r[i][0] * r[i][0] + r[i][1] * r[i][1] + r[i][2] * r[i][2]);
-    double dn = nhat[0] * r[i][0] + nhat[1] * r[i][1] + nhat[2] * r[i][2];
-    c[i][0] = r[i][0] - dn * nhat[0];
-    c[i][1] = r[i][1] - dn * nhat[1];
-    c[i][2] = r[i][2] - dn * nhat[2];
+    r[i][0] = xsub(P[3 * i], x);
+    r[i][1] = xsub(P[3 * i + 1], y);
+    r[i][2] = xsub(P[3 * i + 2], z);
+    rmag[i] = __dsqrt_rn(xdot(r[i][0], r[i][1], r[i][2], r[i][0], r[i][1], r[i][2]));
+    double dn = xdot(nhat[0], nhat[1], nhat[2], r[i][0], r[i][1], r[i][2]);
+    c[i][0] = xsub(r[i][0], xmul(dn, nhat[0]));
+    c[i][1] = xsub(r[i][1], xmul(dn, nhat[1]));
+    c[i][2] = xsub(r[i][2], xmul(dn, nhat[2]));
   }
-  double cx = r[1][1] * r[2][2] - r[1][2] * r[2][1];
-  double cy = r[1][2] * r[2][0] - r[1][0] * r[2][2];
-  double cz = r[1][0] * r[2][1] - r[1][1] * r[2][0];
-  double num = r[0][0] * cx + r[0][1] * cy + r[0][2] * cz;
-  double d01 = r[0][0] * r[1][0] + r[0][1] * r[1][1] + r[0][2] * r[1][2];
-  double d02 = r[0][0] * r[2][0] + r[0][1] * r[2][1] + r[0][2] * r[2][2];
-  double d12 = r[1][0] * r[2][0] + r[1][1] * r[2][1] + r[1][2] * r[2][2];
-  double den = rmag[0] * rmag[1] * rmag[2] + d01 * rmag[2] + d02 * rmag[1] + d12 * rmag[0];
-  double omega = 2.0 * atan2(num, den);
+  double cx = xsub(xmul(r[1][1], r[2][2]), xmul(r[1][2], r[2][1]));
+  double cy = xsub(xmul(r[1][2], r[2][0]), xmul(r[1][0], r[2][2]));
+  double cz = xsub(xmul(r[1][0], r[2][1]), xmul(r[1][1], r[2][0]));
+  double num = xdot(r[0][0], r[0][1], r[0][2], cx, cy, cz);
+  double d01 = xdot(r[0][0], r[0][1], r[0][2], r[1][0], r[1][1], r[1][2]);
+  double d02 = xdot(r[0][0], r[0][1], r[0][2], r[2][0], r[2][1], r[2][2]);
+  double d12 = xdot(r[1][0], r[1][1], r[1][2], r[2][0], r[2][1], r[2][2]);
+  double den = xadd(xadd(xadd(xmul(xmul(rmag[0], rmag[1]), rmag[2]), xmul(d01, rmag[2])), xmul(d02, rmag[1])), xmul(d12, rmag[0]));
+  double omega = xmul(2.0, atan2(num, den));
   double phi = 0.0;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     const int j = (i + 1) % 3;
-    double dv0 = r[j][0] - r[i][0], dv1 = r[j][1] - r[i][1], dv2 = r[j][2] - r[i][2];
-    double tmp = sqrt(dv0 * dv0 + dv1 * dv1 + dv2 * dv2);
-    double n2 = rmag[j] * tmp + (r[j][0] * dv0 + r[j][1] * dv1 + r[j][2] * dv2);
-    double d2 = rmag[i] * tmp + (r[i][0] * dv0 + r[i][1] * dv1 + r[i][2] * dv2);
+    double dv0 = xsub(r[j][0], r[i][0]), dv1 = xsub(r[j][1], r[i][1]), dv2 = xsub(r[j][2], r[i][2]);
+    double tmp = __dsqrt_rn(xdot(dv0, dv1, dv2, dv0, dv1, dv2));
+    double n2 = xadd(xmul(rmag[j], tmp), xdot(r[j][0], r[j][1], r[j][2], dv0, dv1, dv2));
+    double d2 = xadd(xmul(rmag[i], tmp), xdot(r[i][0], r[i][1], r[i][2], dv0, dv1, dv2));
     double gam = 0.0;
-    if (!(fabs(d2) < 1.e-14 || tmp < 1.e-14)) gam = log(n2 / d2) / tmp;
-    double kx = c[i][1] * c[j][2] - c[i][2] * c[j][1];
-    double ky = c[i][2] * c[j][0] - c[i][0] * c[j][2];
-    double kz = c[i][0] * c[j][1] - c[i][1] * c[j][0];
-    phi += (nhat[0] * kx + nhat[1] * ky + nhat[2] * kz) * gam;
+    if (!(fabs(d2) < 1.e-14 || tmp < 1.e-14)) gam = __ddiv_rn(log(__ddiv_rn(n2, d2)), tmp);
+    double kx = xsub(xmul(c[i][1], c[j][2]), xmul(c[i][2], c[j][1]));
+    double ky = xsub(xmul(c[i][2], c[j][0]), xmul(c[i][0], c[j][2]));
+    double kz = xsub(xmul(c[i][0], c[j][1]), xmul(c[i][1], c[j][0]));
+    phi = xadd(phi, xmul(xdot(nhat[0], nhat[1], nhat[2], kx, ky, kz), gam));
   }
-  phi -= (nhat[0] * r[0][0] + nhat[1] * r[0][1] + nhat[2] * r[0][2]) * omega;
+  phi = xsub(phi, xmul(xdot(nhat[0], nhat[1], nhat[2], r[0][0], r[0][1], r[0][2]), omega));
   return phi;
 }
 
 __device__ __forceinline__ void tri_normal(const double* P, double* n) {
   // nhat = unit((p2-p1) x (p3-p2)), thin_wall.F90:1942-1943
-  double a0 = P[3] - P[0], a1 = P[4] - P[1], a2 = P[5] - P[2];
-  double b0 = P[6] - P[3], b1 = P[7] - P[4], b2 = P[8] - P[5];
-  double n0 = a1 * b2 - a2 * b1, n1 = a2 * b0 - a0 * b2, n2 = a0 * b1 - a1 * b0;
-  double m = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
-  n[0] = n0 / m;
-  n[1] = n1 / m;
-  n[2] = n2 / m;
+  double a0 = xsub(P[3], P[0]), a1 = xsub(P[4], P[1]), a2 = xsub(P[5], P[2]);
+  double b0 = xsub(P[6], P[3]), b1 = xsub(P[7], P[4]), b2 = xsub(P[8], P[5]);
+  double n0 = xsub(xmul(a1, b2), xmul(a2, b1)), n1 = xsub(xmul(a2, b0), xmul(a0, b2)), n2 = xsub(xmul(a0, b1), xmul(a1, b0));
+  double m = __dsqrt_rn(xdot(n0, n1, n2, n0, n1, n2));
+  n[0] = __ddiv_rn(n0, m);
+  n[1] = __ddiv_rn(n1, m);
+  n[2] = __ddiv_rn(n2, m);
 }
 
 // ---- bulk async copy (TMA 1-D) helpers ------------------------------------------------------

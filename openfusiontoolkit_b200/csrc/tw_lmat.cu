@@ -148,9 +148,9 @@ __device__ __forceinline__ double near_pair(const double* gA, const double* nA, 
   double s = 0.0;
   for (int q = lane; q < n; q += 32) {
     double b0 = bp[3 * q], b1 = bp[3 * q + 1], b2 = bp[3 * q + 2];
-    double x = b0 * PQ[0] + b1 * PQ[3] + b2 * PQ[6];
-    double y = b0 * PQ[1] + b1 * PQ[4] + b2 * PQ[7];
-    double z = b0 * PQ[2] + b1 * PQ[5] + b2 * PQ[8];
+    double x = xquad(b0, b1, b2, PQ[0], PQ[3], PQ[6]);
+    double y = xquad(b0, b1, b2, PQ[1], PQ[4], PQ[7]);
+    double z = xquad(b0, b1, b2, PQ[2], PQ[5], PQ[8]);
     s += bw[q] * phipot(PA, nh, x, y, z);
   }
   s = warp_sum(s);

@@ -657,3 +657,16 @@ void tco_quad_get(int iquad, double *pts, double *wts) {
     wts[q] = TCQ_WTS[TCQ_OFF[iquad] + q];
   }
 }
+
+/* Batched wrappers for the kernel-level parity tests (same functions, many inputs). */
+void tco_pair_T_batch(int n, const double *Pi, const double *Ai, const double *Pj, const double *Aj,
+                      double *T, int *iquad) {
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int k = 0; k < n; k++)
+    T[k] = tco_pair_T((const double(*)[3])(Pi + 9 * (size_t)k), Ai[k], (const double(*)[3])(Pj + 9 * (size_t)k),
+                      Aj[k], iquad + k);
+}
+void tco_phipot_batch(int n, const double *tri, const double *pt, double *out) {
+#pragma omp parallel for
+  for (int k = 0; k < n; k++) out[k] = tco_phipot((const double(*)[3])(tri + 9 * (size_t)k), pt + 3 * (size_t)k);
+}
