@@ -105,11 +105,16 @@ int thincurr_b200_msensor(void* tw_ptr, void* sensor_ptr, void** Ms_ptr, void** 
  * row_ids[nrows] returns the reference (0-based) DOF id of every local row. */
 int thincurr_b200_plan(void* tw_ptr, int nshards, int shard, int* nrows);
 int thincurr_b200_shard_rows(void* tw_ptr, int nshards, int shard, int* row_ids);
+/* info[8]: patch size, patches, chunks, sum of patch cells (halo included), self tiles, chunk pairs,
+ * cell pairs of those tiles (diagonal tiles counted in full), vertex patches */
+int thincurr_b200_plan_info(void* tw_ptr, int64_t* info);
 
 /* Self-inductance rows of one shard into caller-provided DEVICE memory d_out[nrows][ld]
  * (row r = full reference row row_ids[r], i.e. Lmat(:,row_ids[r]+1); ld >= nelems), on the
  * CUDA device that owns d_out, enqueued on `stream` (cudaStream_t as void*), asynchronous.
- * stats[8] (host, optional): tiles, pairs evaluated, far pairs, near T evaluations, ... */
+ * stats[8] (host, optional; forces a stream sync): [0] far pairs evaluated, [1] near T evaluations,
+ * [2] 1/r evaluations, [3] analytic-potential evaluations; the _host variant adds [5] host->device
+ * bytes of the model upload and [6] device->host bytes of the rows. */
 int thincurr_b200_Lmat_shard(void* tw_ptr, int nshards, int shard, double* d_out, int64_t ld, void* stream,
                              int64_t* stats);
 /* Same from HOST mesh each call (uploads model, builds, copies rows back to h_out[nrows][ld]);
@@ -123,14 +128,19 @@ int thincurr_b200_Bel_shard(void* tw_ptr, int nshards, int shard, double* d_out,
  * hist[19], visited = # ordered pairs not skipped by thin_wall.F90:1034. */
 int thincurr_b200_pair_stats(void* tw_ptr, int64_t* hist, int64_t* visited);
 
+/* Number of operator kernels this library has launched so far (all devices, this process). */
+long long thincurr_b200_launch_count(void);
+
 /* FP64 DFMA peak microbenchmark on the current device (TFLOP/s, FMA = 2 flops). */
 double thincurr_b200_dfma_peak(int device, double* sm_clock_mhz);
 
 /* Kernel-level probes for the parity tests: the device functions of the operator kernels on
  * caller-given inputs.  probe_pairs: T(i,j) with cell i the analytic side when near, and the
- * selected quadrature order (thin_wall.F90:1044-1083); Pi/Pj = [n][3][3] vertices, Ai/Aj areas.
+ * selected quadrature order (thin_wall.F90:1044-1083); Pi/Pj = [n][3][3] vertices, Ai/Aj areas;
+ * mode 0 = FP64 classification + far field from the vertices, mode 1 = the tile kernel's path (FP32
+ * order screen with exact fallback [iquad bit 6 set when taken], far field from point tables).
  * probe_phipot: tw_compute_phipot (thin_wall.F90:1934-1985) for tri[n][3][3], pt[n][3]. */
-int thincurr_b200_probe_pairs(int n, const double* Pi, const double* Ai, const double* Pj, const double* Aj,
+int thincurr_b200_probe_pairs(int n, int mode, const double* Pi, const double* Ai, const double* Pj, const double* Aj,
                               double* T, int* iquad);
 int thincurr_b200_probe_phipot(int n, const double* tri, const double* pt, double* out);
 int thincurr_b200_probe_rsqrt(int n, const double* x, double* y);

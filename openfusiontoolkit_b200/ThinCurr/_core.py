@@ -308,6 +308,14 @@ class ThinCurr():
         sptr = c_void_p(stream) if stream else c_void_p()
         _check(b200_Bel_shard(self.tw_obj, nshards, shard, c_void_p(out.data_ptr()), sptr))
 
+    def plan_info(self):
+        '''! Patch/chunk/tile counts of the owner-computes plan (see thincurr_b200_plan_info).'''
+        from .._interface import b200_plan_info
+        info = numpy.zeros(8, dtype=numpy.int64)
+        _check(b200_plan_info(self.tw_obj, info))
+        return dict(zip(('patch_size', 'npatch', 'nchunk', 'patch_cells', 'ntiles', 'chunk_pairs', 'cell_pairs', 'nvert_patch'),
+                        [int(v) for v in info]))
+
     def pair_stats(self):
         '''! iquad histogram [19] and number of ordered pairs visited by the reference loop nest.'''
         hist = numpy.zeros(19, dtype=numpy.int64)

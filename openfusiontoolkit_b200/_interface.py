@@ -94,6 +94,8 @@ b200_get_model = ctypes_subroutine(oftpy_lib.thincurr_b200_get_model,
 b200_hashes = ctypes_subroutine(oftpy_lib.thincurr_b200_hashes, [c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)], c_int)
 _f64 = numpy.ctypeslib.ndpointer(dtype=numpy.float64, flags='C_CONTIGUOUS')
 _i32 = numpy.ctypeslib.ndpointer(dtype=numpy.int32, flags='C_CONTIGUOUS')
-b200_probe_pairs = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_pairs, [c_int, _f64, _f64, _f64, _f64, _f64, _i32], c_int)
+b200_probe_pairs = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_pairs, [c_int, c_int, _f64, _f64, _f64, _f64, _f64, _i32], c_int)
 b200_probe_phipot = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_phipot, [c_int, _f64, _f64, _f64], c_int)
 b200_probe_rsqrt = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_rsqrt, [c_int, _f64, _f64], c_int)
+b200_launch_count = ctypes_subroutine(oftpy_lib.thincurr_b200_launch_count, [], ctypes.c_longlong)
+b200_plan_info = ctypes_subroutine(oftpy_lib.thincurr_b200_plan_info, [c_void_p, numpy.ctypeslib.ndpointer(dtype=numpy.int64, flags='C_CONTIGUOUS')], c_int)

@@ -58,7 +58,11 @@ struct XmlDoc {
 // ---------------------------------------------------------------------------------------------
 namespace tw {
 
-void HostBuf::alloc(size_t count) {
+void HostBuf::alloc(size_t count, bool zero) {
+  if (p && n == count) {  // reuse (rebuilds of the same operator keep the Python view valid)
+    if (zero) std::memset(p, 0, count * sizeof(double));
+    return;
+  }
   release();
   n = count;
   if (count == 0) return;
@@ -67,7 +71,7 @@ void HostBuf::alloc(size_t count) {
   if (bytes <= (size_t)16 << 30) {
     if (cudaMallocHost((void**)&p, bytes) == cudaSuccess) {
       pinned = true;
-      std::memset(p, 0, bytes);
+      if (zero) std::memset(p, 0, bytes);
       return;
     }
     cudaGetLastError();
@@ -271,7 +275,7 @@ void thincurr_Lmat(void* tw_ptr, bool use_hodlr, void** Lmat_ptr, const char* ca
   auto t0 = std::chrono::steady_clock::now();
   int ndev = visible_devices();
   if (ndev < 1) return set_err(error_str, "No CUDA device available (the B200 backend has no CPU fallback)");
-  m.Lmat.alloc(N * N);
+  m.Lmat.alloc(N * N, false);  // every entry is overwritten by the device->host copies
   if (!m.Lmat.p) return set_err(error_str, "Host allocation of the inductance matrix failed");
   std::string err = ensure_plan(m);
   if (!err.empty()) return set_err(error_str, err);
@@ -542,6 +546,31 @@ int thincurr_b200_plan(void* tw_ptr, int nshards, int shard, int* nrows) {
   return 0;
 }
 
+int thincurr_b200_plan_info(void* tw_ptr, int64_t* info) {
+  Model& m = *(Model*)tw_ptr;
+  std::string err = ensure_plan(m);
+  if (!err.empty()) return fail(err);
+  const PatchSet& ps = m.plan->ps;
+  std::vector<Tile> tiles;
+  build_self_tiles(ps, 0, ps.npatch, tiles);
+  int64_t cells = 0, chunk_pairs = 0, cell_pairs = 0;
+  for (int n : ps.patch_ncell) cells += n;
+  for (auto& t : tiles) {
+    int64_t na = ps.patch_chunk_ptr[t.pa + 1] - ps.patch_chunk_ptr[t.pa], nb = ps.patch_chunk_ptr[t.pb + 1] - ps.patch_chunk_ptr[t.pb];
+    chunk_pairs += na * nb;
+    cell_pairs += (int64_t)ps.patch_ncell[t.pa] * ps.patch_ncell[t.pb];
+  }
+  info[0] = m.plan->patch_size;
+  info[1] = ps.npatch;
+  info[2] = ps.nchunk;
+  info[3] = cells;
+  info[4] = (int64_t)tiles.size();
+  info[5] = chunk_pairs;
+  info[6] = cell_pairs;
+  info[7] = ps.nvert_patch;
+  return 0;
+}
+
 int thincurr_b200_shard_rows(void* tw_ptr, int nshards, int shard, int* row_ids) {
   Model& m = *(Model*)tw_ptr;
   std::string err = ensure_plan(m);
@@ -582,8 +611,11 @@ int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* 
     err = std::string("Device->host copy failed: ") + cudaGetErrorString(cudaGetLastError());
   cudaFree(d);
   if (!err.empty()) return fail(err);
-  if (stats)
+  if (stats) {
     for (int k = 0; k < 8; k++) stats[k] = (int64_t)st[k];
+    stats[5] = m.dev.empty() ? 0 : (int64_t)m.dev[0]->ps.bytes;  // host->device bytes of the model upload
+    stats[6] = (int64_t)bytes;                                   // device->host bytes
+  }
   return 0;
 }
 
@@ -600,6 +632,8 @@ int thincurr_b200_pair_stats(void* tw_ptr, int64_t* hist, int64_t* visited) {
   if (!err.empty()) return fail(err);
   return 0;
 }
+
+long long thincurr_b200_launch_count(void) { return launch_count(); }
 
 double thincurr_b200_dfma_peak(int device, double* sm_clock_mhz) { return gpu_dfma_peak(device, sm_clock_mhz); }
 

@@ -22,6 +22,7 @@ __device__ double g_qpts[341 * 3];  // same tables in global memory (lane-diverg
 __device__ double g_qwts[341];
 __constant__ double c_thr[14];
 __constant__ double c_thr2[14];
+__constant__ float c_thr2f[14];  // same, rounded to FP32 (order screening)
 
 // ---- reciprocal square root --------------------------------------------------------------
 // MUFU.RSQ64H gives ~2^-20.4 relative error on the high word; y1 = y0(1 + e/2 + 3e^2/8) with

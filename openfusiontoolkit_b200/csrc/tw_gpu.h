@@ -17,6 +17,7 @@ struct DevicePatchSet {
   int *dmin = nullptr, *dmax = nullptr, *chunk_dof = nullptr, *inc_ptr = nullptr;
   uint16_t* inc = nullptr;
   int *patch_chunk_ptr = nullptr, *dof_orig = nullptr;
+  size_t bytes = 0;  // host->device bytes of the last upload
   std::string upload_from(const PatchSet& ps);
   void release();
   ~DevicePatchSet() { release(); }
@@ -28,6 +29,9 @@ struct DeviceState {
 };
 
 std::string gpu_init_constants();
+// number of operator kernels launched by this library so far (bench.py's gpu_launches)
+void note_launch();
+long long launch_count();
 
 // Run the tile kernel: out[row_out[internal row]][ld] += (1/4pi) sum ... ; out must be zeroed.
 // h_stats (optional, 8 x u64) forces a stream sync: far pairs, near T evals, 1/r evals, phipot evals.

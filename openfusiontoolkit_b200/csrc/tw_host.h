@@ -64,7 +64,7 @@ struct HostBuf {  // pinned host buffer owned by the model
   double* p = nullptr;
   size_t n = 0;
   bool pinned = false;
-  void alloc(size_t count);
+  void alloc(size_t count, bool zero = true);
   void release();
   ~HostBuf() { release(); }
 };

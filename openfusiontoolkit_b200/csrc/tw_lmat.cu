@@ -1,18 +1,32 @@
 // tw_lmat.cu -- dense element<->element inductance build on sm_100a (FP64, no tensor cores).
 //
 // Replaces the O(nc^2) OpenMP loop nest of tw_compute_LmatDirect (src/physics/thin_wall.F90:
-// 1008-1126) with an owner-computes tiling: one CTA owns the output tile (row patch x column
-// patch), stages a chunk of "row" triangles and a chunk of "column" triangles in shared memory
-// (1-D bulk async copies of the contiguous SoA chunk records, mbarrier-tracked), evaluates the
-// pair integrals T(c1,c2) for the 64x64 chunk pair into a shared-memory tile, and contracts
-// them onto the vertex/hole DOFs.  Every L entry is written by exactly one thread of exactly
-// one CTA (plain read-modify-write between barriers): no atomics, deterministic summation.
+// 1008-1126) with an owner-computes tiling.  One persistent CTA per SM pulls output tiles
+// (row patch x column patch) from a cost-sorted queue.  For every pair of 64-cell chunks of the
+// two patches it
+//   A. stages both chunks' SoA geometry records in shared memory (1-D bulk async copies,
+//      mbarrier-tracked) and classifies the 4096 cell pairs: the quadrature order of
+//      thin_wall.F90:1044-1059 is screened in FP32 on locally shifted coordinates with a rigorous
+//      error band and falls back to a bit-exact FP64 evaluation when a threshold is within the band;
+//   B. bins the pairs by rule (counting sort in shared memory, bins padded to warp multiples) so
+//      that every warp executes ONE rule -- no divergence;
+//   C. evaluates T(c1,c2): far pairs (thin_wall.F90:1069-1083) from per-chunk tables of quadrature
+//      points held in shared memory ((x,y,z,|x|^2) in a local frame, d^2 = |xi|^2+|xj|^2-2 xi.xj,
+//      MUFU.RSQ64H seed + third-order correction = 10 FP64-pipe instructions per 1/r), near pairs
+//      (thin_wall.F90:1061-1068) with one half-warp per pair, lanes over the quadrature points of
+//      the analytic potential; work is handed out in warp-sized batches from a shared counter;
+//   D. contracts T onto the vertex/hole DOFs in two stages (cell x column-DOF partial sums in
+//      shared memory, then row-DOF sums) and adds the block into L.
+// Every L entry is owned by exactly one CTA and updated by plain read-modify-writes between
+// barriers: no atomics on the matrix, deterministic summation.
 //
 // Role rule (SURVEY hard part 1): for entry (a,b) with a<=b in reference numbering the cell
-// carrying `a` is the analytic side of near pairs.  T1 = T(c1 analytic), T2 = T(c2 analytic).
+// carrying `a` is the analytic side of near pairs.  Role-1 values T(c1 analytic) serve entries
+// with a<=b, role-2 values T(c2 analytic) entries with a>b; far pairs are role-symmetric.
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -28,7 +42,17 @@ using tw::kCH;
 using tw::kGeomRows;
 constexpr int NT = 512;            // threads per CTA (16 warps), one CTA per SM
 constexpr int NW = NT / 32;
-constexpr int kMaxNear = kCH * kCH;
+constexpr int TS = kCH + 1;        // row stride of the T tile (bank-conflict-free column access)
+constexpr int NCLS = 12;           // far classes 0..6 (iquad 4..10), near classes 7..11 (28,33,46,55,72 points)
+constexpr int kListCap = kCH * kCH + NCLS * 32;
+constexpr int kTabMaxN = 16;       // largest rule served from shared-memory point tables
+constexpr int kTabMin = 96;        // fewer pairs of a rule than this: evaluate from the vertices instead
+constexpr int UB = 32, US = UB + 1;  // column-DOF block of the contraction and its padded stride
+
+__device__ __constant__ int c_cls_np[NCLS] = {6, 7, 12, 15, 16, 19, 25, 28, 33, 46, 55, 72};
+__device__ __forceinline__ int cls_of(int iq) {
+  return iq <= 10 ? iq - 4 : (iq == 11 ? 7 : (iq == 12 ? 8 : (iq <= 14 ? 9 : (iq <= 16 ? 10 : 11))));
+}
 
 struct LmatArgs {
   // row side / column side patch sets (same pointers for self inductance)
@@ -54,24 +78,37 @@ struct LmatArgs {
 struct Smem {
   double gI[kGeomRows * kCH];
   double gJ[kGeomRows * kCH];
-  double nI[3 * kCH];   // unit normals of row cells
+  double T[kCH * TS];
+  union {
+    struct {
+      double2 tabI[kTabMaxN * 2 * kCH];  // [(p*2+h)*64 + c]: h=0 (-2x,-2y), h=1 (-2z,|x|^2)
+      double2 tabJ[kTabMaxN * 2 * kCH];  //                   h=0 (x,y),     h=1 (z,|x|^2)
+    } tab;
+    double U[3 * kCH * US];              // [comp][c1][b] partial sums of the contraction
+  } w;
+  double nI[3 * kCH];   // unit normals (reference formula) of row / column cells
   double nJ[3 * kCH];
-  double T1[kCH * kCH];  // [c1][c2]
-  double T2[kCH * kCH];
-  unsigned int near_list[kMaxNear];
+  float vfI[9 * kCH], vfJ[9 * kCH];  // vertices in the local frame, FP32 (order screening)
+  float flI[kCH], flJ[kCH];          // 2 * area
+  unsigned short list[kListCap];     // pair ids (c1<<6|c2) sorted by class, bins padded with 0xFFFF
+  unsigned char iqmap[kCH * kCH];    // iquad | need-role-1 << 5 | need-role-2 << 6
   int dminI[kCH], dmaxI[kCH], dminJ[kCH], dmaxJ[kCH];
   int dofI[tw::kMaxChunkDof], dofJ[tw::kMaxChunkDof];
+  int origI[tw::kMaxChunkDof], origJ[tw::kMaxChunkDof];  // reference DOF ids
+  int rowI[tw::kMaxChunkDof], rowJ[tw::kMaxChunkDof];    // output rows (or -1)
   int iptrI[tw::kMaxChunkDof + 1], iptrJ[tw::kMaxChunkDof + 1];
   uint16_t incI[tw::kMaxChunkInc], incJ[tw::kMaxChunkInc];
   unsigned long long bar[2];
-  int near_count;
+  int cnt[NCLS], off[NCLS + 1], fill[NCLS];
+  int qcls[NCLS], qfirst[NCLS + 1], qn;  // batch queue of phase C0
+  int qhead, both_count;
   int tile_id;
 };
 
-// ---- far-field tensor quadrature -----------------------------------------------------------
+// ---- far field from the vertices (rules without a table / tiny bins) --------------------------
 // T = area_i area_j sum_p sum_q w_p w_q / |x_p(i) - x_q(j)|, same rule on both triangles
 // (thin_wall.F90:1069-1083).  j-side points are held in registers in blocks of <= 8; the i-side
-// point is recomputed per p (warp-uniform broadcast from shared memory).
+// point is recomputed per p.
 template <int N>
 __device__ __forceinline__ double far_pair(const double* __restrict__ gI, int c1, const double* __restrict__ gJ, int c2,
                                            int iquad) {
@@ -129,10 +166,60 @@ __device__ __forceinline__ double far_dispatch(const double* gI, int c1, const d
   }
 }
 
-// near pair: T = area_q * sum_q w_q phi_{tri A}(x_q(tri Q)); lanes parallelise over q
-// (thin_wall.F90:1061-1068).  gA/cA = analytic triangle, gQ/cQ = quadrature triangle.
-__device__ __forceinline__ double near_pair(const double* gA, const double* nA, int cA, const double* gQ, int cQ,
-                                            int iquad, int lane) {
+// ---- far field from the shared-memory point tables ----------------------------------------------
+// 10 FP64-pipe instructions per 1/r: 1 add + 3 fma (d^2), 5 (rsqrt correction), 1 fma (weighted sum)
+template <int N, int OFF>
+__device__ __forceinline__ double far_tab(const double2* __restrict__ tabI, const double2* __restrict__ tabJ, int c1, int c2) {
+  const double* bw = c_qwts + OFF;  // OFF = TCQ_OFF[iquad]: weights become constant-bank operands
+  constexpr int NB = (N + 6) / 7;          // j-side register blocks of <= 7 points
+  constexpr int QB = (N + NB - 1) / NB;
+  double total = 0.0;
+#pragma unroll 1
+  for (int q0 = 0; q0 < N; q0 += QB) {
+    double xj[QB], yj[QB], zj[QB], sj[QB], acc[QB];
+#pragma unroll
+    for (int q = 0; q < QB; q++) {
+      const int qq = (q0 + q < N) ? q0 + q : N - 1;
+      const double2 u = tabJ[(qq * 2) * kCH + c2], v = tabJ[(qq * 2 + 1) * kCH + c2];
+      xj[q] = u.x;
+      yj[q] = u.y;
+      zj[q] = v.x;
+      sj[q] = v.y;
+      acc[q] = 0.0;
+    }
+#pragma unroll(N <= 7 ? N : 3)
+    for (int p = 0; p < N; p++) {
+      const double2 a = tabI[(p * 2) * kCH + c1], b = tabI[(p * 2 + 1) * kCH + c1];
+      const double wp = bw[p];
+#pragma unroll
+      for (int q = 0; q < QB; q++) {
+        double d2 = fma(a.x, xj[q], fma(a.y, yj[q], fma(b.x, zj[q], b.y + sj[q])));
+        acc[q] = fma(wp, rsqrt_fast(d2), acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < QB; q++)
+      if (q0 + q < N) total = fma(bw[q0 + q], acc[q], total);
+  }
+  return total;
+}
+
+__device__ __forceinline__ double far_tab_dispatch(const double2* tabI, const double2* tabJ, int c1, int c2, int cls) {
+  switch (cls) {
+    case 0: return far_tab<6, 7>(tabI, tabJ, c1, c2);
+    case 1: return far_tab<7, 13>(tabI, tabJ, c1, c2);
+    case 2: return far_tab<12, 20>(tabI, tabJ, c1, c2);
+    case 3: return far_tab<15, 32>(tabI, tabJ, c1, c2);
+    default: return far_tab<16, 47>(tabI, tabJ, c1, c2);
+  }
+}
+
+// ---- near field ------------------------------------------------------------------------------------
+// T = area_q * sum_q w_q phi_{tri A}(x_q(tri Q)) (thin_wall.F90:1061-1068); gA/cA = analytic
+// triangle, gQ/cQ = quadrature triangle.  `nl` lanes (16 or 32, aligned group of the warp)
+// cooperate on one pair; every lane of the group returns the sum.
+__device__ __forceinline__ double near_pair(const double* gA, const double* nA, int cA, const double* gQ, int cQ, int iquad,
+                                            int gl, int nl, unsigned mask) {
   double PA[9], PQ[9], nh[3];
 #pragma unroll
   for (int k = 0; k < 9; k++) {
@@ -146,17 +233,74 @@ __device__ __forceinline__ double near_pair(const double* gA, const double* nA, 
   const double* bp = g_qpts + 3 * c_qoff[iquad];  // lane-divergent index -> global copy of the tables
   const double* bw = g_qwts + c_qoff[iquad];
   double s = 0.0;
-  for (int q = lane; q < n; q += 32) {
+  for (int q = gl; q < n; q += nl) {
     double b0 = bp[3 * q], b1 = bp[3 * q + 1], b2 = bp[3 * q + 2];
     double x = xquad(b0, b1, b2, PQ[0], PQ[3], PQ[6]);
     double y = xquad(b0, b1, b2, PQ[1], PQ[4], PQ[7]);
     double z = xquad(b0, b1, b2, PQ[2], PQ[5], PQ[8]);
     s += bw[q] * phipot(PA, nh, x, y, z);
   }
-  s = warp_sum(s);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(mask, s, o);
+  if (nl == 32) s += __shfl_xor_sync(mask, s, 16);
   return s * gQ[9 * kCH + cQ];
 }
 
+// ---- order selection: FP32 screen with a rigorous band, exact FP64 fallback -----------------------
+// vI/vJ: vertices in a common local frame rounded to FP32 (|v| <= X); delta = bound of the
+// coordinate error of a vertex DIFFERENCE (input rounding of both operands, = 2^-23 X * 1.01).
+// Returns iquad, or -1 when the decision is not safe in FP32.
+__device__ __forceinline__ int iquad_screen(const float* __restrict__ vI, int c1, const float* __restrict__ vJ, int c2, float fl2,
+                                            float delta) {
+  float pi_[9], pj_[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    pi_[k] = vI[k * kCH + c1];
+    pj_[k] = vJ[k * kCH + c2];
+  }
+  float d2min = 3.0e38f, d2max = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      float dx = pi_[3 * a] - pj_[3 * b], dy = pi_[3 * a + 1] - pj_[3 * b + 1], dz = pi_[3 * a + 2] - pj_[3 * b + 2];
+      float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      d2min = fminf(d2min, d2);
+      d2max = fmaxf(d2max, d2);
+    }
+  // the floor sqrt(2 max(area)) is exact to FP32 rounding; vertex distances carry |err(d)| <= sqrt(3) delta
+  const float dmaxv = sqrtf(d2max);
+  const bool floor_wins = fl2 >= d2max;
+  d2max = fmaxf(d2max, fl2);
+  // coincident in FP32 => true dl_min <= sqrt(3) delta; order 18 as soon as that is < 0.3 dl_max
+  if (d2min == 0.0f) return (3.0f * delta * delta < 0.09f * d2max) ? 18 : -1;
+  // relative error bound of rho^2 = d2min/d2max: 2 err(d)/d per distance + FP32 arithmetic (7 roundings)
+  const float e = 1.7320508f * delta;
+  float band = 2.0f * e * rsqrtf(d2min) + (floor_wins ? 0.0f : 2.0f * e / dmaxv) + 2.0e-6f;
+  band = 1.5f * band + band * band;
+  if (!(band < 0.25f)) return -1;
+  const float r = d2min / d2max, rlo = r * (1.0f - band), rhi = r * (1.0f + band);
+  int nlo = 0, nhi = 0;
+#pragma unroll
+  for (int k = 0; k < 14; k++) {
+    const float t = c_thr2f[k];
+    nlo += (rhi <= t) ? 1 : 0;
+    nhi += (rlo <= t) ? 1 : 0;
+  }
+  return (nlo == nhi) ? 4 + nlo : -1;
+}
+
+__device__ __noinline__ int iquad_exact_cells(const double* gI, int c1, const double* gJ, int c2) {
+  double Pi[9], Pj[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    Pi[k] = gI[k * kCH + c1];
+    Pj[k] = gJ[k * kCH + c2];
+  }
+  return iquad_exact(Pi, Pj, 3, 3, fmax(gI[9 * kCH + c1], gJ[9 * kCH + c2]) * 2.0);
+}
+
+// (kept for the probes) classification directly in FP64
 __device__ __forceinline__ int classify_pair(const double* gI, int c1, const double* gJ, int c2) {
   double Pi[9], Pj[9];
 #pragma unroll
@@ -180,6 +324,29 @@ __device__ __forceinline__ int classify_pair(const double* gI, int c1, const dou
   return iq;
 }
 
+// quadrature-point table of one chunk for one rule in the frame centred at (ox,oy,oz):
+// neg=true stores (-2x,-2y),(-2z,|x|^2) (row side), else (x,y),(z,|x|^2)
+__device__ __forceinline__ void build_table(double2* __restrict__ tab, const double* __restrict__ g, int ncell, int iquad, int n,
+                                            double ox, double oy, double oz, bool neg, int tid0, int nthreads) {
+  const double* bp = c_qpts + 3 * c_qoff[iquad];
+  for (int it = tid0; it < n * kCH; it += nthreads) {
+    const int p = it / kCH, c = it - p * kCH;
+    if (c >= ncell) continue;
+    const double b0 = bp[3 * p], b1 = bp[3 * p + 1], b2 = bp[3 * p + 2];
+    const double x = (b0 * g[0 * kCH + c] + b1 * g[3 * kCH + c] + b2 * g[6 * kCH + c]) - ox;
+    const double y = (b0 * g[1 * kCH + c] + b1 * g[4 * kCH + c] + b2 * g[7 * kCH + c]) - oy;
+    const double z = (b0 * g[2 * kCH + c] + b1 * g[5 * kCH + c] + b2 * g[8 * kCH + c]) - oz;
+    const double s2 = fma(z, z, fma(y, y, x * x));
+    if (neg) {
+      tab[(p * 2) * kCH + c] = make_double2(-2.0 * x, -2.0 * y);
+      tab[(p * 2 + 1) * kCH + c] = make_double2(-2.0 * z, s2);
+    } else {
+      tab[(p * 2) * kCH + c] = make_double2(x, y);
+      tab[(p * 2 + 1) * kCH + c] = make_double2(z, s2);
+    }
+  }
+}
+
 __device__ __forceinline__ void load_chunk(Smem& S, int side, const LmatArgs& A, int chunk, unsigned long long* bar,
                                            uint32_t& phase) {
   // side 0: row chunk (I), 1: column chunk (J).  Geometry record via one bulk async copy issued
@@ -198,16 +365,25 @@ __device__ __forceinline__ void load_chunk(Smem& S, int side, const LmatArgs& A,
   const int* cdof = (side ? A.chunk_dofB : A.chunk_dofA) + cm.dof_off;
   const int* iptr = (side ? A.inc_ptrB : A.inc_ptrA) + cm.dof_off + chunk;
   const uint16_t* inc = (side ? A.incB : A.incA) + cm.inc_off;
+  const int* dorig = side ? A.dof_origB : A.dof_origA;
   int* sdmn = side ? S.dminJ : S.dminI;
   int* sdmx = side ? S.dmaxJ : S.dmaxI;
   int* sdof = side ? S.dofJ : S.dofI;
+  int* sorig = side ? S.origJ : S.origI;
+  int* srow = side ? S.rowJ : S.rowI;
   int* sptr = side ? S.iptrJ : S.iptrI;
   uint16_t* sinc = side ? S.incJ : S.incI;
   for (int i = threadIdx.x; i < kCH; i += NT) {
     sdmn[i] = dmn[i];
     sdmx[i] = dmx[i];
   }
-  for (int i = threadIdx.x; i < cm.ndof; i += NT) sdof[i] = cdof[i];
+  for (int i = threadIdx.x; i < cm.ndof; i += NT) {
+    const int d = cdof[i];
+    sdof[i] = d;
+    sorig[i] = dorig[d];
+    // rows of the column side exist only for self inductance (mirror writes)
+    srow[i] = (side == 0 || A.self) ? A.row_out[d] : -1;
+  }
   for (int i = threadIdx.x; i <= cm.ndof; i += NT) sptr[i] = iptr[i];
   const int ninc = iptr[cm.ndof];
   for (int i = threadIdx.x; i < ninc; i += NT) sinc[i] = inc[i];
@@ -222,6 +398,43 @@ __device__ __forceinline__ void load_chunk(Smem& S, int side, const LmatArgs& A,
     nn[c] = n[0];
     nn[kCH + c] = n[1];
     nn[2 * kCH + c] = n[2];
+  }
+}
+
+// one batch of the work queue: 32 far pairs of one rule (from the vertices) or 2 near pairs
+__device__ __forceinline__ void run_batch_c0(Smem& S, int cls, int first, int lane, bool role2_pass, unsigned long long& st_near,
+                                             unsigned long long& st_phi) {
+  if (cls < 7) {
+    const unsigned e = S.list[first + lane];
+    if (e != 0xFFFFu) {
+      const int c1 = e >> 6, c2 = e & 63;
+      S.T[c1 * TS + c2] = far_dispatch(S.gI, c1, S.gJ, c2, cls + 4);
+    }
+  } else {
+    const int hw = lane >> 4, hl = lane & 15;
+    const unsigned e = S.list[first + hw];
+    unsigned m = 0;
+    int c1 = 0, c2 = 0, iq = 18;
+    if (e != 0xFFFFu) {
+      m = S.iqmap[e];
+      c1 = e >> 6;
+      c2 = e & 63;
+      iq = m & 31;
+    }
+    const bool n1 = m & 32, n2 = m & 64;
+    // first pass: role 1 if needed, else role 2; second pass: role 2 of the pairs that need both
+    const bool do1 = !role2_pass && n1, do2 = role2_pass ? (n1 && n2) : (!n1 && n2);
+    if (do1 || do2) {  // uniform per half-warp; the shuffles name only this half
+      const unsigned mask = 0xFFFFu << (16 * hw);
+      double v;
+      if (do2) v = near_pair(S.gJ, S.nJ, c2, S.gI, c1, iq, hl, 16, mask);
+      else v = near_pair(S.gI, S.nI, c1, S.gJ, c2, iq, hl, 16, mask);
+      if (hl == 0) {
+        S.T[c1 * TS + c2] = v;
+        st_near++;
+        st_phi += c_qnp[iq];
+      }
+    }
   }
 }
 
@@ -250,119 +463,237 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {
     const int cj0 = A.patch_chunk_ptrB[tile.pb], cj1 = A.patch_chunk_ptrB[tile.pb + 1];
 
     for (int ci = ci0; ci < ci1; ci++) {
-      __syncthreads();  // previous contraction finished with gI lists
+      __syncthreads();  // previous contraction finished with the I-side lists
       load_chunk(S, 0, A, ci, &S.bar[0], phI);
-      const int ncI = A.chunksA[ci].ncell, ndI = A.chunksA[ci].ndof;
+      const tw::ChunkMeta cmI = A.chunksA[ci];
+      const int ncI = cmI.ncell, ndI = cmI.ndof;
       for (int cj = cj0; cj < cj1; cj++) {
-        __syncthreads();  // previous contraction finished with gJ / T tiles
+        __syncthreads();  // previous contraction finished with the J-side lists / T / U
         load_chunk(S, 1, A, cj, &S.bar[1], phJ);
-        const int ncJ = A.chunksB[cj].ncell, ndJ = A.chunksB[cj].ndof;
-        if (tid == 0) S.near_count = 0;
+        const tw::ChunkMeta cmJ = A.chunksB[cj];
+        const int ncJ = cmJ.ncell, ndJ = cmJ.ndof;
+        // local frame: midpoint of the two chunk centres
+        const double ox = 0.5 * (cmI.cx + cmJ.cx), oy = 0.5 * (cmI.cy + cmJ.cy), oz = 0.5 * (cmI.cz + cmJ.cz);
+        float delta;
+        {
+          const double hx = 0.5 * (cmI.cx - cmJ.cx), hy = 0.5 * (cmI.cy - cmJ.cy), hz = 0.5 * (cmI.cz - cmJ.cz);
+          const double X = sqrt(hx * hx + hy * hy + hz * hz) + fmax(cmI.rad, cmJ.rad);
+          delta = (float)(X * 1.21e-7);  // two operands, each rounded to FP32 (2^-24 relative), 1% slack
+        }
+        // ---------------- phase A0: FP32 local-frame vertices, list reset ---------------------------
+        for (int i = tid; i < 9 * kCH; i += NT) {
+          const int k = i / kCH, d = k % 3;
+          const double o = d == 0 ? ox : (d == 1 ? oy : oz);
+          S.vfI[i] = (float)(S.gI[i] - o);
+          S.vfJ[i] = (float)(S.gJ[i] - o);
+        }
+        for (int i = tid; i < kCH; i += NT) {
+          S.flI[i] = (float)(2.0 * S.gI[9 * kCH + i]);
+          S.flJ[i] = (float)(2.0 * S.gJ[9 * kCH + i]);
+        }
+        for (int i = tid; i < kListCap; i += NT) S.list[i] = 0xFFFFu;
+        if (tid < NCLS) {
+          S.cnt[tid] = 0;
+          S.fill[tid] = 0;
+        }
+        if (tid == 0) S.both_count = 0;
         __syncthreads();
-
-        // ---------------- phase 1: classification + far field --------------------------------
-        // warp w: column half (w&1), rows (w>>1) + 8m
+        // ---------------- phase A: classification ----------------------------------------------------
+        // warp w handles rows c1 = (w>>1) + 8m, columns lane + 32 (w&1)
+        unsigned mycls = 0;  // 4 bits per iteration: class + 1, 0 = no pair
         {
           const int c2 = lane + 32 * (warp & 1);
+#pragma unroll 1
           for (int m = 0; m < kCH / 8; m++) {
             const int c1 = (warp >> 1) + 8 * m;
-            if (c1 >= ncI) break;  // warp-uniform
-            int iq = 0;
-            bool n1 = false, n2 = false;
-            if (c2 < ncJ) {
+            unsigned code = 0;
+            int cls = -1;
+            if (c1 < ncI && c2 < ncJ) {
+              bool n1, n2 = false;
               if (A.self) {
                 n1 = S.dminI[c1] <= S.dmaxJ[c2];
-                n2 = want2 && (S.dmaxI[c1] > S.dminJ[c2]);
-                if (diag) n2 = false;
+                n2 = want2 && !diag && (S.dmaxI[c1] > S.dminJ[c2]);
               } else {
                 n1 = true;
               }
-              if (n1 || n2) iq = classify_pair(S.gI, c1, S.gJ, c2);
-            }
-            double tval = 0.0;
-            if (iq > 10) {
-              int k = atomicAdd(&S.near_count, 1);
-              S.near_list[k] = (unsigned)c1 | ((unsigned)c2 << 6) | ((unsigned)iq << 12) | ((unsigned)n1 << 17) |
-                               ((unsigned)n2 << 18);
-            }
-            unsigned todo = __ballot_sync(0xffffffffu, iq >= 4 && iq <= 10);
-            while (todo) {
-              const int leader = __ffs(todo) - 1;
-              const int r = __shfl_sync(0xffffffffu, iq, leader);
-              const bool mine = (iq == r);
-              if (mine) {
-                tval = far_dispatch(S.gI, c1, S.gJ, c2, r);
-                st_far++;
-                st_eval += (unsigned long long)c_qnp[r] * c_qnp[r];
+              if (n1 || n2) {
+                int iq = iquad_screen(S.vfI, c1, S.vfJ, c2, fmaxf(S.flI[c1], S.flJ[c2]), delta);
+                if (iq < 0) iq = iquad_exact_cells(S.gI, c1, S.gJ, c2);
+                code = (unsigned)iq | (n1 ? 32u : 0u) | (n2 ? 64u : 0u);
+                cls = cls_of(iq);
               }
-              todo &= ~__ballot_sync(0xffffffffu, mine);
             }
-            if (c2 < kCH) {
-              S.T1[c1 * kCH + c2] = tval;
-              S.T2[c1 * kCH + c2] = tval;
+            S.iqmap[c1 * kCH + c2] = (unsigned char)code;
+            S.T[c1 * TS + c2] = 0.0;
+            const unsigned grp = __match_any_sync(0xffffffffu, cls);
+            if (cls >= 0 && lane == __ffs(grp) - 1) atomicAdd(&S.cnt[cls], __popc(grp));
+            if (cls >= 7 && (code & 96u) == 96u) atomicAdd(&S.both_count, 1);
+            mycls |= (unsigned)(cls + 1) << (4 * m);
+          }
+        }
+        __syncthreads();
+        // ---------------- phase B: bin offsets, queue of phase C0, scatter ---------------------------
+        if (tid == 0) {
+          // near classes first (largest rules first), then far classes by decreasing size
+          const int order[NCLS] = {11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0};
+          int o = 0, nb = 0, nq = 0;
+          unsigned long long fp = 0, ev = 0;
+          for (int k = 0; k < NCLS; k++) {
+            const int c = order[k], n = S.cnt[c];
+            S.off[c] = o;
+            const bool near_c = c >= 7;
+            const bool c0 = near_c || c >= 5 || n < kTabMin;  // evaluated in the mixed phase C0
+            if (n > 0 && c0) {
+              S.qcls[nq] = c;
+              S.qfirst[nq] = nb;
+              nb += near_c ? (n + 1) / 2 : (n + 31) / 32;
+              nq++;
+            }
+            o += near_c ? ((n + 1) & ~1) : ((n + 31) & ~31);
+            if (!near_c) {
+              fp += n;
+              ev += (unsigned long long)n * c_cls_np[c] * c_cls_np[c];
+            }
+          }
+          S.qfirst[nq] = nb;
+          S.qn = nq;
+          S.qhead = 0;
+          st_far += fp;
+          st_eval += ev;
+        }
+        __syncthreads();
+        {
+#pragma unroll 1
+          for (int m = 0; m < kCH / 8; m++) {
+            const int cls = (int)((mycls >> (4 * m)) & 15u) - 1;
+            const unsigned grp = __match_any_sync(0xffffffffu, cls);
+            int base = 0;
+            const int leader = __ffs(grp) - 1;
+            if (cls >= 0 && lane == leader) base = atomicAdd(&S.fill[cls], __popc(grp));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (cls >= 0) {
+              const int c1 = (warp >> 1) + 8 * m, c2 = lane + 32 * (warp & 1);
+              S.list[S.off[cls] + base + __popc(grp & ((1u << lane) - 1u))] = (unsigned short)(c1 * kCH + c2);
             }
           }
         }
         __syncthreads();
-        // ---------------- phase 2: near field (one warp per pair, lanes over points) ----------
+        // ---------------- phase C0: near pairs + far pairs evaluated from the vertices ---------------
         {
-          const int nn = S.near_count;
-          for (int k = warp; k < nn; k += NW) {
-            const unsigned e = S.near_list[k];
-            const int c1 = e & 63, c2 = (e >> 6) & 63, iq = (e >> 12) & 31;
-            if (e & (1u << 17)) {
-              double v = near_pair(S.gI, S.nI, c1, S.gJ, c2, iq, lane);
-              if (lane == 0) S.T1[c1 * kCH + c2] = v;
-              st_near += (lane == 0);
-              st_phi += (lane == 0) ? c_qnp[iq] : 0;
-            }
-            if (e & (1u << 18)) {
-              double v = near_pair(S.gJ, S.nJ, c2, S.gI, c1, iq, lane);
-              if (lane == 0) S.T2[c1 * kCH + c2] = v;
-              st_near += (lane == 0);
-              st_phi += (lane == 0) ? c_qnp[iq] : 0;
+          const int nq = S.qn, total = S.qfirst[nq];
+          for (;;) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(&S.qhead, 1);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b >= total) break;
+            int k = 0;
+            while (b >= S.qfirst[k + 1]) k++;
+            const int cls = S.qcls[k], lb = b - S.qfirst[k];
+            run_batch_c0(S, cls, S.off[cls] + lb * (cls >= 7 ? 2 : 32), lane, false, st_near, st_phi);
+          }
+        }
+        // ---------------- phase C1: far rules with point tables, one rule at a time ------------------
+#pragma unroll 1
+        for (int cls = 4; cls >= 0; cls--) {
+          const int n = S.cnt[cls];  // uniform over the CTA
+          if (n < kTabMin) continue;
+          __syncthreads();           // previous users of the table region are done
+          const int np = c_cls_np[cls];
+          build_table(S.w.tab.tabI, S.gI, ncI, cls + 4, np, ox, oy, oz, true, tid, NT);
+          build_table(S.w.tab.tabJ, S.gJ, ncJ, cls + 4, np, ox, oy, oz, false, tid, NT);
+          if (tid == 0) S.qhead = 0;
+          __syncthreads();
+          const int nb = (n + 31) / 32, first = S.off[cls];
+          for (;;) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(&S.qhead, 1);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b >= nb) break;
+            const unsigned e = S.list[first + b * 32 + lane];
+            if (e != 0xFFFFu) {
+              const int c1 = e >> 6, c2 = e & 63;
+              S.T[c1 * TS + c2] = far_tab_dispatch(S.w.tab.tabI, S.w.tab.tabJ, c1, c2, cls) * S.gI[9 * kCH + c1] * S.gJ[9 * kCH + c2];
             }
           }
         }
-        __syncthreads();
-        // ---------------- phase 3: contraction onto DOFs, owner writes -------------------------
-        {
-          const int nent = ndI * ndJ;
-          for (int e = tid; e < nent; e += NT) {
-            const int ia = e / ndJ, ib = e - ia * ndJ;
-            const int da = S.dofI[ia], db = S.dofJ[ib];
-            const int oa = A.dof_origA[da], ob = A.dof_origB[db];
-            bool role1 = true;
-            if (A.self) {
-              role1 = (oa <= ob);
-              if (diag && !role1) continue;
+        // ---------------- phase D: contraction onto DOFs (two passes when both roles are needed) ------
+        const bool two_pass = S.both_count > 0;  // written before the phase-A barrier
+        for (int pass = 0; pass < (two_pass ? 2 : 1); pass++) {
+          __syncthreads();  // T complete (and the table region free for U)
+          if (pass == 1) {
+            // role-2 values of the near pairs that need both roles
+            if (tid == 0) S.qhead = 0;
+            __syncthreads();
+            int nearb = 0, first_cls_off[5], first_cls_nb[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+              first_cls_off[k] = S.off[11 - k];
+              first_cls_nb[k] = (S.cnt[11 - k] + 1) / 2;
+              nearb += first_cls_nb[k];
             }
-            const double* T = role1 ? S.T1 : S.T2;
-            double acc = 0.0;
-            for (int i1 = S.iptrI[ia]; i1 < S.iptrI[ia + 1]; i1++) {
-              const unsigned w1 = S.incI[i1];
-              const int c1 = w1 & 63, k1 = (w1 >> 6) & 3;
-              const double e1x = S.gI[(10 + 3 * k1) * kCH + c1], e1y = S.gI[(11 + 3 * k1) * kCH + c1],
-                           e1z = S.gI[(12 + 3 * k1) * kCH + c1];
+            for (;;) {
+              int b = 0;
+              if (lane == 0) b = atomicAdd(&S.qhead, 1);
+              b = __shfl_sync(0xffffffffu, b, 0);
+              if (b >= nearb) break;
+              int k = 0, lb = b;
+              while (lb >= first_cls_nb[k]) {
+                lb -= first_cls_nb[k];
+                k++;
+              }
+              run_batch_c0(S, 11 - k, first_cls_off[k] + lb * 2, lane, true, st_near, st_phi);
+            }
+            __syncthreads();
+          }
+          for (int b0 = 0; b0 < ndJ; b0 += UB) {
+            const int nb = min(UB, ndJ - b0);
+            if (b0 > 0) __syncthreads();  // stage 2 of the previous block finished with U
+            // stage 1: U[c1][b] = sum_{(c2,k2) of b} +-E2[c2][k2] T[c1][c2]; lanes over c1
+            for (int it = tid; it < nb * kCH; it += NT) {
+              const int bl = it >> 6, c1 = it & 63;
               double ux = 0.0, uy = 0.0, uz = 0.0;
+              const int ib = b0 + bl;
               for (int i2 = S.iptrJ[ib]; i2 < S.iptrJ[ib + 1]; i2++) {
                 const unsigned w2 = S.incJ[i2];
                 const int c2 = w2 & 63, k2 = (w2 >> 6) & 3;
-                double tv = T[c1 * kCH + c2];
+                double tv = S.T[c1 * TS + c2];
                 if (w2 & 256) tv = -tv;
                 ux = fma(S.gJ[(10 + 3 * k2) * kCH + c2], tv, ux);
                 uy = fma(S.gJ[(11 + 3 * k2) * kCH + c2], tv, uy);
                 uz = fma(S.gJ[(12 + 3 * k2) * kCH + c2], tv, uz);
               }
-              double dsum = e1x * ux + e1y * uy + e1z * uz;
-              acc += (w1 & 256) ? -dsum : dsum;
+              S.w.U[(0 * kCH + c1) * US + bl] = ux;
+              S.w.U[(1 * kCH + c1) * US + bl] = uy;
+              S.w.U[(2 * kCH + c1) * US + bl] = uz;
             }
-            acc *= A.scale;
-            const int ra = A.row_out[da];
-            if (ra >= 0) A.out[(long long)ra * A.ld + ob] += acc;
-            if (A.self && (mirror || diag) && oa != ob) {
-              const int rb = A.row_out[db];
-              if (rb >= 0) A.out[(long long)rb * A.ld + oa] += acc;
+            __syncthreads();
+            // stage 2: L[a][b] += sum_{(c1,k1) of a} +-E1[c1][k1] . U[c1][b]; lanes over b
+            for (int it = tid; it < ndI * UB; it += NT) {
+              const int ia = it >> 5, bl = it & 31;
+              if (bl >= nb) continue;
+              const int ib = b0 + bl;
+              const int oa = S.origI[ia], ob = S.origJ[ib];
+              if (A.self) {
+                const bool role1 = oa <= ob;
+                if (diag && !role1) continue;
+                if (two_pass && role1 != (pass == 0)) continue;
+              }
+              double acc = 0.0;
+              for (int i1 = S.iptrI[ia]; i1 < S.iptrI[ia + 1]; i1++) {
+                const unsigned w1 = S.incI[i1];
+                const int c1 = w1 & 63, k1 = (w1 >> 6) & 3;
+                double dsum = S.gI[(10 + 3 * k1) * kCH + c1] * S.w.U[(0 * kCH + c1) * US + bl];
+                dsum = fma(S.gI[(11 + 3 * k1) * kCH + c1], S.w.U[(1 * kCH + c1) * US + bl], dsum);
+                dsum = fma(S.gI[(12 + 3 * k1) * kCH + c1], S.w.U[(2 * kCH + c1) * US + bl], dsum);
+                acc += (w1 & 256) ? -dsum : dsum;
+              }
+              acc *= A.scale;
+              const int ra = S.rowI[ia];
+              if (ra >= 0) A.out[(long long)ra * A.ld + ob] += acc;
+              if (A.self && (mirror || diag) && oa != ob) {
+                const int rb = S.rowJ[ib];
+                if (rb >= 0) A.out[(long long)rb * A.ld + oa] += acc;
+              }
             }
           }
         }
@@ -370,14 +701,12 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {
     }
   }
   if (A.stats) {
-    st_far = warp_sum((double)st_far);  // counts are < 2^53
-    st_near = warp_sum((double)st_near);
-    st_eval = warp_sum((double)st_eval);
-    st_phi = warp_sum((double)st_phi);
+    st_near = (unsigned long long)warp_sum((double)st_near);  // counts are < 2^53
+    st_phi = (unsigned long long)warp_sum((double)st_phi);
     if (lane == 0) {
-      atomicAdd(&A.stats[0], st_far);
+      if (st_far) atomicAdd(&A.stats[0], st_far);
       atomicAdd(&A.stats[1], st_near);
-      atomicAdd(&A.stats[2], st_eval);
+      if (st_eval) atomicAdd(&A.stats[2], st_eval);
       atomicAdd(&A.stats[3], st_phi);
     }
   }
@@ -395,6 +724,10 @@ namespace tw {
     cudaError_t e_ = (call);                                                                         \
     if (e_ != cudaSuccess) return std::string(#call) + ": " + cudaGetErrorString(e_);                \
   } while (0)
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(); }
 
 template <class T>
 static std::string upload(const std::vector<T>& h, T** d) {
@@ -433,10 +766,13 @@ std::string gpu_init_constants() {
   CK(cudaMemcpyToSymbol(twk::g_qpts, TCQ_PTS, sizeof(TCQ_PTS)));
   CK(cudaMemcpyToSymbol(twk::g_qwts, TCQ_WTS, sizeof(TCQ_WTS)));
   double thr[14], thr2[14];
+  float thr2f[14];
   for (int k = 5; k <= 18; k++) {
     thr[k - 5] = order_threshold(k);
     thr2[k - 5] = thr[k - 5] * thr[k - 5];
+    thr2f[k - 5] = (float)thr2[k - 5];
   }
+  CK(cudaMemcpyToSymbol(twk::c_thr2f, thr2f, sizeof(thr2f)));
   CK(cudaMemcpyToSymbol(twk::c_thr, thr, sizeof(thr)));
   CK(cudaMemcpyToSymbol(twk::c_thr2, thr2, sizeof(thr2)));
   CK(cudaFuncSetAttribute(twk::lmat_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(twk::Smem)));
@@ -456,6 +792,8 @@ std::string DevicePatchSet::upload_from(const PatchSet& ps) {
   if (!(e = upload(ps.inc, &inc)).empty()) return e;
   if (!(e = upload(ps.patch_chunk_ptr, &patch_chunk_ptr)).empty()) return e;
   if (!(e = upload(ps.dof_orig, &dof_orig)).empty()) return e;
+  bytes = ps.chunks.size() * sizeof(ChunkMeta) + ps.geom.size() * 8 + (ps.cell_dmin.size() + ps.cell_dmax.size()) * 4 +
+          (ps.chunk_dof.size() + ps.chunk_inc_ptr.size() + ps.patch_chunk_ptr.size() + ps.dof_orig.size()) * 4 + ps.inc.size() * 2;
   return "";
 }
 void DevicePatchSet::release() {
@@ -516,6 +854,7 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   int grid = (int)std::min<size_t>(tiles.size(), (size_t)nsm);
   twk::lmat_tile_kernel<<<grid, twk::NT, sizeof(twk::Smem), stream>>>(a);
   CK(cudaGetLastError());
+  note_launch();
   if (h_stats) {
     CK(cudaMemcpyAsync(h_stats, d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));

@@ -642,11 +642,13 @@ std::string elem_sets_coupling(const Model& m, const FlatCoils& fc, bool use_reg
                                                             dc.fil_ptr.p, dc.pts.p, dc.scales.p, nrad_cross ? dc.radius.p : nullptr,
                                                             dc.fil_set.p, cf.p, nrad_cross ? ncross.p : nullptr);
   CKO(cudaGetLastError());
+  note_launch();
   const int nd = m.np_active + m.nholes;
   const long long nt = (long long)nd * dc.nsets;
   twk::dof_gather_kernel<<<(unsigned)((nt + 255) / 256), 256>>>(nd, dc.nsets, dc.nfil, kdi_d.p, ldi_d.p, dc.set_ptr.p, cf.p, d_out,
                                                                  stride_dof, stride_set, set_scale ? sscale.p : nullptr);
   CKO(cudaGetLastError());
+  note_launch();
   CKO(cudaDeviceSynchronize());
   if (nrad_cross) {
     nrad_cross->resize(dc.nsets);
@@ -668,6 +670,7 @@ std::string filament_mutual(const FlatCoils& rows, const FlatCoils& cols, bool r
                                                                     dr.scales.p, dr.radius.p, dcn.set_ptr.p, dcn.fil_ptr.p, dcn.pts.p,
                                                                     dcn.scales.p, dcn.mask.p, regularize ? 1 : 0, d.p);
   CKO(cudaGetLastError());
+  note_launch();
   CKO(cudaMemcpy(out.data(), d.p, out.size() * 8, cudaMemcpyDeviceToHost));
   return "";
 }
@@ -780,6 +783,7 @@ std::string gpu_fill_vcoil_block(const Model& m, const std::vector<int>& row_ids
   twk::vcoil_fill_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, stream>>>((int)row_ids.size(), d_rows, ns, nv, m.nelems, d_a2c, d_c2c,
                                                                             d_out, ld, 1.0 / (4.0 * kPi));
   CKO(cudaGetLastError());
+  note_launch();
   CKO(cudaStreamSynchronize(stream));  // host staging buffers above are reused by the caller
   CKO(cudaFreeAsync(d_rows, stream));
   CKO(cudaFreeAsync(d_a2c, stream));
@@ -838,6 +842,7 @@ std::string bel_shard_device(Model& m, int nshards, int shard, double* d_out, cu
   if (nitems > 0) {
     twk::bel_tile_kernel<<<(unsigned)std::min<long long>(nitems, nsm), twk::BNT, sizeof(twk::BelSmem), stream>>>(a);
     CKO(cudaGetLastError());
+  note_launch();
   }
   // V-coil rows (last shard): filament Biot-Savart, scaled with the rest by 1/4pi
   if (shard == nshards - 1 && m.n_vcoils > 0) {
@@ -851,6 +856,7 @@ std::string bel_shard_device(Model& m, int nshards, int shard, double* d_out, cu
                                                                                    dc.pts.p, dc.scales.p, dc.mask.p, d_out + off, nrows, 1,
                                                                                    (long long)m.np * nrows, 1.0 / (4.0 * kPi));
     CKO(cudaGetLastError());
+  note_launch();
     CKO(cudaStreamSynchronize(stream));
   }
   CKO(cudaStreamSynchronize(stream));
@@ -896,6 +902,7 @@ std::string gpu_bmat(Model& m) {
                                                                         dc.scales.p, dc.mask.p, d.p, 1, (long long)np,
                                                                         (long long)np * m.n_icoils, kMu0 / (4.0 * kPi));
     CKO(cudaGetLastError());
+  note_launch();
     CKO(cudaMemcpy(m.Bdr.p, d.p, 3 * np * m.n_icoils * 8, cudaMemcpyDeviceToHost));
   }
   return "";
@@ -950,6 +957,7 @@ std::string gpu_pair_stats(Model& m, int64_t* hist, int64_t* visited) {
   if (!(e = d_hist.zeros(19)).empty()) return e;
   twk::pair_stats_kernel<<<m.nc, 256>>>(m.nc, ca.P.p, ca.A.p, d_imin.p, d_jmax.p, d_hist.p);
   CKO(cudaGetLastError());
+  note_launch();
   unsigned long long h[19];
   CKO(cudaMemcpy(h, d_hist.p, sizeof h, cudaMemcpyDeviceToHost));
   int64_t tot = 0;

@@ -149,6 +149,27 @@ std::string build_patches(const Model& m, int P, PatchSet& ps) {
         ps.geom[g0 + (size_t)9 * kCH + s] = m.ca[c];
         for (int d = 0; d < 3; d++) ps.geom[g0 + (size_t)(19 + d) * kCH + s] = m.norm[3 * (size_t)c + d];
       }
+      {
+        double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+        for (int s = 0; s < cm.ncell; s++)
+          for (int k = 0; k < 3; k++)
+            for (int d = 0; d < 3; d++) {
+              double v = ps.geom[g0 + (size_t)(k * 3 + d) * kCH + s];
+              mn[d] = std::min(mn[d], v);
+              mx[d] = std::max(mx[d], v);
+            }
+        cm.cx = 0.5 * (mn[0] + mx[0]);
+        cm.cy = 0.5 * (mn[1] + mx[1]);
+        cm.cz = 0.5 * (mn[2] + mx[2]);
+        double r2 = 0.0;
+        for (int s = 0; s < cm.ncell; s++)
+          for (int k = 0; k < 3; k++) {
+            double dx = ps.geom[g0 + (size_t)(k * 3) * kCH + s] - cm.cx, dy = ps.geom[g0 + (size_t)(k * 3 + 1) * kCH + s] - cm.cy,
+                   dz = ps.geom[g0 + (size_t)(k * 3 + 2) * kCH + s] - cm.cz;
+            r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+          }
+        cm.rad = std::sqrt(r2) * (1.0 + 1e-12);
+      }
       auto& L = by_chunk[ch];
       std::stable_sort(L.begin(), L.end(), [](const Inc& a, const Inc& b) { return a.dof_local < b.dof_local; });
       std::vector<int> ptr;

@@ -25,6 +25,8 @@ struct ChunkMeta {
   int ndof;     // DOFs that have an incidence in this chunk
   int dof_off;  // offset of this chunk's DOF list (chunk_dof / inc_ptr(+chunk id))
   int inc_off;  // offset of this chunk's incidence list
+  double cx, cy, cz;  // centre of the bounding box of the chunk's vertices
+  double rad;         // radius of the bounding sphere around that centre
 };
 
 // Patch decomposition of ONE model (row or column side).

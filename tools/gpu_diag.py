@@ -30,7 +30,10 @@ Pi, Pj = np.ascontiguousarray(P[ci]), np.ascontiguousarray(P[cj])
 Ai, Aj = np.ascontiguousarray(O.ca[ci]), np.ascontiguousarray(O.ca[cj])
 n = len(ci)
 Tg = np.zeros(n); qg = np.zeros(n, np.int32); To = np.zeros(n); qo = np.zeros(n, np.int32)
-assert I.b200_probe_pairs(n, Pi, Ai, Pj, Aj, Tg, qg) == 0
+mode = int(os.environ.get('PROBE_MODE', '1'))
+assert I.b200_probe_pairs(n, mode, Pi, Ai, Pj, Aj, Tg, qg) == 0
+print('probe mode', mode, 'exact-path fraction %.2e' % ((qg & 64) != 0).mean())
+qg = qg & 31
 L = tw.lib()
 L.tco_pair_T_batch(n, Pi.ctypes.data_as(ctypes.c_void_p), Ai.ctypes.data_as(ctypes.c_void_p), Pj.ctypes.data_as(ctypes.c_void_p),
                    Aj.ctypes.data_as(ctypes.c_void_p), To.ctypes.data_as(ctypes.c_void_p), qo.ctypes.data_as(ctypes.c_void_p))
