@@ -263,7 +263,8 @@ def main():
                 'traffic': None, 'peak_source': 'DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
                 'algorithmic_flops_per_step': flops_total * share, 'flops_per_pair': flops_total / visited,
                 'hbm_write_GBps': nrows * N * 8 / (kern_ms * 1e-3) / 1e9, 'kernel': 'lmat_tile_kernel',
-                'kernel_ms': kern_ms, 'device_evals': {'far_pairs': int(st[0]), 'near_T': int(st[1]), 'inv_r': int(st[2]), 'phipot': int(st[3])}}
+                'kernel_ms': kern_ms, 'cta_finish_spread': {'first_ms': (int(st[7]) - int(st[6])) * 1e-6, 'last_ms': (int(st[4]) - int(st[6])) * 1e-6},
+                'device_evals': {'far_pairs': int(st[0]), 'near_T': int(st[1]), 'inv_r': int(st[2]), 'phipot': int(st[3])}}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         v, nthreads, desc, _ = cpu_sample(mesh)
@@ -274,7 +275,7 @@ def main():
             'config': {'workload': workload_name(mesh, args), 'np': int(mesh['r'].shape[0]), 'nc': int(mesh['lc'].shape[0]),
                        'nelems': int(N), 'visited_pairs': int(visited), 'nc2_pairs': int(mesh['lc'].shape[0]) ** 2,
                        'order_hist': {str(q): int(hist[q]) for q in range(4, 19)}, 'sharding': 'row blocks, %d shard(s), no collective' % world,
-                       'l2': 'flushed every step by the %.1f GB output memset' % (nrows * N * 8 / 1e9)},
+                       'l2': 'flushed every step by the %.1f GB output memset' % (nrows * N * 8 / 1e9), 'plan': T.plan_info()},
             'wall_ms_per_step': ms_wall / args.steps, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'roofline': roofline, 'cpu_baseline': cpu}
     print(json.dumps(line), flush=True)

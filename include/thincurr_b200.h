@@ -89,6 +89,20 @@ int thincurr_b200_setup(int np, const double* r, int nc, const int* lc, const in
                         int nnodesets, const int* nodeset_ptr, const int* nodeset_val, int nclosures,
                         const int* closures, void* xml_ptr, void** tw_ptr, int* sizes);
 
+/* Model from the arrays a Fortran host already holds in its tw_type (thin_wall.F90:111-154), i.e.
+ * what tw_compute_LmatDirect reads: r(3,np), lc(3,nc) AFTER orientation sync (1-based), reg(nc) or
+ * NULL, pmap(np) (1-based DOF id, 0 = inactive), np_active, nholes, the hole CSR kfh(nc+1) (1-based
+ * Fortran offsets) / lfh(2,nfh) = (signed hole id, 1-based local vertex), and optionally the host's
+ * own ca(nc) / qbasis(3,3,nc) (NULL = recomputed with the reference formulas).  No setup work
+ * (orientation sync, holes, DOF map) is repeated. */
+int thincurr_b200_model_from_tw(int np, const double* r, int nc, const int* lc, const int* reg, const int* pmap,
+                                int np_active, int nholes, const int* kfh, const int* lfh, const double* ca,
+                                const double* qbasis, void** tw_ptr);
+
+/* Drop-in for tw_compute_LmatDirect(self, Lmat) (thin_wall.F90:887-1186): the full self-inductance
+ * matrix into CALLER-owned host memory Lmat(nelems,nelems), rows sharded over all visible devices. */
+int thincurr_b200_Lmat_host(void* tw_ptr, double* Lmat);
+
 /* Coil sets / sensors from memory (alternative to XML / floops.loc).  kind: 0 = Vcoil, 1 = Icoil.
  * set_ptr[nsets+1] -> filament ranges; fil_ptr[nfil+1] -> point ranges into pts[][3]. */
 int thincurr_b200_set_coils(void* tw_ptr, int kind, int nsets, const int* set_ptr, const int* fil_ptr,

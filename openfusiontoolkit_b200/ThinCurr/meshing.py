@@ -78,7 +78,7 @@ def build_torus_vessel(ntheta, nphi, R0=1.0, a=0.5, kappa=1.0, nports=0, jitter=
     nodesets = [new_id[numpy.array(pol)], new_id[numpy.array(tor)]]
     for k in range(nports):
         jc = int((k + 0.5) * nphi / nports)
-        nodesets.append(new_id[numpy.array([vid(-(pw_t // 2), jc)])])  # a vertex on the port rim
+        nodesets.append(new_id[numpy.array([vid(-pw_t // 2, jc)])])  # a vertex on the port rim (first removed row)
     r = r[used]
     lc = new_id[lc].astype(numpy.int32)
     closures = numpy.array([lc.shape[0] // 2], dtype=numpy.int32)

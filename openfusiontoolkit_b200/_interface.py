@@ -99,3 +99,6 @@ b200_probe_phipot = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_phipot, [c_i
 b200_probe_rsqrt = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_rsqrt, [c_int, _f64, _f64], c_int)
 b200_launch_count = ctypes_subroutine(oftpy_lib.thincurr_b200_launch_count, [], ctypes.c_longlong)
 b200_plan_info = ctypes_subroutine(oftpy_lib.thincurr_b200_plan_info, [c_void_p, numpy.ctypeslib.ndpointer(dtype=numpy.int64, flags='C_CONTIGUOUS')], c_int)
+b200_model_from_tw = ctypes_subroutine(oftpy_lib.thincurr_b200_model_from_tw,
+    [c_int, _f64, c_int, _i32, c_void_p, _i32, c_int, c_int, _i32, c_void_p, c_void_p, c_void_p, c_void_ptr_ptr], c_int)
+b200_Lmat_host = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_host, [c_void_p, _f64], c_int)

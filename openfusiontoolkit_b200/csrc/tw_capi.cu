@@ -260,25 +260,14 @@ void thincurr_setup(const char* mesh_file, int np, const double* r_loc, int nc, 
   fill_sizes(*m, sizes);
 }
 
-void thincurr_Lmat(void* tw_ptr, bool use_hodlr, void** Lmat_ptr, const char* cache_file, char* error_str) {
-  Model& m = *(Model*)tw_ptr;
-  if (m.n_vcoils > 0 && !m.have_coil_mutuals) return set_err(error_str, "Coil mutuals required if, # of Vcoils > 0");
-  set_err(error_str, "");
-  if (use_hodlr) return set_err(error_str, "HODLR compression is not provided by the B200 dense backend");
-  std::string cache = cstr(cache_file);
+// full self-inductance matrix into host memory dst[nelems][nelems] (reference layout), rows sharded
+// over all visible devices, each shard copied straight to its place
+static std::string lmat_full_host(Model& m, double* dst) {
   const size_t N = (size_t)m.nelems;
-  if (!cache.empty() && cache != "none" && lmat_cache_read(m, cache)) {
-    *Lmat_ptr = m.Lmat.p;
-    return;
-  }
-  std::printf(" Building element<->element self inductance matrix\n");
-  auto t0 = std::chrono::steady_clock::now();
   int ndev = visible_devices();
-  if (ndev < 1) return set_err(error_str, "No CUDA device available (the B200 backend has no CPU fallback)");
-  m.Lmat.alloc(N * N, false);  // every entry is overwritten by the device->host copies
-  if (!m.Lmat.p) return set_err(error_str, "Host allocation of the inductance matrix failed");
+  if (ndev < 1) return "No CUDA device available (the B200 backend has no CPU fallback)";
   std::string err = ensure_plan(m);
-  if (!err.empty()) return set_err(error_str, err);
+  if (!err.empty()) return err;
   ndev = std::min(ndev, std::max(1, m.plan->ps.npatch));
   struct Dev {
     double* d = nullptr;
@@ -300,7 +289,7 @@ void thincurr_Lmat(void* tw_ptr, bool use_hodlr, void** Lmat_ptr, const char* ca
     for (size_t r = 0; r < devs[g].rows.size() && err.empty();) {
       size_t r1 = r + 1;
       while (r1 < devs[g].rows.size() && devs[g].rows[r1] == devs[g].rows[r1 - 1] + 1) r1++;
-      if (cudaMemcpyAsync(m.Lmat.p + (size_t)devs[g].rows[r] * N, devs[g].d + r * N, (r1 - r) * N * 8, cudaMemcpyDeviceToHost,
+      if (cudaMemcpyAsync(dst + (size_t)devs[g].rows[r] * N, devs[g].d + r * N, (r1 - r) * N * 8, cudaMemcpyDeviceToHost,
                           devs[g].s) != cudaSuccess)
         err = std::string("Device->host copy failed: ") + cudaGetErrorString(cudaGetLastError());
       r = r1;
@@ -316,6 +305,26 @@ void thincurr_Lmat(void* tw_ptr, bool use_hodlr, void** Lmat_ptr, const char* ca
     if (devs[g].d) cudaFree(devs[g].d);
   }
   cudaSetDevice(0);
+  return err;
+}
+
+void thincurr_Lmat(void* tw_ptr, bool use_hodlr, void** Lmat_ptr, const char* cache_file, char* error_str) {
+  Model& m = *(Model*)tw_ptr;
+  if (m.n_vcoils > 0 && !m.have_coil_mutuals) return set_err(error_str, "Coil mutuals required if, # of Vcoils > 0");
+  set_err(error_str, "");
+  if (use_hodlr) return set_err(error_str, "HODLR compression is not provided by the B200 dense backend");
+  std::string cache = cstr(cache_file);
+  const size_t N = (size_t)m.nelems;
+  if (!cache.empty() && cache != "none" && lmat_cache_read(m, cache)) {
+    *Lmat_ptr = m.Lmat.p;
+    return;
+  }
+  std::printf(" Building element<->element self inductance matrix\n");
+  auto t0 = std::chrono::steady_clock::now();
+  if (visible_devices() < 1) return set_err(error_str, "No CUDA device available (the B200 backend has no CPU fallback)");
+  m.Lmat.alloc(N * N, false);  // every entry is overwritten by the device->host copies
+  if (!m.Lmat.p) return set_err(error_str, "Host allocation of the inductance matrix failed");
+  std::string err = lmat_full_host(m, m.Lmat.p);
   if (!err.empty()) return set_err(error_str, err);
   double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   std::printf("   Time = %s\n", time_to_string(el).c_str());
@@ -473,6 +482,27 @@ int thincurr_b200_setup(int np, const double* r, int nc, const int* lc, const in
   }
   *tw_ptr = m;
   if (sizes) fill_sizes(*m, sizes);
+  return 0;
+}
+
+int thincurr_b200_model_from_tw(int np, const double* r, int nc, const int* lc, const int* reg, const int* pmap, int np_active,
+                                int nholes, const int* kfh, const int* lfh, const double* ca, const double* qbasis,
+                                void** tw_ptr) {
+  auto* m = new Model();
+  std::string err = m->setup_from_tw(np, r, nc, lc, reg, pmap, np_active, nholes, kfh, lfh, ca, qbasis);
+  if (!err.empty()) {
+    delete m;
+    return fail(err);
+  }
+  *tw_ptr = m;
+  return 0;
+}
+
+int thincurr_b200_Lmat_host(void* tw_ptr, double* Lmat) {
+  Model& m = *(Model*)tw_ptr;
+  if (m.n_vcoils > 0 && !m.have_coil_mutuals) return fail("Coil mutuals required if, # of Vcoils > 0");
+  std::string err = lmat_full_host(m, Lmat);
+  if (!err.empty()) return fail(err);
   return 0;
 }
 

@@ -87,6 +87,7 @@ struct Model {
   std::vector<int> kpe, lpe;   // point -> edges (ascending edge id)
   std::vector<char> be, bp;    // boundary edge / point flags
   int nflipped = 0;
+  bool keep_orientation = false;  // skip the orientation sync (cells come from a host that already ran it)
   // ---- DOFs ----
   int np_active = 0, nholes = 0, n_vcoils = 0, n_icoils = 0, nelems = 0, nfh = 0;
   std::vector<int> pmap;       // [np] 1-based DOF id, 0 = inactive
@@ -113,6 +114,11 @@ struct Model {
   std::string setup_from_arrays(int np_, const double* r_, int nc_, const int* lc1, const int* reg_,
                                 const int* pmap_in, const std::vector<std::vector<int>>& nodesets0,
                                 const std::vector<int>& closure_cells0, const XmlNode* thincurr_xml);
+  // model from the arrays a Fortran host already holds in tw_type (oriented lc, pmap, hole CSR):
+  // no orientation sync, no hole / DOF construction (thin_wall.F90:111-154)
+  std::string setup_from_tw(int np_, const double* r_, int nc_, const int* lc1, const int* reg_, const int* pmap1,
+                            int np_active_, int nholes_, const int* kfh1, const int* lfh1, const double* ca_,
+                            const double* qbasis_);
   std::string load_coils_xml(const XmlNode* group, const char* prefix, std::vector<CoilSet>& out);
   std::string load_eta_xml(const XmlNode* tc);
   void build_rmat();

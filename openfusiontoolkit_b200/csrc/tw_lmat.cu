@@ -29,6 +29,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -40,13 +41,21 @@ namespace twk {
 
 using tw::kCH;
 using tw::kGeomRows;
-constexpr int NT = 512;            // threads per CTA (16 warps), one CTA per SM
+#ifndef TW_LMAT_CTAS_PER_SM
+#define TW_LMAT_CTAS_PER_SM 1
+#endif
+constexpr int kCtasPerSM = TW_LMAT_CTAS_PER_SM;
+constexpr int NT = 512 / kCtasPerSM;  // threads per CTA
 constexpr int NW = NT / 32;
+constexpr int CI = kCH / kCtasPerSM;  // row cells per pass: a pass evaluates CI x kCH cell pairs
+constexpr int kGeomL = 19;         // geometry rows the L kernel stages (vertices, area, qbasis)
 constexpr int TS = kCH + 1;        // row stride of the T tile (bank-conflict-free column access)
 constexpr int NCLS = 12;           // far classes 0..6 (iquad 4..10), near classes 7..11 (28,33,46,55,72 points)
-constexpr int kListCap = kCH * kCH + NCLS * 32;
-constexpr int kTabMaxN = 16;       // largest rule served from shared-memory point tables
-constexpr int kTabMin = 96;        // fewer pairs of a rule than this: evaluate from the vertices instead
+constexpr int kListCap = CI * kCH + NCLS * 32;
+constexpr int kTabMaxN = kCtasPerSM == 1 ? 25 : 16;  // largest rule served from shared-memory point tables
+constexpr int kTabClsMax = kCtasPerSM == 1 ? 6 : 4;   // ... as a far class index
+constexpr int kTabPts = kCtasPerSM == 1 ? 34 : 16;    // points the table pool holds (several rules at once)
+constexpr int kTabMin = 64;        // fewer pairs of a rule than this: evaluate from the vertices instead
 constexpr int UB = 32, US = UB + 1;  // column-DOF block of the contraction and its padded stride
 
 __device__ __constant__ int c_cls_np[NCLS] = {6, 7, 12, 15, 16, 19, 25, 28, 33, 46, 55, 72};
@@ -72,35 +81,39 @@ struct LmatArgs {
   long long ld;
   double scale;                       // 1/(4 pi)
   int self;                           // 1: self inductance (role rule, mirror), 0: mutual
+  int debug_skip;                     // profiling aid: bit0 skip near-field evaluation, bit1 skip far-field evaluation
   unsigned long long* stats;          // [0] far pairs, [1] near T evaluations, [2] 1/r evaluations, [3] phipot evals
 };
 
 struct Smem {
-  double gI[kGeomRows * kCH];
-  double gJ[kGeomRows * kCH];
-  double T[kCH * TS];
+  double gI[kGeomL * kCH];
+  double gJ[kGeomL * kCH];
+  double T[CI * TS];
   union {
     struct {
-      double2 tabI[kTabMaxN * 2 * kCH];  // [(p*2+h)*64 + c]: h=0 (-2x,-2y), h=1 (-2z,|x|^2)
-      double2 tabJ[kTabMaxN * 2 * kCH];  //                   h=0 (x,y),     h=1 (z,|x|^2)
+      double2 tabI[kTabPts * 2 * CI];   // per rule [(p*2+h)*CI + c1]: h=0 (-2x,-2y), h=1 (-2z,|x|^2)
+      double2 tabJ[kTabPts * 2 * kCH];  //          [(p*2+h)*kCH + c2]: h=0 (x,y),    h=1 (z,|x|^2)
     } tab;
-    double U[3 * kCH * US];              // [comp][c1][b] partial sums of the contraction
+    double U[3 * CI * US];               // [comp][c1][b] partial sums of the contraction
+    struct {
+      float vfI[9 * CI], vfJ[9 * kCH];   // vertices in the local frame, FP32 (order screening)
+      float flI[CI], flJ[kCH];           // 2 * area
+    } scr;
   } w;
   double nI[3 * kCH];   // unit normals (reference formula) of row / column cells
   double nJ[3 * kCH];
-  float vfI[9 * kCH], vfJ[9 * kCH];  // vertices in the local frame, FP32 (order screening)
-  float flI[kCH], flJ[kCH];          // 2 * area
   unsigned short list[kListCap];     // pair ids (c1<<6|c2) sorted by class, bins padded with 0xFFFF
-  unsigned char iqmap[kCH * kCH];    // iquad | need-role-1 << 5 | need-role-2 << 6
+  unsigned char iqmap[CI * kCH];     // iquad | need-role-1 << 5 | need-role-2 << 6
   int dminI[kCH], dmaxI[kCH], dminJ[kCH], dmaxJ[kCH];
-  int dofI[tw::kMaxChunkDof], dofJ[tw::kMaxChunkDof];
   int origI[tw::kMaxChunkDof], origJ[tw::kMaxChunkDof];  // reference DOF ids
   int rowI[tw::kMaxChunkDof], rowJ[tw::kMaxChunkDof];    // output rows (or -1)
   int iptrI[tw::kMaxChunkDof + 1], iptrJ[tw::kMaxChunkDof + 1];
+  unsigned char hasI[tw::kMaxChunkDof];  // bit h: the DOF has a cell in row pass h of the chunk
   uint16_t incI[tw::kMaxChunkInc], incJ[tw::kMaxChunkInc];
   unsigned long long bar[2];
   int cnt[NCLS], off[NCLS + 1], fill[NCLS];
-  int qcls[NCLS], qfirst[NCLS + 1], qn;  // batch queue of phase C0
+  int qcls[NCLS + 8], qnb[NCLS + 8], qpt[NCLS + 8];  // work-queue items: class (| 16 = table), batches, table offset
+  int gq0[8], gq1[8], gnb[8], ng;                    // table groups: item range and batch count
   int qhead, both_count;
   int tile_id;
 };
@@ -167,12 +180,14 @@ __device__ __forceinline__ double far_dispatch(const double* gI, int c1, const d
 }
 
 // ---- far field from the shared-memory point tables ----------------------------------------------
-// 10 FP64-pipe instructions per 1/r: 1 add + 3 fma (d^2), 5 (rsqrt correction), 1 fma (weighted sum)
+// 10 FP64-pipe instructions per 1/r: 1 add + 3 fma (d^2), 5 (rsqrt correction), 1 fma (weighted sum).
+// The QB evaluations of one row point are advanced stage by stage so that QB independent
+// dependency chains are in flight (DFMA latency is 8 cycles, the pipe takes one warp every 2).
 template <int N, int OFF>
 __device__ __forceinline__ double far_tab(const double2* __restrict__ tabI, const double2* __restrict__ tabJ, int c1, int c2) {
+  // c1: row cell within the pass (stride CI), c2: column cell (stride kCH)
   const double* bw = c_qwts + OFF;  // OFF = TCQ_OFF[iquad]: weights become constant-bank operands
-  constexpr int NB = (N + 6) / 7;          // j-side register blocks of <= 7 points
-  constexpr int QB = (N + NB - 1) / NB;
+  constexpr int QB = (N == 6) ? 3 : ((N == 15 || N == 25) ? 5 : 4);  // j-side points held in registers
   double total = 0.0;
 #pragma unroll 1
   for (int q0 = 0; q0 < N; q0 += QB) {
@@ -187,15 +202,27 @@ __device__ __forceinline__ double far_tab(const double2* __restrict__ tabI, cons
       sj[q] = v.y;
       acc[q] = 0.0;
     }
-#pragma unroll(N <= 7 ? N : 3)
+#pragma unroll(N <= 7 ? N : 2)
     for (int p = 0; p < N; p++) {
-      const double2 a = tabI[(p * 2) * kCH + c1], b = tabI[(p * 2 + 1) * kCH + c1];
+      const double2 a = tabI[(p * 2) * CI + c1], b = tabI[(p * 2 + 1) * CI + c1];
       const double wp = bw[p];
+      double d2[QB], y0[QB], e[QB], h[QB];
 #pragma unroll
-      for (int q = 0; q < QB; q++) {
-        double d2 = fma(a.x, xj[q], fma(a.y, yj[q], fma(b.x, zj[q], b.y + sj[q])));
-        acc[q] = fma(wp, rsqrt_fast(d2), acc[q]);
-      }
+      for (int q = 0; q < QB; q++) d2[q] = fma(a.x, xj[q], fma(a.y, yj[q], fma(b.x, zj[q], b.y + sj[q])));
+#pragma unroll
+      for (int q = 0; q < QB; q++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[q]) : "d"(d2[q]));
+#pragma unroll
+      for (int q = 0; q < QB; q++) h[q] = d2[q] * y0[q];
+#pragma unroll
+      for (int q = 0; q < QB; q++) e[q] = fma(-h[q], y0[q], 1.0);
+#pragma unroll
+      for (int q = 0; q < QB; q++) h[q] = fma(0.375, e[q], 0.5);
+#pragma unroll
+      for (int q = 0; q < QB; q++) e[q] = e[q] * y0[q];
+#pragma unroll
+      for (int q = 0; q < QB; q++) y0[q] = fma(e[q], h[q], y0[q]);
+#pragma unroll
+      for (int q = 0; q < QB; q++) acc[q] = fma(wp, y0[q], acc[q]);
     }
 #pragma unroll
     for (int q = 0; q < QB; q++)
@@ -210,7 +237,9 @@ __device__ __forceinline__ double far_tab_dispatch(const double2* tabI, const do
     case 1: return far_tab<7, 13>(tabI, tabJ, c1, c2);
     case 2: return far_tab<12, 20>(tabI, tabJ, c1, c2);
     case 3: return far_tab<15, 32>(tabI, tabJ, c1, c2);
-    default: return far_tab<16, 47>(tabI, tabJ, c1, c2);
+    case 4: return far_tab<16, 47>(tabI, tabJ, c1, c2);
+    case 5: return far_tab<19, 63>(tabI, tabJ, c1, c2);
+    default: return far_tab<25, 82>(tabI, tabJ, c1, c2);
   }
 }
 
@@ -250,12 +279,12 @@ __device__ __forceinline__ double near_pair(const double* gA, const double* nA, 
 // vI/vJ: vertices in a common local frame rounded to FP32 (|v| <= X); delta = bound of the
 // coordinate error of a vertex DIFFERENCE (input rounding of both operands, = 2^-23 X * 1.01).
 // Returns iquad, or -1 when the decision is not safe in FP32.
-__device__ __forceinline__ int iquad_screen(const float* __restrict__ vI, int c1, const float* __restrict__ vJ, int c2, float fl2,
-                                            float delta) {
+__device__ __forceinline__ int iquad_screen(const float* __restrict__ vI, int sI, int c1, const float* __restrict__ vJ, int c2,
+                                            float fl2, float delta) {
   float pi_[9], pj_[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) {
-    pi_[k] = vI[k * kCH + c1];
+    pi_[k] = vI[k * sI + c1];
     pj_[k] = vJ[k * kCH + c2];
   }
   float d2min = 3.0e38f, d2max = 0.0f;
@@ -280,14 +309,16 @@ __device__ __forceinline__ int iquad_screen(const float* __restrict__ vI, int c1
   band = 1.5f * band + band * band;
   if (!(band < 0.25f)) return -1;
   const float r = d2min / d2max, rlo = r * (1.0f - band), rhi = r * (1.0f + band);
-  int nlo = 0, nhi = 0;
-#pragma unroll
-  for (int k = 0; k < 14; k++) {
-    const float t = c_thr2f[k];
-    nlo += (rhi <= t) ? 1 : 0;
-    nhi += (rlo <= t) ? 1 : 0;
-  }
-  return (nlo == nhi) ? 4 + nlo : -1;
+  // candidate from the reference expression in fast FP32, then verified against the exact
+  // decision boundaries (iquad >= k <=> rho^2 <= c_thr2f[k-5]) with the band on both sides
+  if (rlo > c_thr2f[0]) return 4;
+  const float qf = -18.420681f / __logf(1.0f - sqrtf(r));
+  int iq = (int)fminf(fmaxf(qf, 4.0f), 18.0f);
+  if (iq < 18 && rhi <= c_thr2f[iq - 4]) iq++;           // candidate one too low
+  else if (iq > 4 && rlo > c_thr2f[iq - 5]) iq--;         // candidate one too high
+  const bool lo_ok = (iq == 4) || (rhi <= c_thr2f[iq - 5]);  // surely iquad >= iq
+  const bool hi_ok = (iq == 18) || (rlo > c_thr2f[iq - 4]);  // surely iquad <  iq + 1
+  return (lo_ok && hi_ok) ? iq : -1;
 }
 
 __device__ __noinline__ int iquad_exact_cells(const double* gI, int c1, const double* gJ, int c2) {
@@ -324,25 +355,26 @@ __device__ __forceinline__ int classify_pair(const double* gI, int c1, const dou
   return iq;
 }
 
-// quadrature-point table of one chunk for one rule in the frame centred at (ox,oy,oz):
-// neg=true stores (-2x,-2y),(-2z,|x|^2) (row side), else (x,y),(z,|x|^2)
-__device__ __forceinline__ void build_table(double2* __restrict__ tab, const double* __restrict__ g, int ncell, int iquad, int n,
-                                            double ox, double oy, double oz, bool neg, int tid0, int nthreads) {
+// quadrature-point table of `ncell` cells (first cell c0 of the chunk record g) for one rule in the
+// frame centred at (ox,oy,oz); table stride `ts`.  neg=true stores (-2x,-2y),(-2z,|x|^2) (row side),
+// else (x,y),(z,|x|^2)
+__device__ __forceinline__ void build_table(double2* __restrict__ tab, int ts, const double* __restrict__ g, int c0, int ncell,
+                                            int iquad, int n, double ox, double oy, double oz, bool neg, int tid0, int nthreads) {
   const double* bp = c_qpts + 3 * c_qoff[iquad];
-  for (int it = tid0; it < n * kCH; it += nthreads) {
-    const int p = it / kCH, c = it - p * kCH;
-    if (c >= ncell) continue;
+  for (int it = tid0; it < n * ts; it += nthreads) {
+    const int p = it / ts, cl = it - p * ts, c = c0 + cl;
+    if (cl >= ncell) continue;
     const double b0 = bp[3 * p], b1 = bp[3 * p + 1], b2 = bp[3 * p + 2];
     const double x = (b0 * g[0 * kCH + c] + b1 * g[3 * kCH + c] + b2 * g[6 * kCH + c]) - ox;
     const double y = (b0 * g[1 * kCH + c] + b1 * g[4 * kCH + c] + b2 * g[7 * kCH + c]) - oy;
     const double z = (b0 * g[2 * kCH + c] + b1 * g[5 * kCH + c] + b2 * g[8 * kCH + c]) - oz;
     const double s2 = fma(z, z, fma(y, y, x * x));
     if (neg) {
-      tab[(p * 2) * kCH + c] = make_double2(-2.0 * x, -2.0 * y);
-      tab[(p * 2 + 1) * kCH + c] = make_double2(-2.0 * z, s2);
+      tab[(p * 2) * ts + cl] = make_double2(-2.0 * x, -2.0 * y);
+      tab[(p * 2 + 1) * ts + cl] = make_double2(-2.0 * z, s2);
     } else {
-      tab[(p * 2) * kCH + c] = make_double2(x, y);
-      tab[(p * 2 + 1) * kCH + c] = make_double2(z, s2);
+      tab[(p * 2) * ts + cl] = make_double2(x, y);
+      tab[(p * 2 + 1) * ts + cl] = make_double2(z, s2);
     }
   }
 }
@@ -357,8 +389,8 @@ __device__ __forceinline__ void load_chunk(Smem& S, int side, const LmatArgs& A,
   const tw::ChunkMeta cm = cms[chunk];
   if (threadIdx.x == 0) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order prior generic accesses before the async write
-    mbar_expect_tx(bar, kGeomRows * kCH * 8);
-    bulk_g2s(g, geom + (size_t)chunk * kGeomRows * kCH, kGeomRows * kCH * 8, bar);
+    mbar_expect_tx(bar, kGeomL * kCH * 8);
+    bulk_g2s(g, geom + (size_t)chunk * kGeomRows * kCH, kGeomL * kCH * 8, bar);
   }
   const int* dmn = (side ? A.dminB : A.dminA) + (size_t)chunk * kCH;
   const int* dmx = (side ? A.dmaxB : A.dmaxA) + (size_t)chunk * kCH;
@@ -368,7 +400,6 @@ __device__ __forceinline__ void load_chunk(Smem& S, int side, const LmatArgs& A,
   const int* dorig = side ? A.dof_origB : A.dof_origA;
   int* sdmn = side ? S.dminJ : S.dminI;
   int* sdmx = side ? S.dmaxJ : S.dmaxI;
-  int* sdof = side ? S.dofJ : S.dofI;
   int* sorig = side ? S.origJ : S.origI;
   int* srow = side ? S.rowJ : S.rowI;
   int* sptr = side ? S.iptrJ : S.iptrI;
@@ -379,7 +410,6 @@ __device__ __forceinline__ void load_chunk(Smem& S, int side, const LmatArgs& A,
   }
   for (int i = threadIdx.x; i < cm.ndof; i += NT) {
     const int d = cdof[i];
-    sdof[i] = d;
     sorig[i] = dorig[d];
     // rows of the column side exist only for self inductance (mirror writes)
     srow[i] = (side == 0 || A.self) ? A.row_out[d] : -1;
@@ -401,23 +431,24 @@ __device__ __forceinline__ void load_chunk(Smem& S, int side, const LmatArgs& A,
   }
 }
 
-// one batch of the work queue: 32 far pairs of one rule (from the vertices) or 2 near pairs
-__device__ __forceinline__ void run_batch_c0(Smem& S, int cls, int first, int lane, bool role2_pass, unsigned long long& st_near,
-                                             unsigned long long& st_phi) {
+// one batch of the work queue: 32 far pairs of one rule (from the vertices) or 2 near pairs.
+// List entries are (c1l<<6 | c2) with c1l the row cell within the pass; c1 = cbase + c1l.
+__device__ __forceinline__ void run_batch_c0(Smem& S, int cbase, int cls, int first, int lane, bool role2_pass,
+                                             unsigned long long& st_near, unsigned long long& st_phi) {
   if (cls < 7) {
     const unsigned e = S.list[first + lane];
     if (e != 0xFFFFu) {
-      const int c1 = e >> 6, c2 = e & 63;
-      S.T[c1 * TS + c2] = far_dispatch(S.gI, c1, S.gJ, c2, cls + 4);
+      const int c1l = e >> 6, c2 = e & 63;
+      S.T[c1l * TS + c2] = far_dispatch(S.gI, cbase + c1l, S.gJ, c2, cls + 4);
     }
   } else {
     const int hw = lane >> 4, hl = lane & 15;
     const unsigned e = S.list[first + hw];
     unsigned m = 0;
-    int c1 = 0, c2 = 0, iq = 18;
+    int c1l = 0, c2 = 0, iq = 18;
     if (e != 0xFFFFu) {
       m = S.iqmap[e];
-      c1 = e >> 6;
+      c1l = e >> 6;
       c2 = e & 63;
       iq = m & 31;
     }
@@ -427,10 +458,10 @@ __device__ __forceinline__ void run_batch_c0(Smem& S, int cls, int first, int la
     if (do1 || do2) {  // uniform per half-warp; the shuffles name only this half
       const unsigned mask = 0xFFFFu << (16 * hw);
       double v;
-      if (do2) v = near_pair(S.gJ, S.nJ, c2, S.gI, c1, iq, hl, 16, mask);
-      else v = near_pair(S.gI, S.nI, c1, S.gJ, c2, iq, hl, 16, mask);
+      if (do2) v = near_pair(S.gJ, S.nJ, c2, S.gI, cbase + c1l, iq, hl, 16, mask);
+      else v = near_pair(S.gI, S.nI, cbase + c1l, S.gJ, c2, iq, hl, 16, mask);
       if (hl == 0) {
-        S.T[c1 * TS + c2] = v;
+        S.T[c1l * TS + c2] = v;
         st_near++;
         st_phi += c_qnp[iq];
       }
@@ -438,7 +469,7 @@ __device__ __forceinline__ void run_batch_c0(Smem& S, int cls, int first, int la
   }
 }
 
-__global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {
+__global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -450,6 +481,11 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {
   __syncthreads();
   uint32_t phI = 0, phJ = 0;
   unsigned long long st_far = 0, st_near = 0, st_eval = 0, st_phi = 0;
+  if (A.stats && tid == 0 && blockIdx.x == 0) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    A.stats[6] = t0;
+  }
 
   for (;;) {
     if (tid == 0) S.tile_id = atomicAdd(A.tile_counter, 1);
@@ -467,6 +503,12 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {
       load_chunk(S, 0, A, ci, &S.bar[0], phI);
       const tw::ChunkMeta cmI = A.chunksA[ci];
       const int ncI = cmI.ncell, ndI = cmI.ndof;
+      __syncthreads();
+      for (int ia = tid; ia < ndI; ia += NT) {
+        unsigned hm = 0;
+        for (int i1 = S.iptrI[ia]; i1 < S.iptrI[ia + 1]; i1++) hm |= 1u << ((S.incI[i1] & 63) / CI);
+        S.hasI[ia] = (unsigned char)hm;
+      }
       for (int cj = cj0; cj < cj1; cj++) {
         __syncthreads();  // previous contraction finished with the J-side lists / T / U
         load_chunk(S, 1, A, cj, &S.bar[1], phJ);
@@ -480,225 +522,297 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {
           const double X = sqrt(hx * hx + hy * hy + hz * hz) + fmax(cmI.rad, cmJ.rad);
           delta = (float)(X * 1.21e-7);  // two operands, each rounded to FP32 (2^-24 relative), 1% slack
         }
-        // ---------------- phase A0: FP32 local-frame vertices, list reset ---------------------------
-        for (int i = tid; i < 9 * kCH; i += NT) {
-          const int k = i / kCH, d = k % 3;
-          const double o = d == 0 ? ox : (d == 1 ? oy : oz);
-          S.vfI[i] = (float)(S.gI[i] - o);
-          S.vfJ[i] = (float)(S.gJ[i] - o);
-        }
-        for (int i = tid; i < kCH; i += NT) {
-          S.flI[i] = (float)(2.0 * S.gI[9 * kCH + i]);
-          S.flJ[i] = (float)(2.0 * S.gJ[9 * kCH + i]);
-        }
-        for (int i = tid; i < kListCap; i += NT) S.list[i] = 0xFFFFu;
-        if (tid < NCLS) {
-          S.cnt[tid] = 0;
-          S.fill[tid] = 0;
-        }
-        if (tid == 0) S.both_count = 0;
-        __syncthreads();
-        // ---------------- phase A: classification ----------------------------------------------------
-        // warp w handles rows c1 = (w>>1) + 8m, columns lane + 32 (w&1)
-        unsigned mycls = 0;  // 4 bits per iteration: class + 1, 0 = no pair
-        {
-          const int c2 = lane + 32 * (warp & 1);
 #pragma unroll 1
-          for (int m = 0; m < kCH / 8; m++) {
-            const int c1 = (warp >> 1) + 8 * m;
-            unsigned code = 0;
-            int cls = -1;
-            if (c1 < ncI && c2 < ncJ) {
-              bool n1, n2 = false;
-              if (A.self) {
-                n1 = S.dminI[c1] <= S.dmaxJ[c2];
-                n2 = want2 && !diag && (S.dmaxI[c1] > S.dminJ[c2]);
-              } else {
-                n1 = true;
+        for (int cbase = 0; cbase < ncI; cbase += CI) {  // row cells [cbase, cbase + nI1) of the chunk
+          const int nI1 = min(CI, ncI - cbase);
+          if (cbase > 0) __syncthreads();  // previous pass finished with T / U / lists
+          // ---------------- phase A0: FP32 local-frame vertices, list reset ---------------------------
+          for (int i = tid; i < 9 * kCH; i += NT) {
+            const int k = i / kCH, d = k % 3;
+            const double o = d == 0 ? ox : (d == 1 ? oy : oz);
+            S.w.scr.vfJ[i] = (float)(S.gJ[i] - o);
+          }
+          for (int i = tid; i < 9 * CI; i += NT) {
+            const int k = i / CI, c = i - k * CI, d = k % 3;
+            const double o = d == 0 ? ox : (d == 1 ? oy : oz);
+            S.w.scr.vfI[i] = (float)(S.gI[k * kCH + cbase + c] - o);
+          }
+          for (int i = tid; i < kCH; i += NT) S.w.scr.flJ[i] = (float)(2.0 * S.gJ[9 * kCH + i]);
+          for (int i = tid; i < CI; i += NT) S.w.scr.flI[i] = (float)(2.0 * S.gI[9 * kCH + cbase + i]);
+          for (int i = tid; i < kListCap; i += NT) S.list[i] = 0xFFFFu;
+          if (tid < NCLS) {
+            S.cnt[tid] = 0;
+            S.fill[tid] = 0;
+          }
+          if (tid == 0) S.both_count = 0;
+          __syncthreads();
+          // ---------------- phase A: classification ----------------------------------------------------
+          // warp w handles rows c1l = (w>>1) + (NW/2) m, columns lane + 32 (w&1)
+          unsigned mycls = 0;  // 4 bits per iteration: class + 1, 0 = no pair
+          {
+            const int c2 = lane + 32 * (warp & 1);
+#pragma unroll 1
+            for (int m = 0; m < CI / (NW / 2); m++) {
+              const int c1l = (warp >> 1) + (NW / 2) * m, c1 = cbase + c1l;
+              unsigned code = 0;
+              int cls = -1;
+              if (c1l < nI1 && c2 < ncJ) {
+                bool n1, n2 = false;
+                if (A.self) {
+                  n1 = S.dminI[c1] <= S.dmaxJ[c2];
+                  n2 = want2 && !diag && (S.dmaxI[c1] > S.dminJ[c2]);
+                } else {
+                  n1 = true;
+                }
+                if (n1 || n2) {
+                  int iq = iquad_screen(S.w.scr.vfI, CI, c1l, S.w.scr.vfJ, c2, fmaxf(S.w.scr.flI[c1l], S.w.scr.flJ[c2]), delta);
+                  if (iq < 0) iq = iquad_exact_cells(S.gI, c1, S.gJ, c2);
+                  code = (unsigned)iq | (n1 ? 32u : 0u) | (n2 ? 64u : 0u);
+                  cls = cls_of(iq);
+                }
               }
-              if (n1 || n2) {
-                int iq = iquad_screen(S.vfI, c1, S.vfJ, c2, fmaxf(S.flI[c1], S.flJ[c2]), delta);
-                if (iq < 0) iq = iquad_exact_cells(S.gI, c1, S.gJ, c2);
-                code = (unsigned)iq | (n1 ? 32u : 0u) | (n2 ? 64u : 0u);
-                cls = cls_of(iq);
+              S.iqmap[c1l * kCH + c2] = (unsigned char)code;  // (T of unused pairs is never read by a used entry)
+              const unsigned grp = __match_any_sync(0xffffffffu, cls);
+              if (cls >= 0 && lane == __ffs(grp) - 1) atomicAdd(&S.cnt[cls], __popc(grp));
+              if (cls >= 7 && (code & 96u) == 96u) atomicAdd(&S.both_count, 1);
+              mycls |= (unsigned)(cls + 1) << (4 * m);
+            }
+          }
+          __syncthreads();
+          // ---------------- phase B: bin offsets, work queue(s), scatter, point tables -------------------
+          // Queue items: near classes (largest rules first), far bins too small for a table (evaluated
+          // from the vertices), then the table rules by decreasing size.  Table rules are packed into
+          // groups whose point tables fit the shared-memory pool together; a group is one barrier
+          // interval with one dynamic queue, so a pass normally has a single evaluation phase.
+          if (tid == 0) {
+            const int order[NCLS] = {11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0};
+            int o = 0, nb = 0, nq = 0, ng = 0, pts = 0;
+            unsigned long long fp = 0, ev = 0;
+            S.gq0[0] = 0;
+            for (int k = 0; k < NCLS; k++) {
+              const int c = order[k], n = S.cnt[c];
+              S.off[c] = o;
+              const bool near_c = c >= 7;
+              const bool c0 = near_c || c > kTabClsMax || n < kTabMin;  // evaluated analytically / from the vertices
+              if (n > 0 && c0) {
+                S.qcls[nq] = c;
+                S.qnb[nq] = near_c ? (n + 1) / 2 : (n + 31) / 32;
+                nb += S.qnb[nq];
+                nq++;
+              }
+              o += near_c ? ((n + 1) & ~1) : ((n + 31) & ~31);
+              if (!near_c) {
+                fp += n;
+                ev += (unsigned long long)n * c_cls_np[c] * c_cls_np[c];
               }
             }
-            S.iqmap[c1 * kCH + c2] = (unsigned char)code;
-            S.T[c1 * TS + c2] = 0.0;
-            const unsigned grp = __match_any_sync(0xffffffffu, cls);
-            if (cls >= 0 && lane == __ffs(grp) - 1) atomicAdd(&S.cnt[cls], __popc(grp));
-            if (cls >= 7 && (code & 96u) == 96u) atomicAdd(&S.both_count, 1);
-            mycls |= (unsigned)(cls + 1) << (4 * m);
-          }
-        }
-        __syncthreads();
-        // ---------------- phase B: bin offsets, queue of phase C0, scatter ---------------------------
-        if (tid == 0) {
-          // near classes first (largest rules first), then far classes by decreasing size
-          const int order[NCLS] = {11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0};
-          int o = 0, nb = 0, nq = 0;
-          unsigned long long fp = 0, ev = 0;
-          for (int k = 0; k < NCLS; k++) {
-            const int c = order[k], n = S.cnt[c];
-            S.off[c] = o;
-            const bool near_c = c >= 7;
-            const bool c0 = near_c || c >= 5 || n < kTabMin;  // evaluated in the mixed phase C0
-            if (n > 0 && c0) {
-              S.qcls[nq] = c;
-              S.qfirst[nq] = nb;
-              nb += near_c ? (n + 1) / 2 : (n + 31) / 32;
+            for (int c = kTabClsMax; c >= 0; c--) {
+              const int n = S.cnt[c];
+              if (n < kTabMin) continue;
+              const int np = c_cls_np[c];
+              if (pts + np > kTabPts) {  // close the group
+                S.gq1[ng] = nq;
+                S.gnb[ng] = nb;
+                ng++;
+                S.gq0[ng] = nq;
+                nb = 0;
+                pts = 0;
+              }
+              S.qcls[nq] = c | 16;  // bit 4: evaluate from the tables
+              S.qnb[nq] = (n + 31) / 32;
+              S.qpt[nq] = pts;
+              nb += S.qnb[nq];
+              pts += np;
               nq++;
             }
-            o += near_c ? ((n + 1) & ~1) : ((n + 31) & ~31);
-            if (!near_c) {
-              fp += n;
-              ev += (unsigned long long)n * c_cls_np[c] * c_cls_np[c];
-            }
+            S.gq1[ng] = nq;
+            S.gnb[ng] = nb;
+            S.ng = ng + 1;
+            S.qhead = 0;
+            st_far += fp;
+            st_eval += ev;
           }
-          S.qfirst[nq] = nb;
-          S.qn = nq;
-          S.qhead = 0;
-          st_far += fp;
-          st_eval += ev;
-        }
-        __syncthreads();
-        {
+          __syncthreads();  // (also: the FP32 scratch is dead, the table region may be written)
+          {
 #pragma unroll 1
-          for (int m = 0; m < kCH / 8; m++) {
-            const int cls = (int)((mycls >> (4 * m)) & 15u) - 1;
-            const unsigned grp = __match_any_sync(0xffffffffu, cls);
-            int base = 0;
-            const int leader = __ffs(grp) - 1;
-            if (cls >= 0 && lane == leader) base = atomicAdd(&S.fill[cls], __popc(grp));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (cls >= 0) {
-              const int c1 = (warp >> 1) + 8 * m, c2 = lane + 32 * (warp & 1);
-              S.list[S.off[cls] + base + __popc(grp & ((1u << lane) - 1u))] = (unsigned short)(c1 * kCH + c2);
+            for (int m = 0; m < CI / (NW / 2); m++) {
+              const int cls = (int)((mycls >> (4 * m)) & 15u) - 1;
+              const unsigned grp = __match_any_sync(0xffffffffu, cls);
+              int base = 0;
+              const int leader = __ffs(grp) - 1;
+              if (cls >= 0 && lane == leader) base = atomicAdd(&S.fill[cls], __popc(grp));
+              base = __shfl_sync(0xffffffffu, base, leader);
+              if (cls >= 0) {
+                const int c1l = (warp >> 1) + (NW / 2) * m, c2 = lane + 32 * (warp & 1);
+                S.list[S.off[cls] + base + __popc(grp & ((1u << lane) - 1u))] = (unsigned short)(c1l * kCH + c2);
+              }
             }
           }
-        }
-        __syncthreads();
-        // ---------------- phase C0: near pairs + far pairs evaluated from the vertices ---------------
-        {
-          const int nq = S.qn, total = S.qfirst[nq];
-          for (;;) {
-            int b = 0;
-            if (lane == 0) b = atomicAdd(&S.qhead, 1);
-            b = __shfl_sync(0xffffffffu, b, 0);
-            if (b >= total) break;
-            int k = 0;
-            while (b >= S.qfirst[k + 1]) k++;
-            const int cls = S.qcls[k], lb = b - S.qfirst[k];
-            run_batch_c0(S, cls, S.off[cls] + lb * (cls >= 7 ? 2 : 32), lane, false, st_near, st_phi);
-          }
-        }
-        // ---------------- phase C1: far rules with point tables, one rule at a time ------------------
+          // ---------------- phase C: evaluation, one dynamic queue per table group --------------------------
+          const int ngroups = S.ng;
 #pragma unroll 1
-        for (int cls = 4; cls >= 0; cls--) {
-          const int n = S.cnt[cls];  // uniform over the CTA
-          if (n < kTabMin) continue;
-          __syncthreads();           // previous users of the table region are done
-          const int np = c_cls_np[cls];
-          build_table(S.w.tab.tabI, S.gI, ncI, cls + 4, np, ox, oy, oz, true, tid, NT);
-          build_table(S.w.tab.tabJ, S.gJ, ncJ, cls + 4, np, ox, oy, oz, false, tid, NT);
-          if (tid == 0) S.qhead = 0;
-          __syncthreads();
-          const int nb = (n + 31) / 32, first = S.off[cls];
-          for (;;) {
-            int b = 0;
-            if (lane == 0) b = atomicAdd(&S.qhead, 1);
-            b = __shfl_sync(0xffffffffu, b, 0);
-            if (b >= nb) break;
-            const unsigned e = S.list[first + b * 32 + lane];
-            if (e != 0xFFFFu) {
-              const int c1 = e >> 6, c2 = e & 63;
-              S.T[c1 * TS + c2] = far_tab_dispatch(S.w.tab.tabI, S.w.tab.tabJ, c1, c2, cls) * S.gI[9 * kCH + c1] * S.gJ[9 * kCH + c2];
+          for (int g = 0; g < ngroups; g++) {
+            if (g > 0) {
+              __syncthreads();  // previous group is done with the table pool
+              if (tid == 0) S.qhead = 0;
             }
-          }
-        }
-        // ---------------- phase D: contraction onto DOFs (two passes when both roles are needed) ------
-        const bool two_pass = S.both_count > 0;  // written before the phase-A barrier
-        for (int pass = 0; pass < (two_pass ? 2 : 1); pass++) {
-          __syncthreads();  // T complete (and the table region free for U)
-          if (pass == 1) {
-            // role-2 values of the near pairs that need both roles
-            if (tid == 0) S.qhead = 0;
+            const int q0 = S.gq0[g], q1 = S.gq1[g], total = S.gnb[g];
+            for (int k = q0; k < q1; k++) {
+              const int qc = S.qcls[k];
+              if (!(qc & 16)) continue;
+              const int cls = qc & 15, pt = S.qpt[k];
+              build_table(S.w.tab.tabI + pt * 2 * CI, CI, S.gI, cbase, nI1, cls + 4, c_cls_np[cls], ox, oy, oz, true, tid, NT);
+              build_table(S.w.tab.tabJ + pt * 2 * kCH, kCH, S.gJ, 0, ncJ, cls + 4, c_cls_np[cls], ox, oy, oz, false, tid, NT);
+            }
             __syncthreads();
-            int nearb = 0, first_cls_off[5], first_cls_nb[5];
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-              first_cls_off[k] = S.off[11 - k];
-              first_cls_nb[k] = (S.cnt[11 - k] + 1) / 2;
-              nearb += first_cls_nb[k];
-            }
             for (;;) {
               int b = 0;
               if (lane == 0) b = atomicAdd(&S.qhead, 1);
               b = __shfl_sync(0xffffffffu, b, 0);
-              if (b >= nearb) break;
-              int k = 0, lb = b;
-              while (lb >= first_cls_nb[k]) {
-                lb -= first_cls_nb[k];
+              if (b >= total) break;
+              int k = q0, lb = b;
+              while (lb >= S.qnb[k]) {
+                lb -= S.qnb[k];
                 k++;
               }
-              run_batch_c0(S, 11 - k, first_cls_off[k] + lb * 2, lane, true, st_near, st_phi);
+              const int qc = S.qcls[k], cls = qc & 15;
+              if (A.debug_skip && ((cls >= 7) ? (A.debug_skip & 1) : (A.debug_skip & 2))) continue;
+              if (qc & 16) {
+                const unsigned e = S.list[S.off[cls] + lb * 32 + lane];
+                if (e != 0xFFFFu) {
+                  const int c1l = e >> 6, c2 = e & 63, pt = S.qpt[k];
+                  S.T[c1l * TS + c2] = far_tab_dispatch(S.w.tab.tabI + pt * 2 * CI, S.w.tab.tabJ + pt * 2 * kCH, c1l, c2, cls) *
+                                       S.gI[9 * kCH + cbase + c1l] * S.gJ[9 * kCH + c2];
+                }
+              } else {
+                run_batch_c0(S, cbase, cls, S.off[cls] + lb * (cls >= 7 ? 2 : 32), lane, false, st_near, st_phi);
+              }
             }
-            __syncthreads();
           }
-          for (int b0 = 0; b0 < ndJ; b0 += UB) {
-            const int nb = min(UB, ndJ - b0);
-            if (b0 > 0) __syncthreads();  // stage 2 of the previous block finished with U
-            // stage 1: U[c1][b] = sum_{(c2,k2) of b} +-E2[c2][k2] T[c1][c2]; lanes over c1
-            for (int it = tid; it < nb * kCH; it += NT) {
-              const int bl = it >> 6, c1 = it & 63;
-              double ux = 0.0, uy = 0.0, uz = 0.0;
-              const int ib = b0 + bl;
-              for (int i2 = S.iptrJ[ib]; i2 < S.iptrJ[ib + 1]; i2++) {
-                const unsigned w2 = S.incJ[i2];
-                const int c2 = w2 & 63, k2 = (w2 >> 6) & 3;
-                double tv = S.T[c1 * TS + c2];
-                if (w2 & 256) tv = -tv;
-                ux = fma(S.gJ[(10 + 3 * k2) * kCH + c2], tv, ux);
-                uy = fma(S.gJ[(11 + 3 * k2) * kCH + c2], tv, uy);
-                uz = fma(S.gJ[(12 + 3 * k2) * kCH + c2], tv, uz);
+          // ---------------- phase D: contraction onto DOFs (two passes when both roles are needed) ------
+          const bool two_pass = S.both_count > 0;  // written before the phase-A barrier
+          for (int pass = 0; pass < (two_pass ? 2 : 1); pass++) {
+            __syncthreads();  // T complete (and the table region free for U)
+            if (pass == 1) {
+              // role-2 values of the near pairs that need both roles
+              if (tid == 0) S.qhead = 0;
+              __syncthreads();
+              int nearb = 0, first_cls_off[5], first_cls_nb[5];
+#pragma unroll
+              for (int k = 0; k < 5; k++) {
+                first_cls_off[k] = S.off[11 - k];
+                first_cls_nb[k] = (S.cnt[11 - k] + 1) / 2;
+                nearb += first_cls_nb[k];
               }
-              S.w.U[(0 * kCH + c1) * US + bl] = ux;
-              S.w.U[(1 * kCH + c1) * US + bl] = uy;
-              S.w.U[(2 * kCH + c1) * US + bl] = uz;
+              for (;;) {
+                int b = 0;
+                if (lane == 0) b = atomicAdd(&S.qhead, 1);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b >= nearb) break;
+                int k = 0, lb = b;
+                while (lb >= first_cls_nb[k]) {
+                  lb -= first_cls_nb[k];
+                  k++;
+                }
+                if (A.debug_skip & 1) continue;
+                run_batch_c0(S, cbase, 11 - k, first_cls_off[k] + lb * 2, lane, true, st_near, st_phi);
+              }
+              __syncthreads();
             }
-            __syncthreads();
-            // stage 2: L[a][b] += sum_{(c1,k1) of a} +-E1[c1][k1] . U[c1][b]; lanes over b
-            for (int it = tid; it < ndI * UB; it += NT) {
-              const int ia = it >> 5, bl = it & 31;
-              if (bl >= nb) continue;
-              const int ib = b0 + bl;
-              const int oa = S.origI[ia], ob = S.origJ[ib];
-              if (A.self) {
-                const bool role1 = oa <= ob;
-                if (diag && !role1) continue;
-                if (two_pass && role1 != (pass == 0)) continue;
+            for (int b0 = 0; b0 < ndJ; b0 += UB) {
+              const int nb = min(UB, ndJ - b0);
+              if (b0 > 0) __syncthreads();  // stage 2 of the previous block finished with U
+              // stage 1: U[c1][b] = sum_{(c2,k2) of b} +-E2[c2][k2] T[c1][c2]; lanes over c1
+              for (int it = tid; it < nb * CI; it += NT) {
+                const int bl = it / CI, c1l = it - bl * CI;
+                double ux = 0.0, uy = 0.0, uz = 0.0;
+                const int ib = b0 + bl;
+                for (int i2 = S.iptrJ[ib]; i2 < S.iptrJ[ib + 1]; i2++) {
+                  const unsigned w2 = S.incJ[i2];
+                  const int c2 = w2 & 63, k2 = (w2 >> 6) & 3;
+                  double tv = S.T[c1l * TS + c2];
+                  if (w2 & 256) tv = -tv;
+                  ux = fma(S.gJ[(10 + 3 * k2) * kCH + c2], tv, ux);
+                  uy = fma(S.gJ[(11 + 3 * k2) * kCH + c2], tv, uy);
+                  uz = fma(S.gJ[(12 + 3 * k2) * kCH + c2], tv, uz);
+                }
+                S.w.U[(0 * CI + c1l) * US + bl] = ux;
+                S.w.U[(1 * CI + c1l) * US + bl] = uy;
+                S.w.U[(2 * CI + c1l) * US + bl] = uz;
               }
-              double acc = 0.0;
-              for (int i1 = S.iptrI[ia]; i1 < S.iptrI[ia + 1]; i1++) {
-                const unsigned w1 = S.incI[i1];
-                const int c1 = w1 & 63, k1 = (w1 >> 6) & 3;
-                double dsum = S.gI[(10 + 3 * k1) * kCH + c1] * S.w.U[(0 * kCH + c1) * US + bl];
-                dsum = fma(S.gI[(11 + 3 * k1) * kCH + c1], S.w.U[(1 * kCH + c1) * US + bl], dsum);
-                dsum = fma(S.gI[(12 + 3 * k1) * kCH + c1], S.w.U[(2 * kCH + c1) * US + bl], dsum);
-                acc += (w1 & 256) ? -dsum : dsum;
-              }
-              acc *= A.scale;
-              const int ra = S.rowI[ia];
-              if (ra >= 0) A.out[(long long)ra * A.ld + ob] += acc;
-              if (A.self && (mirror || diag) && oa != ob) {
-                const int rb = S.rowJ[ib];
-                if (rb >= 0) A.out[(long long)rb * A.ld + oa] += acc;
+              __syncthreads();
+              // stage 2: L[a][b] += sum_{(c1,k1) of a, c1 in this pass} +-E1[c1][k1] . U[c1][b]; lanes over b.
+              // Entries are handled in groups of G: all loads of the old values are issued first, the
+              // sums are formed while they are in flight, then the stores (one exposed latency per group).
+              constexpr int G = 4;
+              for (int it0 = tid; it0 < ndI * UB; it0 += G * NT) {
+                double* pa[G];
+                double* pb[G];
+                double olda[G], oldb[G], accv[G];
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                  pa[g] = nullptr;
+                  pb[g] = nullptr;
+                  const int it = it0 + g * NT;
+                  if (it >= ndI * UB) continue;
+                  const int ia = it >> 5, bl = it & 31;
+                  if (bl >= nb) continue;
+                  const int ib = b0 + bl;
+                  const int oa = S.origI[ia], ob = S.origJ[ib];
+                  if (A.self) {
+                    const bool role1 = oa <= ob;
+                    if (diag && !role1) continue;
+                    if (two_pass && role1 != (pass == 0)) continue;
+                  }
+                  if (!((S.hasI[ia] >> (cbase / CI)) & 1)) continue;  // no cell of this DOF in the pass
+                  const int ra = S.rowI[ia];
+                  if (ra >= 0) pa[g] = A.out + (long long)ra * A.ld + ob;
+                  if (A.self && (mirror || diag) && oa != ob) {
+                    const int rb = S.rowJ[ib];
+                    if (rb >= 0) pb[g] = A.out + (long long)rb * A.ld + oa;
+                  }
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                  olda[g] = pa[g] ? __ldcg(pa[g]) : 0.0;
+                  oldb[g] = pb[g] ? __ldcg(pb[g]) : 0.0;
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                  accv[g] = 0.0;
+                  if (!pa[g] && !pb[g]) continue;
+                  const int it = it0 + g * NT;
+                  const int ia = it >> 5, bl = it & 31;
+                  double acc = 0.0;
+                  for (int i1 = S.iptrI[ia]; i1 < S.iptrI[ia + 1]; i1++) {
+                    const unsigned w1 = S.incI[i1];
+                    const int c1l = (int)(w1 & 63) - cbase, k1 = (w1 >> 6) & 3;
+                    if (c1l < 0 || c1l >= CI) continue;
+                    const int c1 = w1 & 63;
+                    double dsum = S.gI[(10 + 3 * k1) * kCH + c1] * S.w.U[(0 * CI + c1l) * US + bl];
+                    dsum = fma(S.gI[(11 + 3 * k1) * kCH + c1], S.w.U[(1 * CI + c1l) * US + bl], dsum);
+                    dsum = fma(S.gI[(12 + 3 * k1) * kCH + c1], S.w.U[(2 * CI + c1l) * US + bl], dsum);
+                    acc += (w1 & 256) ? -dsum : dsum;
+                  }
+                  accv[g] = acc * A.scale;
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                  if (pa[g]) __stcg(pa[g], olda[g] + accv[g]);
+                  if (pb[g]) __stcg(pb[g], oldb[g] + accv[g]);
+                }
               }
             }
           }
         }
       }
     }
+  }
+  if (A.stats && tid == 0) {  // load balance: first / last CTA finish time (ns, globaltimer)
+    unsigned long long tend;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tend));
+    atomicMax(&A.stats[4], tend);
+    atomicMin(&A.stats[7], tend);
   }
   if (A.stats) {
     st_near = (unsigned long long)warp_sum((double)st_near);  // counts are < 2^53
@@ -830,6 +944,7 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   CK(cudaMemcpyAsync(d_row_out, row_out.data(), row_out.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
   CK(cudaMemsetAsync(d_counter, 0, sizeof(int), stream));
   CK(cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), stream));
+  CK(cudaMemsetAsync(d_stats + 7, 0xff, sizeof(unsigned long long), stream));
   twk::LmatArgs a;
   a.chunksA = A.chunks; a.chunksB = B.chunks;
   a.geomA = A.geom; a.geomB = B.geom;
@@ -847,11 +962,12 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   a.ld = ld;
   a.scale = 1.0 / (4.0 * kPi);
   a.self = self ? 1 : 0;
+  a.debug_skip = std::getenv("THINCURR_B200_DEBUG_SKIP") ? std::atoi(std::getenv("THINCURR_B200_DEBUG_SKIP")) : 0;
   a.stats = d_stats;
   int dev = 0, nsm = 148;
   CK(cudaGetDevice(&dev));
   CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  int grid = (int)std::min<size_t>(tiles.size(), (size_t)nsm);
+  int grid = (int)std::min<size_t>(tiles.size(), (size_t)twk::kCtasPerSM * nsm);
   twk::lmat_tile_kernel<<<grid, twk::NT, sizeof(twk::Smem), stream>>>(a);
   CK(cudaGetLastError());
   note_launch();

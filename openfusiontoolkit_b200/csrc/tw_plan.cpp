@@ -44,9 +44,16 @@ std::string build_patches(const Model& m, int P, PatchSet& ps) {
   ps = PatchSet();
   ps.ndof = nv + nh;
   if (P <= 0) {
-    // enough tiles to fill 148 SMs several times over, patches as large as possible otherwise
-    P = 256;
-    while (P > 32 && (double)(nv / P) * (nv / P) / 2.0 < 2000.0) P /= 2;
+    // Large patches keep the halo (cells shared by neighbouring patches are evaluated once per
+    // patch) small; the tile count must still fill 148 SMs many times over for load balance.
+    // The bisection produces 2^k patches, so count those.
+    P = 1024;
+    for (;;) {
+      long np2 = 1;
+      while (np2 * P < nv) np2 *= 2;
+      if (P <= 32 || np2 * np2 / 2 >= 1500) break;
+      P /= 2;
+    }
   }
   // dof -> vertices (periodic meshes map several vertices to one DOF)
   std::vector<int> kdv(nv + 1, 0), ldv;

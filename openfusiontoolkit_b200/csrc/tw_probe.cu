@@ -21,7 +21,7 @@ __global__ void probe_pairs_kernel(int n, int mode, const double* __restrict__ P
                                    int* __restrict__ iquad) {
   extern __shared__ __align__(16) unsigned char probe_smem[];
   double2* tabI = reinterpret_cast<double2*>(probe_smem);
-  double2* tabJ = tabI + kTabMaxN * 2 * kCH;
+  double2* tabJ = tabI + kTabMaxN * 2 * kCH;  // (I-side stride CI <= kCH)
   double* gI = reinterpret_cast<double*>(tabJ + kTabMaxN * 2 * kCH);
   double* gJ = gI + 10 * kCH;
   double* nI = gJ + 10 * kCH;
@@ -67,19 +67,19 @@ __global__ void probe_pairs_kernel(int n, int mode, const double* __restrict__ P
         vfJ[lane * kCH] = (float)(gJ[lane * kCH] - o);
       }
       __syncwarp();
-      iq = iquad_screen(vfI, 0, vfJ, 0, fmaxf((float)(2.0 * gI[9 * kCH]), (float)(2.0 * gJ[9 * kCH])), (float)(X * 1.21e-7));
+      iq = iquad_screen(vfI, kCH, 0, vfJ, 0, fmaxf((float)(2.0 * gI[9 * kCH]), (float)(2.0 * gJ[9 * kCH])), (float)(X * 1.21e-7));
       if (iq < 0) iq = iquad_exact_cells(gI, 0, gJ, 0) | 64;  // bit 6: the exact path was taken
     }
     const int iqv = iq & 31;
     double v;
     if (iqv > 10) {
       v = near_pair(gI, nI, 0, gJ, 0, iqv, lane, 32, 0xffffffffu);
-    } else if (mode == 0 || iqv > 8) {
+    } else if (mode == 0 || iqv - 4 > kTabClsMax) {
       v = far_dispatch(gI, 0, gJ, 0, iqv);
     } else {
       const int np = c_qnp[iqv];
-      build_table(tabI, gI, 1, iqv, np, ox, oy, oz, true, lane, 32);
-      build_table(tabJ, gJ, 1, iqv, np, ox, oy, oz, false, lane, 32);
+      build_table(tabI, CI, gI, 0, 1, iqv, np, ox, oy, oz, true, lane, 32);
+      build_table(tabJ, kCH, gJ, 0, 1, iqv, np, ox, oy, oz, false, lane, 32);
       __syncwarp();
       v = far_tab_dispatch(tabI, tabJ, 0, 0, iqv - 4) * gI[9 * kCH] * gJ[9 * kCH];
     }

@@ -112,7 +112,7 @@ std::string Model::mesh_init() {
       if (n == 2) lcc[3 * c + j] = lec[kec[e]] + lec[kec[e] + 1] - c;
       else if (n > 2) return "Non-manifold edge (more than two cells) is not supported";
     }
-  sync_face_normals();
+  if (!keep_orientation) sync_face_normals();
   // ---- boundary flags (mesh_local.F90:1044-1092)
   be.assign(ne, 0);
   bp.assign(np, 0);
@@ -538,6 +538,52 @@ std::string Model::setup_from_arrays(int np_, const double* r_, int nc_, const i
 }
 
 // ------------------------------------------------------------------ resistance matrix
+std::string Model::setup_from_tw(int np_, const double* r_, int nc_, const int* lc1, const int* reg_, const int* pmap1,
+                                 int np_active_, int nholes_, const int* kfh1, const int* lfh1, const double* ca_,
+                                 const double* qbasis_) {
+  if (np_ < 3 || nc_ < 1) return "Mesh must contain at least one cell";
+  np = np_;
+  nc = nc_;
+  r.assign(r_, r_ + 3 * (size_t)np);
+  lc.resize(3 * (size_t)nc);
+  for (size_t i = 0; i < lc.size(); i++) lc[i] = lc1[i] - 1;
+  reg.assign(nc, 1);
+  if (reg_) reg.assign(reg_, reg_ + nc);
+  nreg = 1;
+  for (int v : reg) nreg = std::max(nreg, v);
+  keep_orientation = true;
+  std::string err = mesh_init();
+  if (!err.empty()) return err;
+  vcoils.clear();
+  icoils.clear();
+  n_vcoils = n_icoils = 0;
+  np_active = np_active_;
+  nholes = nholes_;
+  pmap.assign(pmap1, pmap1 + np);
+  for (int v : pmap)
+    if (v < 0 || v > np_active) return "pmap entry outside [0, np_active]";
+  // Fortran CSR kfh(nc+1) (1-based offsets), lfh(2,nfh) column-major: (signed hole id, 1-based local vertex)
+  kfh.resize(nc + 1);
+  for (int c = 0; c <= nc; c++) kfh[c] = kfh1 ? kfh1[c] - 1 : 0;
+  nfh = kfh[nc];
+  lfh.resize(2 * (size_t)nfh);
+  for (int i = 0; i < nfh; i++) {
+    lfh[2 * i] = lfh1[2 * i];
+    lfh[2 * i + 1] = lfh1[2 * i + 1] - 1;
+    if (lfh[2 * i] == 0 || std::abs(lfh[2 * i]) > nholes || lfh[2 * i + 1] < 0 || lfh[2 * i + 1] > 2) return "Invalid hole incidence";
+  }
+  nelems = np_active + nholes + n_vcoils;
+  geometry();
+  // the host's own areas / basis vectors win so that both sides use bit-identical inputs
+  if (ca_) ca.assign(ca_, ca_ + nc);
+  if (qbasis_) qbasis.assign(qbasis_, qbasis_ + 9 * (size_t)nc);
+  eta_surf.assign(nreg, -1.0);
+  eta_vol.assign(nreg, -1.0);
+  thickness.assign(nreg, -1.0);
+  sens_mask.assign(nreg, 0);
+  return "";
+}
+
 void Model::build_rmat() {
   // R[a][b] = sum_c eta_s(reg_c)/mu0 (E_c[a].E_c[b]) area_c, V-coil diagonal = R_coil/mu0
   // (thin_wall.F90:1690-1930).  Assembled through per-row ordered maps -> sorted 1-based CSR,

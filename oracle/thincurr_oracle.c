@@ -670,3 +670,76 @@ void tco_phipot_batch(int n, const double *tri, const double *pt, double *out) {
 #pragma omp parallel for
   for (int k = 0; k < n; k++) out[k] = tco_phipot((const double(*)[3])(tri + 9 * (size_t)k), pt + 3 * (size_t)k);
 }
+
+/* ------------------------------------------------------------------ */
+/* Rows of the self-inductance matrix from the per-entry definition     */
+/*  -- an independent restatement of what the loop nest  */
+/* of thin_wall.F90:1008-1154 accumulates, used to check rows of large  */
+/* matrices without running the full O(nc^2) loop:                      */
+/*   L[a][b] = 1/(4 pi) sum_{c1 : E_c1[a]!=0} sum_{c2 : E_c2[b]!=0}     */
+/*             (E_c1[a].E_c2[b]) T(cell of the smaller DOF analytic)    */
+/* dofs[] are 0-based vertex/hole DOF ids; out[nd][nelems].             */
+/* ------------------------------------------------------------------ */
+static int cell_dofs(const tco_model *m, int c, int *dof, double (*E)[3]) {
+  /* distinct DOFs of a cell with their summed basis vectors */
+  int n = 0;
+  for (int k = 0; k < 3; k++) {
+    int d = m->pmap[m->lc[3 * c + k]] - 1;
+    if (d < 0) continue;
+    int s = 0;
+    while (s < n && dof[s] != d) s++;
+    if (s == n) { dof[n] = d; E[n][0] = E[n][1] = E[n][2] = 0.0; n++; }
+    for (int x = 0; x < 3; x++) E[s][x] += m->qbasis[9 * c + 3 * k + x];
+  }
+  for (int ii = m->kfh[c]; ii < m->kfh[c + 1]; ii++) {
+    int d = m->np_active + abs(m->lfh[2 * ii]) - 1, k = m->lfh[2 * ii + 1];
+    int s = 0;
+    while (s < n && dof[s] != d) s++;
+    if (s == n) { dof[n] = d; E[n][0] = E[n][1] = E[n][2] = 0.0; n++; }
+    for (int x = 0; x < 3; x++) E[s][x] += isign(m->lfh[2 * ii]) * m->qbasis[9 * c + 3 * k + x];
+  }
+  return n;
+}
+
+void tco_lmat_rows(const tco_model *m, int nd, const int *dofs, double *out) {
+  const long long N = m->nelems;
+  memset(out, 0, sizeof(double) * (size_t)nd * (size_t)N);
+  for (int r = 0; r < nd; r++) {
+    const int a = dofs[r];
+    double *row = out + (size_t)r * N;
+    for (int c1 = 0; c1 < m->nc; c1++) {
+      int d1[16];
+      double E1[16][3];
+      int n1 = cell_dofs(m, c1, d1, E1), s1 = -1;
+      for (int s = 0; s < n1; s++)
+        if (d1[s] == a) s1 = s;
+      if (s1 < 0) continue;
+      double P1[3][3], Etmp[3][3];
+      load_cell(m, c1, P1, Etmp);
+#pragma omp parallel for schedule(dynamic, 256)
+      for (int c2 = 0; c2 < m->nc; c2++) {
+        int d2[16];
+        double E2[16][3], P2[3][3], Et2[3][3];
+        int n2 = cell_dofs(m, c2, d2, E2);
+        if (n2 == 0) continue;
+        load_cell(m, c2, P2, Et2);
+        double T12 = 0.0, T21 = 0.0;
+        int have12 = 0, have21 = 0;
+        for (int s = 0; s < n2; s++) {
+          const int b = d2[s];
+          double T;
+          if (a <= b) {
+            if (!have12) { T12 = tco_pair_T(P1, m->ca[c1], P2, m->ca[c2], NULL); have12 = 1; }
+            T = T12;
+          } else {
+            if (!have21) { T21 = tco_pair_T(P2, m->ca[c2], P1, m->ca[c1], NULL); have21 = 1; }
+            T = T21;
+          }
+          const double v = dot3(E1[s1], E2[s]) * T / (4.0 * PI);
+#pragma omp atomic
+          row[b] += v;
+        }
+      }
+    }
+  }
+}

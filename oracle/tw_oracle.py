@@ -493,6 +493,15 @@ class OracleModel:
             self.Lmat = Lm
         return Lm
 
+    def lmat_rows(self, dofs):
+        """Rows of the self-inductance matrix (vertex/hole DOFs, 0-based) from the per-entry
+        definition; independent of the loop-nest restatement in compute_Lmat."""
+        dofs = np.ascontiguousarray(dofs, np.int32)
+        out = np.zeros((len(dofs), self.nelems))
+        lib().tco_lmat_rows(ctypes.byref(self.c), ctypes.c_int(len(dofs)), dofs.ctypes.data_as(ctypes.c_void_p),
+                            out.ctypes.data_as(ctypes.c_void_p))
+        return out
+
     def cross_coupling(self, other):
         """tw_compute_LmatDirect(self, M, col_model=other); returns Python view (self.nelems, other.nelems)."""
         M = np.zeros((self.nelems, other.nelems))  # Fortran (other.nelems, self.nelems)

@@ -1,0 +1,155 @@
+"""GPU parity of the coil / sensor coupling and B-field reconstruction operators and of the mutual
+(cross-coupling) inductance against the oracle (tw_compute_Ael2dr/_Lmat_coils :567-883,
+tw_compute_mutuals :1418-1686, tw_compute_Bops :1989-2226, tw_compute_LmatDirect with col_model),
+plus the reference's passive-V-coil eigenvalue golden and the frequency-response goldens computed
+from the GPU-built operators."""
+import numpy as np
+import pytest
+from helpers import MU0, dummy_mesh, goldens, load_mesh, split_nodesets, ref_circle, ref_floop
+from oracle import tw_oracle as tw
+
+pytestmark = pytest.mark.gpu
+G = goldens()
+
+
+def relerr(A, B):
+    return np.abs(np.asarray(A) - np.asarray(B)).max() / np.abs(B).max()
+
+
+@pytest.fixture(scope='module')
+def env():
+    from openfusiontoolkit_b200 import OFT_env
+    return OFT_env(nthreads=-1)
+
+
+def make(env, name, g, vcoils=None, icoils=None):
+    from openfusiontoolkit_b200.ThinCurr import ThinCurr
+    if name == 'passive':
+        r, lc = dummy_mesh([0.0, 0.0, 10.0], size=0.25, nsplit=1)
+        m = dict(r=r, lc=lc, reg=None, nodesets=[], sidesets=[])
+    else:
+        m = load_mesh(name)
+    ns = split_nodesets(m, g.get('jumper_start', 0))
+    cl = m['sidesets'][0] if m['sidesets'] else None
+    eta = g.get('eta', 10.0) * MU0
+    vc = [[dict(pts=ref_circle(R, Z), scale=1.0, radius=1.e-2, res_per_len=1.256637E-5)] for (R, Z) in (vcoils or [])]
+    ic = [[dict(pts=ref_circle(R, Z), scale=1.0) for (R, Z) in icoils]] if icoils else []
+    O = tw.OracleModel(m['r'], m['lc'], m['reg'], nodesets=ns, closures=cl if cl is not None else (), eta=[eta],
+                       vcoils=tw.CoilSets([dict(filaments=[(f['pts'], 1.0, 1.e-2, 1.256637E-5) for f in s]) for s in vc]),
+                       icoils=tw.CoilSets([dict(filaments=[(f['pts'], 1.0, -1.0, -1.0) for f in s]) for s in ic]))
+    T = ThinCurr(env)
+    T.setup_model(r=m['r'], lc=m['lc'], reg=m['reg'], nodesets=ns if len(ns) else None, closures=cl)
+    if vc:
+        T.set_coils('vcoil', vc)
+    if ic:
+        T.set_coils('icoil', ic)
+    T.set_eta_values(eta_surf=np.array([eta]))
+    return O, T
+
+
+def test_passive_vcoil_eigen_golden(env):
+    """run_eig 'passive' case (test_ThinCurr.py:1163-1168): V-coil rows of L and R."""
+    import scipy.linalg as sl
+    g = G['eig_passive']
+    O, T = make(env, 'passive', g, vcoils=g['vcoils'])
+    Mo = O.compute_Mcoil()
+    Mg = T.compute_Mcoil()
+    assert Mg.shape == Mo.shape
+    Lo = O.compute_Lmat()
+    T.compute_Lmat()
+    assert relerr(T.Lmat, Lo) < 1e-12
+    T.compute_Rmat()
+    w = np.sort(np.abs(sl.eigh(T.Lmat, T.Rmat.toarray(), eigvals_only=True)))[::-1][:4]
+    assert np.abs(w / np.array(g['vals']) - 1.0).max() < g['tol']
+
+
+def test_vcoil_precondition(env):
+    """thincurr_f.F90:555-558: L of a model with V-coils needs the coil mutuals first."""
+    g = G['eig_passive']
+    O, T = make(env, 'passive', g, vcoils=g['vcoils'])
+    with pytest.raises(Exception, match='Coil mutuals required'):
+        T.compute_Lmat()
+
+
+@pytest.mark.parametrize('name', ['plate', 'cyl', 'torus', 'passive'])
+def test_coil_sensor_operators_and_fr_goldens(env, name):
+    g = G['fr_' + name]
+    O, T = make(env, name, g, vcoils=g.get('vcoils'), icoils=g['icoils'])
+    Mco = O.compute_Mcoil()
+    Mcg = T.compute_Mcoil()
+    assert relerr(Mcg, Mco) < 1e-12
+    fl = [(ref_floop(R, Z), 1.0) for (R, Z) in g['floops']]
+    Mso, Msco = O.compute_Msensor(fl)
+    Msg, Mscg, _ = T.compute_Msensor(sensors=fl)
+    assert relerr(Msg, Mso) < 1e-12 and relerr(Mscg, Msco) < 1e-12
+    Lo = O.compute_Lmat()
+    T.compute_Lmat()
+    assert relerr(T.Lmat, Lo) < 1e-12
+    T.compute_Rmat()
+    R = T.Rmat.toarray()
+    dc = 1.0 / MU0
+    om = 2.0 * np.pi * g['freq']
+    x = np.linalg.solve(1j * om * T.Lmat + R, 1j * (-om * Mcg[0] * dc))
+    sig = np.stack([x.real, x.imag]) @ Msg
+    sig[0] += dc * Mscg[0]
+    assert np.abs(sig[0] / np.array(g['real']) - 1.0).max() < g['tol']
+    assert np.abs(sig[1] / np.array(g['imag']) - 1.0).max() < g['tol']
+
+
+def test_sensor_file_roundtrip(env, tmp_path):
+    """compute_Msensor through the reference's floops.loc format (thin_wall.F90:2604-2618)."""
+    from openfusiontoolkit_b200.ThinCurr.sensor import circular_flux_loop, save_sensors
+    g = G['fr_plate']
+    O, T = make(env, 'plate', g, icoils=g['icoils'])
+    T.compute_Mcoil()
+    sens = [circular_flux_loop(R, Z, 'FLOOP_%d' % k) for k, (R, Z) in enumerate(g['floops'])]
+    path = str(tmp_path / 'floops.loc')
+    save_sensors(sens, path)
+    Ms, Msc, info = T.compute_Msensor(sensor_file=path)
+    assert info['names'] == ['FLOOP_0', 'FLOOP_1']
+    O.compute_Mcoil()
+    Mso, Msco = O.compute_Msensor([(ref_floop(R, Z), 1.0) for (R, Z) in g['floops']])
+    assert relerr(Ms, Mso) < 1e-12 and relerr(Msc, Msco) < 1e-12
+
+
+def test_cross_coupling(env):
+    """Mutual inductance between two models: plate (row) x passive dummy mesh moved close (column)."""
+    from openfusiontoolkit_b200.ThinCurr import ThinCurr
+    m1 = load_mesh('plate')
+    r2, lc2 = dummy_mesh([0.1, 0.05, 0.08], size=0.6, nsplit=3)
+    O1 = tw.OracleModel(m1['r'], m1['lc'], m1['reg'])
+    O2 = tw.OracleModel(r2, lc2, None)
+    Mo = O1.cross_coupling(O2)
+    T1, T2 = ThinCurr(env), ThinCurr(env)
+    T1.setup_model(r=m1['r'], lc=m1['lc'], reg=m1['reg'])
+    T2.setup_model(r=r2, lc=lc2)
+    Mg = T1.cross_coupling(T2)
+    assert Mg.shape == (T1.nelems, T2.nelems) == Mo.shape
+    big = np.abs(Mo) > 1e-8 * np.abs(Mo).max()
+    assert (np.abs(Mg - Mo)[big] / np.abs(Mo)[big]).max() < 1e-10
+    assert relerr(Mg, Mo) < 1e-13
+    # model x itself reproduces the self-inductance only up to the role rule of near pairs
+    Ms = T1.cross_coupling(T1)
+    T1.compute_Lmat()
+    assert relerr(Ms, T1.Lmat) < 1e-4
+
+
+@pytest.mark.parametrize('name', ['plate', 'torus', 'passive'])
+def test_bmat(env, name):
+    """B-field reconstruction operators.  The near field is a central finite difference of the
+    analytic potential with step 1e-6 (thin_wall.F90:1995,2049-2075), which amplifies last-digit
+    differences of log/atan2 by ~1e6: tolerance 1e-8 relative to the largest entry (SURVEY hard part 8)."""
+    g = G['fr_' + name]
+    O, T = make(env, name, g, vcoils=g.get('vcoils'), icoils=g['icoils'])
+    if g.get('vcoils'):
+        O.compute_Mcoil()
+        T.compute_Mcoil()
+    Bo, Bdo = O.compute_Bmat()
+    Bg, Bdg = T.compute_Bmat()
+    # reference memory layout Bel(nelems,np,3): Python view (3,nelems,np) over [comp][p][e] memory
+    Bg_mem = np.asarray(Bg).reshape(3, T.np, T.nelems)
+    assert relerr(Bg_mem, Bo) < 1e-8
+    far = np.abs(Bo) < 1e-2 * np.abs(Bo).max()
+    assert np.abs(Bg_mem - Bo)[far].max() / np.abs(Bo).max() < 1e-9
+    Bdg_mem = np.asarray(Bdg).reshape(3, T.n_icoils, T.np)
+    assert relerr(Bdg_mem, Bdo) < 1e-13

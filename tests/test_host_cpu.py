@@ -1,0 +1,141 @@
+"""CPU-only checks of the host side of the B200 library (no GPU compute is called):
+the shared library loads and exports every symbol include/thincurr_b200.h declares, the C++ model
+setup (tw_setup restatement) agrees exactly with the oracle's, the resistance matrix and hashes
+agree, and the owner-computes plan partitions rows and tiles correctly."""
+import os
+import re
+import ctypes
+import numpy as np
+import pytest
+from helpers import MU0, load_mesh, split_nodesets, dummy_mesh
+from oracle import tw_oracle as tw
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MESHES = [('plate', 0), ('cyl', 2), ('torus', 0), ('ex_cyl', -1), ('ex_torus', 0), ('ex_ports', 0)]
+
+
+@pytest.fixture(scope='module')
+def env():
+    from openfusiontoolkit_b200 import OFT_env
+    return OFT_env(nthreads=-1)
+
+
+def _pair(env, name, js, eta=10.0):
+    from openfusiontoolkit_b200.ThinCurr import ThinCurr
+    m = load_mesh(name)
+    ns = split_nodesets(m, js)
+    cl = m['sidesets'][0] if m['sidesets'] else None
+    O = tw.OracleModel(m['r'], m['lc'], m['reg'], nodesets=ns, closures=cl if cl is not None else (), eta=[eta * MU0])
+    T = ThinCurr(env)
+    T.setup_model(r=m['r'], lc=m['lc'], reg=m['reg'], nodesets=ns if len(ns) else None, closures=cl)
+    return O, T
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'thincurr_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    names = set(re.findall(r'\b((?:thincurr|oftpy)_\w+)\s*\(', hdr))
+    assert len(names) >= 30
+    lib = ctypes.CDLL(os.path.join(ROOT, 'openfusiontoolkit_b200', 'libthincurr_b200.so'))
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, 'declared but not exported: %s' % missing
+
+
+def test_fortran_interface_matches_header():
+    """Every procedure bound in the ISO_C_BINDING interface module exists in the C header."""
+    f90 = open(os.path.join(ROOT, 'include', 'thincurr_b200_f.F90')).read()
+    hdr = open(os.path.join(ROOT, 'include', 'thincurr_b200.h')).read()
+    bound = re.findall(r'BIND\(C,\s*NAME="(\w+)"\)', f90)
+    assert len(bound) >= 8
+    for n in bound:
+        assert re.search(r'\b%s\s*\(' % n, hdr), n
+
+
+@pytest.mark.parametrize('name,js', MESHES)
+def test_setup_matches_oracle(env, name, js):
+    O, T = _pair(env, name, js)
+    assert (T.np, T.nc, T.np_active, T.nholes, T.nelems) == (O.np_, O.nc, O.np_active, O.nholes, O.nelems)
+    A = T.get_model_arrays()
+    assert np.array_equal(A['pmap'], O.pmap)
+    assert np.array_equal(A['lc'], O.lc), 'orientation sync must flip the same cells'
+    assert np.array_equal(A['kfh'], O.kfh)
+    assert np.array_equal(A['lfh'], np.asarray(O.lfh).reshape(-1, 2)[:O.nfh])
+    assert np.abs(A['qbasis'] - O.qbasis).max() <= 1e-13 * np.abs(O.qbasis).max()
+    assert np.abs(A['ca'] - O.ca).max() <= 1e-15 * O.ca.max()
+    assert T.model_hashes() == (O.hash_lc(), O.hash_r())
+
+
+@pytest.mark.parametrize('name,js', [('plate', 0), ('cyl', 2), ('torus', 0)])
+def test_rmat_matches_oracle(env, name, js):
+    O, T = _pair(env, name, js)
+    T.set_eta_values(eta_surf=np.array([10.0 * MU0]))
+    T.compute_Rmat()
+    Ro = O.compute_Rmat().toarray()
+    Rg = T.Rmat.toarray()
+    assert np.abs(Rg - Ro).max() <= 1e-13 * np.abs(Ro).max()
+    assert np.allclose(T.get_eta_values(), 10.0 * MU0, rtol=1e-15)
+
+
+def test_error_conventions(env):
+    from openfusiontoolkit_b200.ThinCurr import ThinCurr
+    T = ThinCurr(env)
+    with pytest.raises(ValueError):
+        T.setup_model()
+    with pytest.raises(Exception):
+        T.setup_model(mesh_file='/nonexistent/mesh.h5')
+    m = load_mesh('plate')
+    T.setup_model(r=m['r'], lc=m['lc'], reg=m['reg'])
+    with pytest.raises(ValueError):
+        T.setup_model(r=m['r'], lc=m['lc'])
+    with pytest.raises(IndexError):
+        T.set_eta_values(eta_surf=np.ones(3))
+    with pytest.raises(ValueError):
+        T.set_eta_values(eta_surf=-np.ones(1))
+    with pytest.raises(Exception, match='HODLR'):
+        T.compute_Lmat(use_hodlr=True)
+
+
+def test_no_cpu_fallback(env):
+    """Without a CUDA device every operator build must fail loudly (no silent CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from openfusiontoolkit_b200.ThinCurr import ThinCurr
+    m = load_mesh('plate')
+    T = ThinCurr(env)
+    T.setup_model(r=m['r'], lc=m['lc'], reg=m['reg'])
+    with pytest.raises(Exception, match='CUDA'):
+        T.compute_Lmat()
+    with pytest.raises(Exception, match='CUDA'):
+        T.compute_Bmat()
+
+
+@pytest.mark.parametrize('name,js', [('torus', 0), ('ex_torus', 0), ('ex_ports', 0)])
+@pytest.mark.parametrize('nshards', [1, 2, 8])
+def test_plan_partitions_rows(env, name, js, nshards):
+    O, T = None, None
+    from openfusiontoolkit_b200.ThinCurr import ThinCurr
+    m = load_mesh(name)
+    ns = split_nodesets(m, js)
+    T = ThinCurr(env)
+    T.setup_model(r=m['r'], lc=m['lc'], reg=m['reg'], nodesets=ns if len(ns) else None,
+                  closures=m['sidesets'][0] if m['sidesets'] else None)
+    rows = [T.shard_rows(nshards, s) for s in range(nshards)]
+    allr = np.concatenate(rows)
+    assert np.array_equal(np.sort(allr), np.arange(T.nelems)), 'shards must partition the rows'
+    info = T.plan_info()
+    assert info['patch_cells'] >= T.nc and info['ntiles'] == info['npatch'] * (info['npatch'] + 1) // 2
+    if nshards > 1 and T.nelems > 2000:
+        sizes = np.array([len(r) for r in rows], float)
+        assert sizes.max() / sizes.mean() < 1.35, 'row blocks are balanced by cell count'
+
+
+def test_dummy_mesh_generator_matches_reference_counts():
+    from openfusiontoolkit_b200.ThinCurr.meshing import build_ThinCurr_dummy, build_torus_vessel
+    r, lc = build_ThinCurr_dummy([0., 0., 0.], size=0.25, nsplit=1)
+    r2, lc2 = dummy_mesh([0., 0., 0.], size=0.25, nsplit=1)
+    assert np.array_equal(lc, lc2) and np.allclose(r, r2)
+    m = build_torus_vessel(24, 48, nports=4)
+    used = np.zeros(len(m['r']), bool)
+    used[m['lc'].ravel()] = True
+    assert used.all() and len(m['nodesets']) == 2 + 4

@@ -1,0 +1,58 @@
+"""world_size-2 gloo test of the multi-rank host logic (bench.py's sharding): every rank plans the
+same model, owns a disjoint row block, and the union covers the matrix; the weak-scaling mesh sizes
+grow so that pairs per rank stay constant."""
+import os
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from openfusiontoolkit_b200 import OFT_env
+    from openfusiontoolkit_b200.ThinCurr import ThinCurr
+    from openfusiontoolkit_b200.ThinCurr.meshing import build_torus_vessel
+    m = build_torus_vessel(40, 80, nports=4)
+    T = ThinCurr(OFT_env(nthreads=-1))
+    T.setup_model(r=m['r'], lc=m['lc'], nodesets=m['nodesets'], closures=m['closures'])
+    rows = T.shard_rows(world, rank)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, rows.tolist())
+    hashes = [None] * world
+    dist.all_gather_object(hashes, T.model_hashes())
+    if rank == 0:
+        q.put((T.nelems, gathered, hashes))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_row_partition():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    nelems, gathered, hashes = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    allr = np.concatenate([np.array(g) for g in gathered])
+    assert np.array_equal(np.sort(allr), np.arange(nelems))
+    assert len(set(hashes)) == 1, 'all ranks must see the same model'
+    assert abs(len(gathered[0]) - len(gathered[1])) < 0.2 * nelems
+
+
+def test_weak_scaling_mesh_sizes():
+    sys.path.insert(0, ROOT)
+    from bench import vessel_dims
+    base = np.prod(vessel_dims(1))
+    for n in (2, 4, 8):
+        cells = np.prod(vessel_dims(n))
+        assert abs(cells ** 2 / n / base ** 2 - 1.0) < 0.03, 'pairs per rank stay constant'
