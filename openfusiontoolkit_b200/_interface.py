@@ -12,7 +12,7 @@ import numpy
 from numpy import float64, int32
 
 root_path = os.path.realpath(os.path.dirname(__file__))
-lib_path = os.path.join(root_path, 'libthincurr_b200.so')
+lib_path = os.environ.get('THINCURR_B200_LIB') or os.path.join(root_path, 'libthincurr_b200.so')  # override: tuning variants
 if not os.path.exists(lib_path):
     try:
         from .build import build as _build

@@ -26,23 +26,26 @@ def needs_build():
     return False
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defs=(), out=None):
+    """defs/out: build a tuning variant (extra -D flags) under another file name; the product
+    library is always the default build."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + ['-D' + d for d in defs] + ['-o', out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
-    with open(os.path.join(HERE, 'build.log'), 'w') as f:
+    with open(os.path.join(HERE, 'build.log' if out is None else os.path.basename(out) + '.log'), 'w') as f:
         f.write(' '.join(cmd) + '\n' + log)
     if res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError('nvcc failed building libthincurr_b200.so')
     if verbose:
         print(log)
-    return LIB
+    return out or LIB
 
 
 if __name__ == '__main__':
-    build(force='--force' in sys.argv, verbose=True)
-    print('built', LIB)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith('-D')]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith('-o')]
+    print('built', build(force='--force' in sys.argv, verbose='-v' in sys.argv, defs=defs, out=outs[0] if outs else None))

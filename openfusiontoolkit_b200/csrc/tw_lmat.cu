@@ -122,7 +122,7 @@ struct Smem {
 // T = area_i area_j sum_p sum_q w_p w_q / |x_p(i) - x_q(j)|, same rule on both triangles
 // (thin_wall.F90:1069-1083).  j-side points are held in registers in blocks of <= 8; the i-side
 // point is recomputed per p.
-template <int N>
+template <int N>  // @region far_vertex
 __device__ __forceinline__ double far_pair(const double* __restrict__ gI, int c1, const double* __restrict__ gJ, int c2,
                                            int iquad) {
   const double* bp = c_qpts + 3 * c_qoff[iquad];
@@ -167,7 +167,7 @@ __device__ __forceinline__ double far_pair(const double* __restrict__ gI, int c1
   return total * gI[9 * kCH + c1] * gJ[9 * kCH + c2];
 }
 
-__device__ __forceinline__ double far_dispatch(const double* gI, int c1, const double* gJ, int c2, int iquad) {
+__device__ __forceinline__ double far_dispatch(const double* gI, int c1, const double* gJ, int c2, int iquad) {  // @region far_dispatch
   switch (iquad) {
     case 4: return far_pair<6>(gI, c1, gJ, c2, iquad);
     case 5: return far_pair<7>(gI, c1, gJ, c2, iquad);
@@ -183,7 +183,7 @@ __device__ __forceinline__ double far_dispatch(const double* gI, int c1, const d
 // 10 FP64-pipe instructions per 1/r: 1 add + 3 fma (d^2), 5 (rsqrt correction), 1 fma (weighted sum).
 // The QB evaluations of one row point are advanced stage by stage so that QB independent
 // dependency chains are in flight (DFMA latency is 8 cycles, the pipe takes one warp every 2).
-template <int N, int OFF>
+template <int N, int OFF>  // @region far_tab
 __device__ __forceinline__ double far_tab(const double2* __restrict__ tabI, const double2* __restrict__ tabJ, int c1, int c2) {
   // c1: row cell within the pass (stride CI), c2: column cell (stride kCH)
   const double* bw = c_qwts + OFF;  // OFF = TCQ_OFF[iquad]: weights become constant-bank operands
@@ -231,7 +231,7 @@ __device__ __forceinline__ double far_tab(const double2* __restrict__ tabI, cons
   return total;
 }
 
-__device__ __forceinline__ double far_tab_dispatch(const double2* tabI, const double2* tabJ, int c1, int c2, int cls) {
+__device__ __forceinline__ double far_tab_dispatch(const double2* tabI, const double2* tabJ, int c1, int c2, int cls) {  // @region far_tab_dispatch
   switch (cls) {
     case 0: return far_tab<6, 7>(tabI, tabJ, c1, c2);
     case 1: return far_tab<7, 13>(tabI, tabJ, c1, c2);
@@ -247,7 +247,7 @@ __device__ __forceinline__ double far_tab_dispatch(const double2* tabI, const do
 // T = area_q * sum_q w_q phi_{tri A}(x_q(tri Q)) (thin_wall.F90:1061-1068); gA/cA = analytic
 // triangle, gQ/cQ = quadrature triangle.  `nl` lanes (16 or 32, aligned group of the warp)
 // cooperate on one pair; every lane of the group returns the sum.
-__device__ __forceinline__ double near_pair(const double* gA, const double* nA, int cA, const double* gQ, int cQ, int iquad,
+__device__ __forceinline__ double near_pair(const double* gA, const double* nA, int cA, const double* gQ, int cQ, int iquad,  // @region near_pair
                                             int gl, int nl, unsigned mask) {
   double PA[9], PQ[9], nh[3];
 #pragma unroll
@@ -279,7 +279,7 @@ __device__ __forceinline__ double near_pair(const double* gA, const double* nA, 
 // vI/vJ: vertices in a common local frame rounded to FP32 (|v| <= X); delta = bound of the
 // coordinate error of a vertex DIFFERENCE (input rounding of both operands, = 2^-23 X * 1.01).
 // Returns iquad, or -1 when the decision is not safe in FP32.
-__device__ __forceinline__ int iquad_screen(const float* __restrict__ vI, int sI, int c1, const float* __restrict__ vJ, int c2,
+__device__ __forceinline__ int iquad_screen(const float* __restrict__ vI, int sI, int c1, const float* __restrict__ vJ, int c2,  // @region iquad_screen
                                             float fl2, float delta) {
   float pi_[9], pj_[9];
 #pragma unroll
@@ -321,7 +321,7 @@ __device__ __forceinline__ int iquad_screen(const float* __restrict__ vI, int sI
   return (lo_ok && hi_ok) ? iq : -1;
 }
 
-__device__ __noinline__ int iquad_exact_cells(const double* gI, int c1, const double* gJ, int c2) {
+__device__ __noinline__ int iquad_exact_cells(const double* gI, int c1, const double* gJ, int c2) {  // @region iquad_exact_cells
   double Pi[9], Pj[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) {
@@ -332,7 +332,7 @@ __device__ __noinline__ int iquad_exact_cells(const double* gI, int c1, const do
 }
 
 // (kept for the probes) classification directly in FP64
-__device__ __forceinline__ int classify_pair(const double* gI, int c1, const double* gJ, int c2) {
+__device__ __forceinline__ int classify_pair(const double* gI, int c1, const double* gJ, int c2) {  // @region classify_pair
   double Pi[9], Pj[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) {
@@ -358,7 +358,7 @@ __device__ __forceinline__ int classify_pair(const double* gI, int c1, const dou
 // quadrature-point table of `ncell` cells (first cell c0 of the chunk record g) for one rule in the
 // frame centred at (ox,oy,oz); table stride `ts`.  neg=true stores (-2x,-2y),(-2z,|x|^2) (row side),
 // else (x,y),(z,|x|^2)
-__device__ __forceinline__ void build_table(double2* __restrict__ tab, int ts, const double* __restrict__ g, int c0, int ncell,
+__device__ __forceinline__ void build_table(double2* __restrict__ tab, int ts, const double* __restrict__ g, int c0, int ncell,  // @region build_table
                                             int iquad, int n, double ox, double oy, double oz, bool neg, int tid0, int nthreads) {
   const double* bp = c_qpts + 3 * c_qoff[iquad];
   for (int it = tid0; it < n * ts; it += nthreads) {
@@ -379,7 +379,7 @@ __device__ __forceinline__ void build_table(double2* __restrict__ tab, int ts, c
   }
 }
 
-__device__ __forceinline__ void load_chunk(Smem& S, int side, const LmatArgs& A, int chunk, unsigned long long* bar,
+__device__ __forceinline__ void load_chunk(Smem& S, int side, const LmatArgs& A, int chunk, unsigned long long* bar,  // @region load_chunk
                                            uint32_t& phase) {
   // side 0: row chunk (I), 1: column chunk (J).  Geometry record via one bulk async copy issued
   // by a single thread; the small index lists by all threads; normals computed after arrival.
@@ -433,7 +433,7 @@ __device__ __forceinline__ void load_chunk(Smem& S, int side, const LmatArgs& A,
 
 // one batch of the work queue: 32 far pairs of one rule (from the vertices) or 2 near pairs.
 // List entries are (c1l<<6 | c2) with c1l the row cell within the pass; c1 = cbase + c1l.
-__device__ __forceinline__ void run_batch_c0(Smem& S, int cbase, int cls, int first, int lane, bool role2_pass,
+__device__ __forceinline__ void run_batch_c0(Smem& S, int cbase, int cls, int first, int lane, bool role2_pass,  // @region run_batch_c0
                                              unsigned long long& st_near, unsigned long long& st_phi) {
   if (cls < 7) {
     const unsigned e = S.list[first + lane];
@@ -469,7 +469,7 @@ __device__ __forceinline__ void run_batch_c0(Smem& S, int cbase, int cls, int fi
   }
 }
 
-__global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArgs A) {
+__global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArgs A) {  // @region kernel_head
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArg
     const int ci0 = A.patch_chunk_ptrA[tile.pa], ci1 = A.patch_chunk_ptrA[tile.pa + 1];
     const int cj0 = A.patch_chunk_ptrB[tile.pb], cj1 = A.patch_chunk_ptrB[tile.pb + 1];
 
-    for (int ci = ci0; ci < ci1; ci++) {
+    for (int ci = ci0; ci < ci1; ci++) {  // @region chunk_loop
       __syncthreads();  // previous contraction finished with the I-side lists
       load_chunk(S, 0, A, ci, &S.bar[0], phI);
       const tw::ChunkMeta cmI = A.chunksA[ci];
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArg
         for (int cbase = 0; cbase < ncI; cbase += CI) {  // row cells [cbase, cbase + nI1) of the chunk
           const int nI1 = min(CI, ncI - cbase);
           if (cbase > 0) __syncthreads();  // previous pass finished with T / U / lists
-          // ---------------- phase A0: FP32 local-frame vertices, list reset ---------------------------
+          // ---------------- phase A0: FP32 local-frame vertices, list reset ---------------------------  // @region A0_fp32_stage
           for (int i = tid; i < 9 * kCH; i += NT) {
             const int k = i / kCH, d = k % 3;
             const double o = d == 0 ? ox : (d == 1 ? oy : oz);
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArg
           }
           if (tid == 0) S.both_count = 0;
           __syncthreads();
-          // ---------------- phase A: classification ----------------------------------------------------
+          // ---------------- phase A: classification ----------------------------------------------------  // @region A_classify
           // warp w handles rows c1l = (w>>1) + (NW/2) m, columns lane + 32 (w&1)
           unsigned mycls = 0;  // 4 bits per iteration: class + 1, 0 = no pair
           {
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArg
             }
           }
           __syncthreads();
-          // ---------------- phase B: bin offsets, work queue(s), scatter, point tables -------------------
+          // ---------------- phase B: bin offsets, work queue(s), scatter, point tables -------------------  // @region B_bin
           // Queue items: near classes (largest rules first), far bins too small for a table (evaluated
           // from the vertices), then the table rules by decreasing size.  Table rules are packed into
           // groups whose point tables fit the shared-memory pool together; a group is one barrier
@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArg
               }
             }
           }
-          // ---------------- phase C: evaluation, one dynamic queue per table group --------------------------
+          // ---------------- phase C: evaluation, one dynamic queue per table group --------------------------  // @region C_eval
           const int ngroups = S.ng;
 #pragma unroll 1
           for (int g = 0; g < ngroups; g++) {
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArg
               }
             }
           }
-          // ---------------- phase D: contraction onto DOFs (two passes when both roles are needed) ------
+          // ---------------- phase D: contraction onto DOFs (two passes when both roles are needed) ------  // @region D_contract_ctl
           const bool two_pass = S.both_count > 0;  // written before the phase-A barrier
           for (int pass = 0; pass < (two_pass ? 2 : 1); pass++) {
             __syncthreads();  // T complete (and the table region free for U)
@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArg
               }
               __syncthreads();
             }
-            for (int b0 = 0; b0 < ndJ; b0 += UB) {
+            for (int b0 = 0; b0 < ndJ; b0 += UB) {  // @region D_stage1
               const int nb = min(UB, ndJ - b0);
               if (b0 > 0) __syncthreads();  // stage 2 of the previous block finished with U
               // stage 1: U[c1][b] = sum_{(c2,k2) of b} +-E2[c2][k2] T[c1][c2]; lanes over c1
@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArg
                 S.w.U[(2 * CI + c1l) * US + bl] = uz;
               }
               __syncthreads();
-              // stage 2: L[a][b] += sum_{(c1,k1) of a, c1 in this pass} +-E1[c1][k1] . U[c1][b]; lanes over b.
+              // stage 2: L[a][b] += sum_{(c1,k1) of a, c1 in this pass} +-E1[c1][k1] . U[c1][b]; lanes over b.  // @region D_stage2
               // Entries are handled in groups of G: all loads of the old values are issued first, the
               // sums are formed while they are in flight, then the stores (one exposed latency per group).
               constexpr int G = 4;
@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArg
       }
     }
   }
-  if (A.stats && tid == 0) {  // load balance: first / last CTA finish time (ns, globaltimer)
+  if (A.stats && tid == 0) {  // load balance: first / last CTA finish time (ns, globaltimer)  // @region tail
     unsigned long long tend;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tend));
     atomicMax(&A.stats[4], tend);

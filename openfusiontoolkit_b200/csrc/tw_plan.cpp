@@ -291,13 +291,22 @@ void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& til
       bool owned = pb >= p0 && pb < p1;
       if (owned && pb < pa) continue;  // produced by the mirror write of tile (pb,pa)
       Tile t;
-      t.pa = pa;
-      t.pb = pb;
       t.flags = 0;
-      if (pa == pb) t.flags |= 1;
-      else if (owned) t.flags |= 2;
-      if (pa != pb && omax[pa] > omin[pb]) t.flags |= 4;
-      t.cost = tile_cost(ps, ps, balls, balls, pa, pb, h) * ((t.flags & 1) ? 0.5f : 1.0f);
+      if (!owned && pb < pa) {
+        // rows of pa against an unowned lower patch: evaluate the tile in the orientation (pb,pa) the
+        // single-device build uses and keep only its mirror writes, so that every shard count
+        // produces the same bits (row_out is -1 on the unowned side: no direct write happens)
+        t.pa = pb;
+        t.pb = pa;
+        t.flags |= 2;
+      } else {
+        t.pa = pa;
+        t.pb = pb;
+        if (pa == pb) t.flags |= 1;
+        else if (owned) t.flags |= 2;
+      }
+      if (t.pa != t.pb && omax[t.pa] > omin[t.pb]) t.flags |= 4;
+      t.cost = tile_cost(ps, ps, balls, balls, t.pa, t.pb, h) * ((t.flags & 1) ? 0.5f : 1.0f);
       tiles.push_back(t);
     }
   std::stable_sort(tiles.begin(), tiles.end(), [](const Tile& a, const Tile& b) { return a.cost > b.cost; });

@@ -49,7 +49,10 @@ __global__ void probe_pairs_kernel(int n, int mode, const double* __restrict__ P
     }
     // local frame as in the tile kernel: midpoint of two "chunk centres" (here vertex 0 of each cell,
     // displaced so that the frame is not trivially centred), X = bound on |v - o|
-    const double ox = 0.5 * (gI[0] + gJ[0]) + 0.01, oy = 0.5 * (gI[kCH] + gJ[kCH]) - 0.02, oz = 0.5 * (gI[2 * kCH] + gJ[2 * kCH]) + 0.005;
+    // (the displacement scales with the cells like a chunk radius does: ~3.4 sqrt(area_i + area_j))
+    const double dref = sqrt(gI[9 * kCH] + gJ[9 * kCH]);
+    const double ox = 0.5 * (gI[0] + gJ[0]) + 1.5 * dref, oy = 0.5 * (gI[kCH] + gJ[kCH]) - 3.0 * dref,
+                 oz = 0.5 * (gI[2 * kCH] + gJ[2 * kCH]) + 0.75 * dref;
     double X = 0.0;
     for (int k = 0; k < 3; k++) {
       double ax = gI[(3 * k) * kCH] - ox, ay = gI[(3 * k + 1) * kCH] - oy, az = gI[(3 * k + 2) * kCH] - oz;

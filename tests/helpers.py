@@ -62,3 +62,32 @@ def dummy_mesh(center, size=1.0, nsplit=0):
             lc_new += [[lc[j, 0], ni[0], ni[2]], [ni[0], lc[j, 1], ni[1]], [ni[1], lc[j, 2], ni[2]], [ni[0], ni[1], ni[2]]]
         lc, r = np.array(lc_new), np.array(r_new)
     return r, lc
+
+
+def mutual_abs_sum(O1, O2):
+    """A[a][b] = (1/4pi) sum_{c1,c2} sum_comp |E_c1[a]|.|E_c2[b]| T(c1,c2): the magnitude of the terms an
+    entry of the mutual matrix is summed from.  |M| << A marks entries dominated by cancellation, where
+    the reference's own result moves by ~eps*A with the (atomic, thread-dependent) summation order
+    (thin_wall.F90:1092-1121), so parity there is judged against eps*A and not against |M|."""
+    import ctypes
+    from oracle import tw_oracle as tw
+    nc1, nc2 = O1.nc, O2.nc
+    P1, P2 = O1.r[O1.lc].reshape(nc1, 9), O2.r[O2.lc].reshape(nc2, 9)
+    ii, jj = np.meshgrid(np.arange(nc1), np.arange(nc2), indexing='ij')
+    ci, cj = ii.ravel(), jj.ravel()
+    Pi, Pj = np.ascontiguousarray(P1[ci]), np.ascontiguousarray(P2[cj])
+    Ai, Aj = np.ascontiguousarray(O1.ca[ci]), np.ascontiguousarray(O2.ca[cj])
+    n = len(ci)
+    To, qo = np.zeros(n), np.zeros(n, np.int32)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    tw.lib().tco_pair_T_batch(n, vp(Pi), vp(Ai), vp(Pj), vp(Aj), vp(To), vp(qo))
+    T = To.reshape(nc1, nc2)
+    E1, E2 = np.zeros((O1.nelems, nc1, 3)), np.zeros((O2.nelems, nc2, 3))
+    for c, d in enumerate(O1.cell_basis()):
+        for k, v in d.items():
+            E1[k, c] = v
+    for c, d in enumerate(O2.cell_basis()):
+        for k, v in d.items():
+            E2[k, c] = v
+    A = sum(np.abs(E1[:, :, k]) @ T @ np.abs(E2[:, :, k]).T for k in range(3))
+    return A / (4.0 * np.pi)

@@ -5,7 +5,7 @@ plus the reference's passive-V-coil eigenvalue golden and the frequency-response
 from the GPU-built operators."""
 import numpy as np
 import pytest
-from helpers import MU0, dummy_mesh, goldens, load_mesh, split_nodesets, ref_circle, ref_floop
+from helpers import MU0, dummy_mesh, goldens, load_mesh, mutual_abs_sum, split_nodesets, ref_circle, ref_floop
 from oracle import tw_oracle as tw
 
 pytestmark = pytest.mark.gpu
@@ -125,8 +125,13 @@ def test_cross_coupling(env):
     T2.setup_model(r=r2, lc=lc2)
     Mg = T1.cross_coupling(T2)
     assert Mg.shape == (T1.nelems, T2.nelems) == Mo.shape
-    big = np.abs(Mo) > 1e-8 * np.abs(Mo).max()
-    assert (np.abs(Mg - Mo)[big] / np.abs(Mo)[big]).max() < 1e-10
+    # entry-wise 1e-10, plus the reference's own summation-order noise on entries that cancel:
+    # two CPU summation orders of the oracle already differ by 6.6e-10 on an entry with |M| = 4e-8 A
+    A = mutual_abs_sum(O1, O2)
+    tol = 1e-10 * np.abs(Mo) + 64 * np.finfo(float).eps * A
+    assert (np.abs(Mg - Mo) <= tol).all(), (np.abs(Mg - Mo) / tol).max()
+    well = np.abs(Mo) > 1e-4 * A   # entries that lose < 4 digits to cancellation: plain relative error
+    assert (np.abs(Mg - Mo)[well] / np.abs(Mo)[well]).max() < 1e-10
     assert relerr(Mg, Mo) < 1e-13
     # model x itself reproduces the self-inductance only up to the role rule of near pairs
     Ms = T1.cross_coupling(T1)

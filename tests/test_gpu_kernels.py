@@ -60,8 +60,14 @@ def test_pair_integrals_scaled_geometry():
         assert I.b200_probe_pairs(len(Ai), 1, Pi2, Ai2, Pj2, Aj2, Tg, qg) == 0
         assert np.array_equal(qg & 31, qo)
         # a far-away origin costs digits in BOTH implementations (cancellation in the vertex differences)
-        tol = 2e-14 if shift == 0.0 else 1e-9
-        assert (np.abs(Tg - To) / np.abs(To)).max() < tol
+        rel = np.abs(Tg - To) / np.abs(To)
+        if shift == 0.0:
+            # far field: a few ulp; analytic near field: libm log/atan2 differences amplified by the
+            # conditioning of the potential formula (thin_wall.F90:1966-1983)
+            far = qo <= 10
+            assert rel[far].max() < 2e-14 and rel[~far].max() < 2e-13, (rel[far].max(), rel[~far].max())
+        else:
+            assert rel.max() < 1e-9
 
 
 def test_phipot():
