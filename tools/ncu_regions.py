@@ -30,12 +30,12 @@ def func_of(frames):
     names = []
     for f, n in frames:
         if f == 'tw_device.cuh':
-            if 82 <= n <= 90: names.append('rsqrt_fast')
-            elif 92 <= n <= 110: names.append('iquad_exact')
-            elif 112 <= n <= 130: names.append('iquad_fast/x-ops')
-            elif 131 <= n <= 175: names.append('phipot')
-            elif 176 <= n <= 190: names.append('tri_normal')
-            else: names.append('device.cuh:%d' % n)
+            for lo, hi, nm in DEVREG:
+                if lo <= n <= hi:
+                    names.append(nm)
+                    break
+            else:
+                names.append('device.cuh:%d' % n)
         elif f == 'tw_lmat.cu':
             for lo, hi, nm in REG:
                 if lo <= n <= hi:
@@ -49,6 +49,12 @@ def func_of(frames):
 
 
 REG = []
+DEVREG = []
+_dev = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'openfusiontoolkit_b200', 'csrc', 'tw_device.cuh')).read().splitlines()
+_heads = [(i + 1, re.search(r'(\w+)\(', l).group(1)) for i, l in enumerate(_dev) if l.startswith('__device__') and re.search(r'\w+\(', l)]
+_heads = [(ln, re.sub(r'^(xmul|xadd|xsub|xdot|xquad)$', 'x-ops', nm)) for ln, nm in _heads]
+for k, (ln, nm) in enumerate(_heads):
+    DEVREG.append((ln, (_heads[k + 1][0] - 1) if k + 1 < len(_heads) else len(_dev), nm))
 src_lines = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'openfusiontoolkit_b200', 'csrc', 'tw_lmat.cu')).read().splitlines()
 # regions from "// @region name" markers or function heads
 marks = [(i + 1, re.search(r'@region (\S+)', l).group(1)) for i, l in enumerate(src_lines) if '@region' in l]
