@@ -16,6 +16,8 @@ struct DevicePatchSet {
   double* geom = nullptr;
   int *dmin = nullptr, *dmax = nullptr, *chunk_dof = nullptr, *inc_ptr = nullptr;
   uint16_t* inc = nullptr;
+  ChunkAux* aux = nullptr;   // [nchunk] index records of the L kernel
+  int nchunk = 0;
   int *patch_chunk_ptr = nullptr, *dof_orig = nullptr;
   size_t bytes = 0;  // host->device bytes of the last upload
   std::string upload_from(const PatchSet& ps);

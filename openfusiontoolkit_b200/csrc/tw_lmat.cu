@@ -41,22 +41,18 @@ namespace twk {
 
 using tw::kCH;
 using tw::kGeomRows;
-#ifndef TW_LMAT_CTAS_PER_SM
-#define TW_LMAT_CTAS_PER_SM 1
-#endif
-constexpr int kCtasPerSM = TW_LMAT_CTAS_PER_SM;
-constexpr int NT = 512 / kCtasPerSM;  // threads per CTA
+constexpr int NT = 512;            // threads per CTA (one persistent CTA per SM, 128 registers per thread)
 constexpr int NW = NT / 32;
-constexpr int CI = kCH / kCtasPerSM;  // row cells per pass: a pass evaluates CI x kCH cell pairs
-constexpr int kGeomL = 19;         // geometry rows the L kernel stages (vertices, area, qbasis)
+constexpr int CI = kCH;            // row cells per pass: a pass evaluates one pair of chunks, CI x kCH cell pairs
+constexpr int kGeomL = 22;         // geometry rows the L kernel stages (vertices, area, qbasis, phipot normal)
+static_assert(CI == tw::kRowHalf, "row block of the plan records");
 constexpr int TS = kCH + 1;        // row stride of the T tile (bank-conflict-free column access)
 constexpr int NCLS = 12;           // far classes 0..6 (iquad 4..10), near classes 7..11 (28,33,46,55,72 points)
 constexpr int kListCap = CI * kCH + NCLS * 32;
-constexpr int kTabMaxN = kCtasPerSM == 1 ? 25 : 16;  // largest rule served from shared-memory point tables
-constexpr int kTabClsMax = kCtasPerSM == 1 ? 6 : 4;   // ... as a far class index
-constexpr int kTabPts = kCtasPerSM == 1 ? 34 : 16;    // points the table pool holds (several rules at once)
+constexpr int kTabMaxN = 25;       // largest rule served from shared-memory point tables
+constexpr int kTabClsMax = 6;      // ... as a far class index
+constexpr int kTabPts = 34;        // points the table pool holds (several rules at once)
 constexpr int kTabMin = 64;        // fewer pairs of a rule than this: evaluate from the vertices instead
-constexpr int UB = 32, US = UB + 1;  // column-DOF block of the contraction and its padded stride
 
 __device__ __constant__ int c_cls_np[NCLS] = {6, 7, 12, 15, 16, 19, 25, 28, 33, 46, 55, 72};
 __device__ __forceinline__ int cls_of(int iq) {
@@ -67,13 +63,9 @@ struct LmatArgs {
   // row side / column side patch sets (same pointers for self inductance)
   const tw::ChunkMeta *chunksA, *chunksB;
   const double *geomA, *geomB;
-  const int *dminA, *dmaxA, *dminB, *dmaxB;
-  const int *chunk_dofA, *chunk_dofB;
-  const int *inc_ptrA, *inc_ptrB;
-  const uint16_t *incA, *incB;
   const int *patch_chunk_ptrA, *patch_chunk_ptrB;
-  const int *dof_origA, *dof_origB;   // internal -> reference DOF id
-  const int *row_out;                 // internal row DOF -> output row index or -1
+  const tw::ChunkAux *auxA, *auxB;    // per-chunk index records
+  const int *chunk_row;               // [chunk of A][kMaxChunkDof] output row of each local DOF or -1 (this launch)
   const tw::Tile* tiles;
   int ntiles;
   int* tile_counter;
@@ -81,42 +73,71 @@ struct LmatArgs {
   long long ld;
   double scale;                       // 1/(4 pi)
   int self;                           // 1: self inductance (role rule, mirror), 0: mutual
-  int debug_skip;                     // profiling aid: bit0 skip near-field evaluation, bit1 skip far-field evaluation
+  int debug_skip;                     // profiling aid: bit0 skip near-field evaluation, bit1 skip far-field evaluation,
+                                      // bit2 skip the contraction
   unsigned long long* stats;          // [0] far pairs, [1] near T evaluations, [2] 1/r evaluations, [3] phipot evals
 };
 
+// one staged chunk (row or column side): SoA geometry record + index record + output rows, each
+// filled by one bulk async copy
+struct alignas(16) ChunkState {
+  double g[kGeomL * kCH];             // rows 0-8 vertices, 9 area, 10-18 qbasis, 19-21 unit normal (phipot's)
+  tw::ChunkAux x;
+  int row[tw::kMaxChunkDof];          // output rows (or -1)
+  double cx, cy, cz, rad;
+  int ncell, ndof;
+  unsigned long long bar;             // mbarrier of the bulk copies
+};
+static_assert(offsetof(ChunkState, x) % 16 == 0 && offsetof(ChunkState, row) % 16 == 0, "bulk copy alignment");
+
+// classification result of one pass (CI x kCH cell pairs): pair lists binned by rule + the work queue
+struct PassBuf {
+  unsigned short list[kListCap];      // pair ids (c1l<<6|c2) sorted by class, bins padded with 0xFFFF
+  unsigned char iqmap[CI * kCH];      // iquad | need-role-1 << 5 | need-role-2 << 6
+  int cnt[NCLS], off[NCLS + 1], fill[NCLS];
+  int qcls[NCLS + 8], qnb[NCLS + 8], qpt[NCLS + 8];  // queue items: class (| 16 = table), batches, table offset
+  int gq0[8], gq1[8], gnb[8], ng;     // table groups: item range and batch count
+  int qhead, both_count;
+};
+
 struct Smem {
-  double gI[kGeomL * kCH];
-  double gJ[kGeomL * kCH];
-  double T[CI * TS];
-  union {
+  ChunkState I;                       // row chunk
+  ChunkState J[2];                    // column chunks: the one in use and the next one (prefetched)
+  PassBuf pb;
+  alignas(16) double T[CI * TS];
+  union {                             // phases that never overlap share this region
     struct {
       double2 tabI[kTabPts * 2 * CI];   // per rule [(p*2+h)*CI + c1]: h=0 (-2x,-2y), h=1 (-2z,|x|^2)
       double2 tabJ[kTabPts * 2 * kCH];  //          [(p*2+h)*kCH + c2]: h=0 (x,y),    h=1 (z,|x|^2)
     } tab;
-    double U[3 * CI * US];               // [comp][c1][b] partial sums of the contraction
     struct {
-      float vfI[9 * CI], vfJ[9 * kCH];   // vertices in the local frame, FP32 (order screening)
-      float flI[CI], flJ[kCH];           // 2 * area
-    } scr;
-  } w;
-  double nI[3 * kCH];   // unit normals (reference formula) of row / column cells
-  double nJ[3 * kCH];
-  unsigned short list[kListCap];     // pair ids (c1<<6|c2) sorted by class, bins padded with 0xFFFF
-  unsigned char iqmap[CI * kCH];     // iquad | need-role-1 << 5 | need-role-2 << 6
-  int dminI[kCH], dmaxI[kCH], dminJ[kCH], dmaxJ[kCH];
-  int origI[tw::kMaxChunkDof], origJ[tw::kMaxChunkDof];  // reference DOF ids
-  int rowI[tw::kMaxChunkDof], rowJ[tw::kMaxChunkDof];    // output rows (or -1)
-  int iptrI[tw::kMaxChunkDof + 1], iptrJ[tw::kMaxChunkDof + 1];
-  unsigned char hasI[tw::kMaxChunkDof];  // bit h: the DOF has a cell in row pass h of the chunk
-  uint16_t incI[tw::kMaxChunkInc], incJ[tw::kMaxChunkInc];
-  unsigned long long bar[2];
-  int cnt[NCLS], off[NCLS + 1], fill[NCLS];
-  int qcls[NCLS + 8], qnb[NCLS + 8], qpt[NCLS + 8];  // work-queue items: class (| 16 = table), batches, table offset
-  int gq0[8], gq1[8], gnb[8], ng;                    // table groups: item range and batch count
-  int qhead, both_count;
+      float vfI[9 * CI], vfJ[9 * kCH];  // vertices in the local frame, FP32 (order screening)
+      float flI[CI], flJ[kCH];          // 2 * area
+      char pad[kTabPts * 2 * CI * 16 - (9 * CI + 9 * kCH + CI + kCH) * 4];  // (the contraction scratch starts at tabJ)
+      double P[NW][3 * CI];             // per warp: products of the contraction
+    } w;
+  } u;
   int tile_id;
+#ifdef TW_LMAT_PROF
+  long long prof[16], prof_last[2];
+#endif
 };
+static_assert(sizeof(Smem) <= 232448, "shared memory of one CTA");
+template <int N> struct ShowSize;
+#ifdef TW_SHOW_SMEM
+ShowSize<sizeof(Smem)> show_smem_size;
+#endif
+#ifdef TW_LMAT_PROF
+// section timing of CTA 0 (tuning builds only): who = 0 service thread 0, 1 evaluation thread 0
+#define TW_MARK(S, who, t, i)                                   \
+  if ((t) == 0 && blockIdx.x == 0) {                            \
+    const long long now_ = clock64();                           \
+    (S).prof[i] += now_ - (S).prof_last[who];                   \
+    (S).prof_last[who] = now_;                                  \
+  }
+#else
+#define TW_MARK(S, who, t, i)
+#endif
 
 // ---- far field from the vertices (rules without a table / tiny bins) --------------------------
 // T = area_i area_j sum_p sum_q w_p w_q / |x_p(i) - x_q(j)|, same rule on both triangles
@@ -167,7 +188,7 @@ __device__ __forceinline__ double far_pair(const double* __restrict__ gI, int c1
   return total * gI[9 * kCH + c1] * gJ[9 * kCH + c2];
 }
 
-__device__ __forceinline__ double far_dispatch(const double* gI, int c1, const double* gJ, int c2, int iquad) {  // @region far_dispatch
+__device__ __noinline__ double far_dispatch(const double* gI, int c1, const double* gJ, int c2, int iquad) {  // @region far_dispatch
   switch (iquad) {
     case 4: return far_pair<6>(gI, c1, gJ, c2, iquad);
     case 5: return far_pair<7>(gI, c1, gJ, c2, iquad);
@@ -202,9 +223,14 @@ __device__ __forceinline__ double far_tab(const double2* __restrict__ tabI, cons
       sj[q] = v.y;
       acc[q] = 0.0;
     }
+    double2 an = tabI[c1], bn = tabI[CI + c1];  // row point p+1 is loaded while point p is evaluated
 #pragma unroll(N <= 7 ? N : 2)
     for (int p = 0; p < N; p++) {
-      const double2 a = tabI[(p * 2) * CI + c1], b = tabI[(p * 2 + 1) * CI + c1];
+      const double2 a = an, b = bn;
+      if (p + 1 < N) {
+        an = tabI[((p + 1) * 2) * CI + c1];
+        bn = tabI[((p + 1) * 2 + 1) * CI + c1];
+      }
       const double wp = bw[p];
       double d2[QB], y0[QB], e[QB], h[QB];
 #pragma unroll
@@ -279,14 +305,7 @@ __device__ __forceinline__ double near_pair(const double* gA, const double* nA, 
 // vI/vJ: vertices in a common local frame rounded to FP32 (|v| <= X); delta = bound of the
 // coordinate error of a vertex DIFFERENCE (input rounding of both operands, = 2^-23 X * 1.01).
 // Returns iquad, or -1 when the decision is not safe in FP32.
-__device__ __forceinline__ int iquad_screen(const float* __restrict__ vI, int sI, int c1, const float* __restrict__ vJ, int c2,  // @region iquad_screen
-                                            float fl2, float delta) {
-  float pi_[9], pj_[9];
-#pragma unroll
-  for (int k = 0; k < 9; k++) {
-    pi_[k] = vI[k * sI + c1];
-    pj_[k] = vJ[k * kCH + c2];
-  }
+__device__ __forceinline__ int iquad_screen(const float (&pi_)[9], const float (&pj_)[9], float fl2, float delta) {  // @region iquad_screen
   float d2min = 3.0e38f, d2max = 0.0f;
 #pragma unroll
   for (int a = 0; a < 3; a++)
@@ -379,76 +398,246 @@ __device__ __forceinline__ void build_table(double2* __restrict__ tab, int ts, c
   }
 }
 
-__device__ __forceinline__ void load_chunk(Smem& S, int side, const LmatArgs& A, int chunk, unsigned long long* bar,  // @region load_chunk
-                                           uint32_t& phase) {
-  // side 0: row chunk (I), 1: column chunk (J).  Geometry record via one bulk async copy issued
-  // by a single thread; the small index lists by all threads; normals computed after arrival.
-  const tw::ChunkMeta* cms = side ? A.chunksB : A.chunksA;
-  const double* geom = side ? A.geomB : A.geomA;
-  double* g = side ? S.gJ : S.gI;
-  const tw::ChunkMeta cm = cms[chunk];
-  if (threadIdx.x == 0) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order prior generic accesses before the async write
-    mbar_expect_tx(bar, kGeomL * kCH * 8);
-    bulk_g2s(g, geom + (size_t)chunk * kGeomRows * kCH, kGeomL * kCH * 8, bar);
+// ---- staging of a chunk (one service thread) ---------------------------------------------------------
+// side 0: row chunk, 1: column chunk.  Three bulk async copies (geometry rows, index record, output rows of
+// this launch) complete on the slot's mbarrier; nothing is read from global memory by the other threads.
+__device__ __forceinline__ void stage_issue(ChunkState& C, int side, const LmatArgs& A, int chunk) {  // @region stage_issue
+  const bool rows = side == 0 || A.self;  // rows of the column side exist only for self inductance (mirror writes)
+  const uint32_t bytes = kGeomL * kCH * 8 + (uint32_t)sizeof(tw::ChunkAux) + (rows ? (uint32_t)sizeof(C.row) : 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order prior generic accesses before the async writes
+  mbar_expect_tx(&C.bar, bytes);
+  bulk_g2s(C.g, (side ? A.geomB : A.geomA) + (size_t)chunk * kGeomRows * kCH, kGeomL * kCH * 8, &C.bar);
+  bulk_g2s(&C.x, (side ? A.auxB : A.auxA) + chunk, (uint32_t)sizeof(tw::ChunkAux), &C.bar);
+  if (rows) bulk_g2s(C.row, A.chunk_row + (size_t)chunk * tw::kMaxChunkDof, (uint32_t)sizeof(C.row), &C.bar);
+  const tw::ChunkMeta cm = (side ? A.chunksB : A.chunksA)[chunk];
+  C.ncell = cm.ncell;
+  C.ndof = cm.ndof;
+  C.cx = cm.cx;
+  C.cy = cm.cy;
+  C.cz = cm.cz;
+  C.rad = cm.rad;
+}
+
+// ---- prep: classification of the CI x kCH cell pairs of a pass, binned by rule -------------------------
+// Stage 0 (before the pass barrier): FP32 local-frame copies of the vertices and the bin counters.
+__device__ __forceinline__ void prep_stage(Smem& S, const ChunkState& I, const ChunkState& J, int tid) {  // @region A0_fp32_stage
+  PassBuf& pb = S.pb;
+  // local frame: midpoint of the two chunk centres
+  const double ox = 0.5 * (I.cx + J.cx), oy = 0.5 * (I.cy + J.cy), oz = 0.5 * (I.cz + J.cz);
+  for (int i = tid; i < 9 * kCH; i += NT) {
+    const int k = i / kCH, dd = k % 3;
+    const double o = dd == 0 ? ox : (dd == 1 ? oy : oz);
+    S.u.w.vfJ[i] = (float)(J.g[i] - o);
+    S.u.w.vfI[i] = (float)(I.g[i] - o);
   }
-  const int* dmn = (side ? A.dminB : A.dminA) + (size_t)chunk * kCH;
-  const int* dmx = (side ? A.dmaxB : A.dmaxA) + (size_t)chunk * kCH;
-  const int* cdof = (side ? A.chunk_dofB : A.chunk_dofA) + cm.dof_off;
-  const int* iptr = (side ? A.inc_ptrB : A.inc_ptrA) + cm.dof_off + chunk;
-  const uint16_t* inc = (side ? A.incB : A.incA) + cm.inc_off;
-  const int* dorig = side ? A.dof_origB : A.dof_origA;
-  int* sdmn = side ? S.dminJ : S.dminI;
-  int* sdmx = side ? S.dmaxJ : S.dmaxI;
-  int* sorig = side ? S.origJ : S.origI;
-  int* srow = side ? S.rowJ : S.rowI;
-  int* sptr = side ? S.iptrJ : S.iptrI;
-  uint16_t* sinc = side ? S.incJ : S.incI;
-  for (int i = threadIdx.x; i < kCH; i += NT) {
-    sdmn[i] = dmn[i];
-    sdmx[i] = dmx[i];
+  for (int i = tid; i < kCH; i += NT) {
+    S.u.w.flJ[i] = (float)(2.0 * J.g[9 * kCH + i]);
+    S.u.w.flI[i] = (float)(2.0 * I.g[9 * kCH + i]);
   }
-  for (int i = threadIdx.x; i < cm.ndof; i += NT) {
-    const int d = cdof[i];
-    sorig[i] = dorig[d];
-    // rows of the column side exist only for self inductance (mirror writes)
-    srow[i] = (side == 0 || A.self) ? A.row_out[d] : -1;
-  }
-  for (int i = threadIdx.x; i <= cm.ndof; i += NT) sptr[i] = iptr[i];
-  const int ninc = iptr[cm.ndof];
-  for (int i = threadIdx.x; i < ninc; i += NT) sinc[i] = inc[i];
-  mbar_wait(bar, phase);
-  phase ^= 1;
-  double* nn = side ? S.nJ : S.nI;
-  for (int c = threadIdx.x; c < kCH; c += NT) {
-    double P[9], n[3] = {0.0, 0.0, 1.0};
-#pragma unroll
-    for (int k = 0; k < 9; k++) P[k] = g[k * kCH + c];
-    if (c < cm.ncell) tri_normal(P, n);
-    nn[c] = n[0];
-    nn[kCH + c] = n[1];
-    nn[2 * kCH + c] = n[2];
+  if (tid < NCLS) pb.cnt[tid] = 0;
+  if (tid == 0) {
+    pb.both_count = 0;
+    pb.qhead = 0;
   }
 }
 
+// Stage 1 (after the pass barrier).  No atomics or warp votes inside the pair loop: every thread keeps a
+// packed histogram of its pairs; one warp scan gives the lane offsets and one shared atomic per (warp, class)
+// the warp's share of the bin.  Ends with the bins and the work queue complete (two barriers inside).
+__device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int flags, int tid,
+                                              unsigned long long& st_far, unsigned long long& st_eval) {
+  PassBuf& pb = S.pb;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int ncI = I.ncell, ncJ = J.ncell;
+  const bool diag = flags & 1, want2 = (flags & 4) && A.self;
+  float delta;
+  {
+    const double hx = 0.5 * (I.cx - J.cx), hy = 0.5 * (I.cy - J.cy), hz = 0.5 * (I.cz - J.cz);
+    const double X = sqrt(hx * hx + hy * hy + hz * hz) + fmax(I.rad, J.rad);
+    delta = (float)(X * 1.21e-7);  // two operands, each rounded to FP32 (2^-24 relative), 1% slack
+  }
+  // ---------------- classification --------------------------------------------------------------------  // @region A_classify
+  // a thread owns one row cell c1 and the kCH/TPR columns c2 = NIT * (t % TPR) + m: the pairs of a thread,
+  // and of the TPR threads of a row, are consecutive in a bin, so a batch of 32 pairs of the evaluation
+  // reads few distinct row-side table entries (broadcast) and consecutive column-side entries
+  constexpr int TPR = NT / CI, NIT = kCH / TPR;
+  static_assert(NIT <= 8 && TPR * CI == NT && NIT * TPR == kCH, "4-bit per-thread class counts");
+  unsigned mycls = 0;            // 4 bits per iteration: class + 1, 0 = no pair
+  unsigned long long hist = 0;   // 4 bits per class: pairs of this thread
+  int nboth = 0;
+  const int c1 = tid / TPR, c2b = NIT * (tid % TPR);
+  if (c1 < ncI) {
+    float pi_[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) pi_[k] = S.u.w.vfI[k * CI + c1];
+    const float fli = S.u.w.flI[c1];
+    const int dminI = I.x.dmin[c1], dmaxI = I.x.dmax[c1];
+#pragma unroll 2
+    for (int m = 0; m < NIT; m++) {
+      const int c2 = c2b + m;
+      if (c2 < ncJ) {
+        bool n1, n2 = false;
+        if (A.self) {
+          n1 = dminI <= J.x.dmax[c2];
+          n2 = want2 && !diag && (dmaxI > J.x.dmin[c2]);
+        } else {
+          n1 = true;
+        }
+        if (n1 || n2) {
+          float pj_[9];
+#pragma unroll
+          for (int k = 0; k < 9; k++) pj_[k] = S.u.w.vfJ[k * kCH + c2];
+          int iq = iquad_screen(pi_, pj_, fmaxf(fli, S.u.w.flJ[c2]), delta);
+          if (iq < 0) iq = iquad_exact_cells(I.g, c1, J.g, c2);
+          const int cls = cls_of(iq);
+          if (cls >= 7) {  // near pairs carry their order and roles (T of unused pairs is never read by a used entry)
+            pb.iqmap[c1 * kCH + c2] = (unsigned char)((unsigned)iq | (n1 ? 32u : 0u) | (n2 ? 64u : 0u));
+            nboth += (n1 && n2) ? 1 : 0;
+          }
+          mycls |= (unsigned)(cls + 1) << (4 * m);
+          hist += 1ull << (4 * cls);
+        }
+      }
+    }
+  }
+  TW_MARK(S, 0, tid, 5)
+  // ---------------- bins: warp scan of the packed histograms (10-bit fields, 6 classes per word) -----------  // @region B_bin
+  unsigned long long h0 = 0, h1 = 0;
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    h0 |= ((hist >> (4 * c)) & 15ull) << (10 * c);
+    h1 |= ((hist >> (4 * (c + 6))) & 15ull) << (10 * c);
+  }
+  unsigned long long s0 = h0, s1 = h1;  // inclusive scan over the lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
+    if (lane >= o) {
+      s0 += t0;
+      s1 += t1;
+    }
+  }
+  const unsigned long long w0 = __shfl_sync(0xffffffffu, s0, 31), w1 = __shfl_sync(0xffffffffu, s1, 31);  // warp totals
+  s0 -= h0;  // exclusive
+  s1 -= h1;
+  int wbase = 0;  // lane c < NCLS: offset of this warp's pairs within bin c
+  if (lane < NCLS) {
+    const int tot = (int)(((lane < 6 ? w0 : w1) >> (10 * (lane % 6))) & 1023ull);
+    if (tot) wbase = atomicAdd(&pb.cnt[lane], tot);
+  }
+  nboth = __reduce_add_sync(0xffffffffu, nboth);
+  if (lane == 0 && nboth) atomicAdd(&pb.both_count, nboth);
+  __syncthreads();
+  TW_MARK(S, 0, tid, 6)
+  // bin offsets: near classes (largest rules) first; bins padded to whole batches
+  int start = 0;  // lane c < NCLS: first list slot of this warp's pairs of class c
+  if (lane < NCLS) {
+    int o = 0;
+    for (int c = NCLS - 1; c > lane; c--) {
+      const int n = pb.cnt[c];
+      o += c >= 7 ? ((n + 1) & ~1) : ((n + 31) & ~31);
+    }
+    start = o + wbase;
+    if (warp == 0) {
+      const int n = pb.cnt[lane];
+      pb.off[lane] = o;
+      const int padded = lane >= 7 ? ((n + 1) & ~1) : ((n + 31) & ~31);
+      for (int i = n; i < padded; i++) pb.list[o + i] = 0xFFFFu;  // padding of the last batch
+    }
+  }
+  // the work queue (one thread, working from registers: the counts are loaded first, all loops are unrolled).
+  // Items: near classes (largest rules first), far bins too small for a table (evaluated from the vertices),
+  // then the table rules by decreasing size.  Table rules are packed into groups whose point tables fit the
+  // shared-memory pool together; a group is one barrier interval.
+  if (tid == NT - 1) {
+    int n_[NCLS];
+#pragma unroll
+    for (int c = 0; c < NCLS; c++) n_[c] = pb.cnt[c];
+    int nb = 0, nq = 0, ng = 0, pts = 0;
+    unsigned long long fp = 0, ev = 0;
+    pb.gq0[0] = 0;
+#pragma unroll
+    for (int c = NCLS - 1; c >= 0; c--) {
+      const int n = n_[c];
+      const bool near_c = c >= 7;
+      const bool c0 = near_c || c > kTabClsMax || n < kTabMin;  // evaluated analytically / from the vertices
+      if (n > 0 && c0) {
+        const int nbat = near_c ? (n + 1) / 2 : (n + 31) / 32;
+        pb.qcls[nq] = c;
+        pb.qnb[nq] = nbat;
+        nb += nbat;
+        nq++;
+      }
+      if (!near_c) {
+        constexpr int np2[7] = {36, 49, 144, 225, 256, 361, 625};
+        fp += n;
+        ev += (unsigned long long)(n * np2[c < 7 ? c : 0]);
+      }
+    }
+#pragma unroll
+    for (int c = kTabClsMax; c >= 0; c--) {
+      const int n = n_[c];
+      if (n < kTabMin) continue;
+      constexpr int npc[7] = {6, 7, 12, 15, 16, 19, 25};
+      const int np = npc[c];
+      if (pts + np > kTabPts) {  // close the group
+        pb.gq1[ng] = nq;
+        pb.gnb[ng] = nb;
+        ng++;
+        pb.gq0[ng] = nq;
+        nb = 0;
+        pts = 0;
+      }
+      const int nbat = (n + 31) / 32;
+      pb.qcls[nq] = c | 16;  // bit 4: evaluate from the tables
+      pb.qnb[nq] = nbat;
+      pb.qpt[nq] = pts;
+      nb += nbat;
+      pts += np;
+      nq++;
+    }
+    pb.gq1[ng] = nq;
+    pb.gnb[ng] = nb;
+    pb.ng = ng + 1;
+    st_far += fp;
+    st_eval += ev;
+  }
+  // ---------------- scatter the pair ids into the bins ------------------------------------------------------  // @region B_scatter
+  unsigned long long used = 0;  // 4 bits per class: pairs of this thread already placed
+#pragma unroll 1
+  for (int m = 0; m < NIT; m++) {
+    const int cls = (int)((mycls >> (4 * m)) & 15u) - 1;
+    const int st = __shfl_sync(0xffffffffu, start, cls < 0 ? 0 : cls);
+    if (cls >= 0) {
+      const int excl = (int)(((cls < 6 ? s0 : s1) >> (10 * (cls % 6))) & 1023ull);
+      const int mine = (int)((used >> (4 * cls)) & 15ull);
+      used += 1ull << (4 * cls);
+      pb.list[st + excl + mine] = (unsigned short)(c1 * kCH + c2b + m);
+    }
+  }
+  __syncthreads();  // lists, queue; the FP32 scratch is dead: the table region may be written
+}
+
+// ---- evaluation: T(c1,c2) of one pass -----------------------------------------------------------------
 // one batch of the work queue: 32 far pairs of one rule (from the vertices) or 2 near pairs.
-// List entries are (c1l<<6 | c2) with c1l the row cell within the pass; c1 = cbase + c1l.
-__device__ __forceinline__ void run_batch_c0(Smem& S, int cbase, int cls, int first, int lane, bool role2_pass,  // @region run_batch_c0
-                                             unsigned long long& st_near, unsigned long long& st_phi) {
+// List entries are (c1<<6 | c2).
+__device__ __forceinline__ void run_batch_c0(const ChunkState& I, const ChunkState& J, const PassBuf& pb, double* __restrict__ T,  // @region run_batch_c0
+                                             int cls, int first, int lane, bool role2_pass, unsigned long long& st_near,
+                                             unsigned long long& st_phi) {
   if (cls < 7) {
-    const unsigned e = S.list[first + lane];
+    const unsigned e = pb.list[first + lane];
     if (e != 0xFFFFu) {
-      const int c1l = e >> 6, c2 = e & 63;
-      S.T[c1l * TS + c2] = far_dispatch(S.gI, cbase + c1l, S.gJ, c2, cls + 4);
+      const int c1 = e >> 6, c2 = e & 63;
+      T[c1 * TS + c2] = far_dispatch(I.g, c1, J.g, c2, cls + 4);
     }
   } else {
     const int hw = lane >> 4, hl = lane & 15;
-    const unsigned e = S.list[first + hw];
+    const unsigned e = pb.list[first + hw];
     unsigned m = 0;
-    int c1l = 0, c2 = 0, iq = 18;
+    int c1 = 0, c2 = 0, iq = 18;
     if (e != 0xFFFFu) {
-      m = S.iqmap[e];
-      c1l = e >> 6;
+      m = pb.iqmap[e];
+      c1 = e >> 6;
       c2 = e & 63;
       iq = m & 31;
     }
@@ -458,10 +647,10 @@ __device__ __forceinline__ void run_batch_c0(Smem& S, int cbase, int cls, int fi
     if (do1 || do2) {  // uniform per half-warp; the shuffles name only this half
       const unsigned mask = 0xFFFFu << (16 * hw);
       double v;
-      if (do2) v = near_pair(S.gJ, S.nJ, c2, S.gI, cbase + c1l, iq, hl, 16, mask);
-      else v = near_pair(S.gI, S.nI, cbase + c1l, S.gJ, c2, iq, hl, 16, mask);
+      if (do2) v = near_pair(J.g, J.g + 19 * kCH, c2, I.g, c1, iq, hl, 16, mask);
+      else v = near_pair(I.g, I.g + 19 * kCH, c1, J.g, c2, iq, hl, 16, mask);
       if (hl == 0) {
-        S.T[c1l * TS + c2] = v;
+        T[c1 * TS + c2] = v;
         st_near++;
         st_phi += c_qnp[iq];
       }
@@ -469,17 +658,232 @@ __device__ __forceinline__ void run_batch_c0(Smem& S, int cbase, int cls, int fi
   }
 }
 
-__global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArgs A) {  // @region kernel_head
+__device__ __forceinline__ void eval_pass(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int tid,
+                                          unsigned long long& st_near, unsigned long long& st_phi) {
+  PassBuf& pb = S.pb;
+  double* __restrict__ T = S.T;
+  const int lane = tid & 31;
+  const int ncI = I.ncell, ncJ = J.ncell;
+  const double ox = 0.5 * (I.cx + J.cx), oy = 0.5 * (I.cy + J.cy), oz = 0.5 * (I.cz + J.cz);
+  const int ngroups = pb.ng;
+#pragma unroll 1
+  for (int g = 0; g < ngroups; g++) {  // @region C_eval
+    if (g > 0) {
+      __syncthreads();  // previous group is done with the table pool and the queue head
+      if (tid == 0) pb.qhead = 0;
+    }
+    const int q0 = pb.gq0[g], q1 = pb.gq1[g], total = pb.gnb[g];
+    bool any_tab = false;
+    for (int k = q0; k < q1; k++) {
+      const int qc = pb.qcls[k];
+      if (!(qc & 16)) continue;
+      any_tab = true;
+      const int cls = qc & 15, pt = pb.qpt[k];
+      build_table(S.u.tab.tabI + pt * 2 * CI, CI, I.g, 0, ncI, cls + 4, c_cls_np[cls], ox, oy, oz, true, tid, NT);
+      build_table(S.u.tab.tabJ + pt * 2 * kCH, kCH, J.g, 0, ncJ, cls + 4, c_cls_np[cls], ox, oy, oz, false, tid, NT);
+    }
+    if (any_tab || g > 0) __syncthreads();
+    // dynamic queue; the next batch index is fetched while the current batch is evaluated
+    int bnext = 0;
+    if (lane == 0) bnext = atomicAdd(&pb.qhead, 1);
+    for (;;) {
+      const int b = __shfl_sync(0xffffffffu, bnext, 0);
+      if (b >= total) break;
+      if (lane == 0) bnext = atomicAdd(&pb.qhead, 1);
+      int k = q0, lb = b;
+      while (lb >= pb.qnb[k]) {
+        lb -= pb.qnb[k];
+        k++;
+      }
+      const int qc = pb.qcls[k], cls = qc & 15;
+      if (A.debug_skip && ((cls >= 7) ? (A.debug_skip & 1) : (A.debug_skip & 2))) continue;
+      if (qc & 16) {
+        const unsigned e = pb.list[pb.off[cls] + lb * 32 + lane];
+        if (e != 0xFFFFu) {
+          const int c1 = e >> 6, c2 = e & 63, pt = pb.qpt[k];
+          T[c1 * TS + c2] = far_tab_dispatch(S.u.tab.tabI + pt * 2 * CI, S.u.tab.tabJ + pt * 2 * kCH, c1, c2, cls) * I.g[9 * kCH + c1] *
+                            J.g[9 * kCH + c2];
+        }
+      } else {
+        run_batch_c0(I, J, pb, T, cls, pb.off[cls] + lb * (cls >= 7 ? 2 : 32), lane, false, st_near, st_phi);
+      }
+    }
+  }
+}
+
+// second role: re-evaluate the near pairs that need both roles (all other T values stay)
+__device__ __forceinline__ void eval_role2(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int tid,  // @region C_role2
+                                           unsigned long long& st_near, unsigned long long& st_phi) {
+  PassBuf& pb = S.pb;
+  const int lane = tid & 31;
+  int nearb = 0, first_cls_off[5], first_cls_nb[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    first_cls_off[k] = pb.off[11 - k];
+    first_cls_nb[k] = (pb.cnt[11 - k] + 1) / 2;
+    nearb += first_cls_nb[k];
+  }
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(&pb.qhead, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= nearb) break;
+    int k = 0, lb = b;
+    while (lb >= first_cls_nb[k]) {
+      lb -= first_cls_nb[k];
+      k++;
+    }
+    if (A.debug_skip & 1) continue;
+    run_batch_c0(I, J, pb, S.T, 11 - k, first_cls_off[k] + lb * 2, lane, true, st_near, st_phi);
+  }
+}
+
+// ---- drain: contraction of T onto the DOFs, added into L ------------------------------------------------
+// A warp takes column DOFs b = warp, warp+16, ... in blocks of DB.  For a block the old values of all its
+// entries (row DOFs a = lane, lane+32; entry (a,b) and its mirror) are loaded first, so one memory latency is
+// paid per block.  Then per b -- stage 1, lanes = row cells c1 (two per lane):
+// u(c1) = sum_{(c2,k2) of b} +-q2[c2][k2] T[c1][c2]; the three products q1[c1][k].u(c1) (cell c1's contribution
+// to its vertices) go to a per-warp scratch; stage 2, lanes = row DOFs a: sum of the scratch entries of a's
+// cells, added to the old value and stored.  Every entry is owned by this CTA: plain loads and stores, no
+// atomics, no block-wide barriers.
+// role_sel 0: all entries; 1: only entries with a <= b (a second-role pass follows); 2: only a > b
+struct DrainSel {
+  const LmatArgs* A;
+  bool diag, mirror;
+  int role_sel;
+  // output addresses of entry (ia, ib) and of its mirror; false if the entry is not written in this pass
+  __device__ __forceinline__ bool addr(const ChunkState& I, const ChunkState& J, int ia, int ib, double*& pa, double*& pm) const {
+    pa = nullptr;
+    pm = nullptr;
+    const int oa = I.x.orig[ia], ob = J.x.orig[ib];
+    if (A->self) {
+      const bool role1 = oa <= ob;
+      if ((diag && !role1) || (role_sel == 1 && !role1) || (role_sel == 2 && role1)) return false;
+    }
+    const int ra = I.row[ia];
+    if (ra >= 0) pa = A->out + (long long)ra * A->ld + ob;
+    if (A->self && (mirror || diag) && oa != ob) {
+      const int rb = J.row[ib];
+      if (rb >= 0) pm = A->out + (long long)rb * A->ld + oa;
+    }
+    return pa || pm;
+  }
+};
+
+__device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int flags, int role_sel,  // @region D_drain
+                                           int tid) {
+  const double* __restrict__ T = S.T;
+  DrainSel sel;
+  sel.A = &A;
+  sel.diag = flags & 1;
+  sel.mirror = flags & 2;
+  sel.role_sel = role_sel;
+  const int ndI = I.ndof, ndJ = J.ndof;
+  const int lane = tid & 31, warp = tid >> 5;
+  double* __restrict__ P = S.u.w.P[warp];  // [3][CI] products of this warp
+  constexpr int DB = 4;
+#pragma unroll 1
+  for (int ib0 = warp; ib0 < ndJ; ib0 += NW * DB) {
+    // old values of the block's entries
+    double olda[DB][2], oldm[DB][2];
+#pragma unroll
+    for (int j = 0; j < DB; j++)
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        olda[j][r] = 0.0;
+        oldm[j][r] = 0.0;
+        const int ib = ib0 + j * NW, ia = lane + 32 * r;
+        if (ib < ndJ && ia < ndI) {
+          double *pa, *pm;
+          if (sel.addr(I, J, ia, ib, pa, pm)) {
+            if (pa) olda[j][r] = __ldcg(pa);
+            if (pm) oldm[j][r] = __ldcg(pm);
+          }
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < DB; j++) {
+      const int ib = ib0 + j * NW;
+      if (ib >= ndJ) break;
+      // stage 1
+      double ux0 = 0.0, uy0 = 0.0, uz0 = 0.0, ux1 = 0.0, uy1 = 0.0, uz1 = 0.0;
+      for (int i2 = J.x.iptr[ib]; i2 < J.x.iptr[ib + 1]; i2++) {
+        const unsigned w2 = J.x.inc[i2];
+        const int c2 = w2 & 63, k2 = (w2 >> 6) & 3;
+        double t0 = T[lane * TS + c2], t1 = T[(lane + 32) * TS + c2];
+        if (w2 & 256) {
+          t0 = -t0;
+          t1 = -t1;
+        }
+        const double qx = J.g[(10 + 3 * k2) * kCH + c2], qy = J.g[(11 + 3 * k2) * kCH + c2], qz = J.g[(12 + 3 * k2) * kCH + c2];
+        ux0 = fma(qx, t0, ux0);
+        uy0 = fma(qy, t0, uy0);
+        uz0 = fma(qz, t0, uz0);
+        ux1 = fma(qx, t1, ux1);
+        uy1 = fma(qy, t1, uy1);
+        uz1 = fma(qz, t1, uz1);
+      }
+      __syncwarp();  // stage 2 of the previous column DOF is done with the scratch
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        P[k * CI + lane] = fma(I.g[(12 + 3 * k) * kCH + lane], uz0, fma(I.g[(11 + 3 * k) * kCH + lane], uy0, I.g[(10 + 3 * k) * kCH + lane] * ux0));
+        P[k * CI + lane + 32] =
+            fma(I.g[(12 + 3 * k) * kCH + lane + 32], uz1, fma(I.g[(11 + 3 * k) * kCH + lane + 32], uy1, I.g[(10 + 3 * k) * kCH + lane + 32] * ux1));
+      }
+      __syncwarp();
+      // stage 2: row DOFs lane, lane+32 from the preloaded values, further row DOFs (rare) directly
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const int ia = lane + 32 * r;
+        if (ia >= ndI) continue;
+        double *pa, *pm;
+        if (!sel.addr(I, J, ia, ib, pa, pm)) continue;
+        double acc = 0.0;
+        for (int i1 = I.x.iptr[ia]; i1 < I.x.iptr[ia + 1]; i1++) {
+          const unsigned w1 = I.x.inc[i1];
+          const double v = P[((w1 >> 6) & 3) * CI + (w1 & 63)];
+          acc += (w1 & 256) ? -v : v;
+        }
+        acc *= A.scale;
+        if (pa) __stcg(pa, olda[j][r] + acc);
+        if (pm) __stcg(pm, oldm[j][r] + acc);
+      }
+#pragma unroll 1
+      for (int ia = lane + 64; ia < ndI; ia += 32) {
+        double *pa, *pm;
+        if (!sel.addr(I, J, ia, ib, pa, pm)) continue;
+        const double oa_ = pa ? __ldcg(pa) : 0.0, om_ = pm ? __ldcg(pm) : 0.0;
+        double acc = 0.0;
+        for (int i1 = I.x.iptr[ia]; i1 < I.x.iptr[ia + 1]; i1++) {
+          const unsigned w1 = I.x.inc[i1];
+          const double v = P[((w1 >> 6) & 3) * CI + (w1 & 63)];
+          acc += (w1 & 256) ? -v : v;
+        }
+        acc *= A.scale;
+        if (pa) __stcg(pa, oa_ + acc);
+        if (pm) __stcg(pm, om_ + acc);
+      }
+    }
+  }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {  // @region kernel_head
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) {
-    mbar_init(&S.bar[0], 1);
-    mbar_init(&S.bar[1], 1);
+    mbar_init(&S.I.bar, 1);
+    mbar_init(&S.J[0].bar, 1);
+    mbar_init(&S.J[1].bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+#ifdef TW_LMAT_PROF
+  if (tid < 16) S.prof[tid] = 0;
+  if (tid < 2) S.prof_last[tid] = clock64();
+#endif
   __syncthreads();
-  uint32_t phI = 0, phJ = 0;
+  uint32_t phI = 0, phJ = 0;  // mbarrier phases: row slot, bit s = column slot s
   unsigned long long st_far = 0, st_near = 0, st_eval = 0, st_phi = 0;
   if (A.stats && tid == 0 && blockIdx.x == 0) {
     unsigned long long t0;
@@ -488,326 +892,67 @@ __global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArg
   }
 
   for (;;) {
+    __syncthreads();  // the previous tile is drained (chunk slots, T and the scratch are free)
     if (tid == 0) S.tile_id = atomicAdd(A.tile_counter, 1);
     __syncthreads();
     const int t = S.tile_id;
     if (t >= A.ntiles) break;
     const tw::Tile tile = A.tiles[t];
-    const bool diag = tile.flags & 1, mirror = tile.flags & 2;
-    const bool want2 = (tile.flags & 4) && A.self;
+    const int flags = tile.flags;
     const int ci0 = A.patch_chunk_ptrA[tile.pa], ci1 = A.patch_chunk_ptrA[tile.pa + 1];
     const int cj0 = A.patch_chunk_ptrB[tile.pb], cj1 = A.patch_chunk_ptrB[tile.pb + 1];
-
+    if (ci0 >= ci1 || cj0 >= cj1) continue;
+    int js = 0;  // column slot of the current pass
+    if (tid == 0) {
+      stage_issue(S.I, 0, A, ci0);
+      stage_issue(S.J[0], 1, A, cj0);
+    }
+    __syncthreads();  // chunk headers written by the staging thread
+    mbar_wait(&S.I.bar, phI);
+    phI ^= 1;
+    TW_MARK(S, 0, tid, 0)
     for (int ci = ci0; ci < ci1; ci++) {  // @region chunk_loop
-      __syncthreads();  // previous contraction finished with the I-side lists
-      load_chunk(S, 0, A, ci, &S.bar[0], phI);
-      const tw::ChunkMeta cmI = A.chunksA[ci];
-      const int ncI = cmI.ncell, ndI = cmI.ndof;
-      __syncthreads();
-      for (int ia = tid; ia < ndI; ia += NT) {
-        unsigned hm = 0;
-        for (int i1 = S.iptrI[ia]; i1 < S.iptrI[ia + 1]; i1++) hm |= 1u << ((S.incI[i1] & 63) / CI);
-        S.hasI[ia] = (unsigned char)hm;
-      }
       for (int cj = cj0; cj < cj1; cj++) {
-        __syncthreads();  // previous contraction finished with the J-side lists / T / U
-        load_chunk(S, 1, A, cj, &S.bar[1], phJ);
-        const tw::ChunkMeta cmJ = A.chunksB[cj];
-        const int ncJ = cmJ.ncell, ndJ = cmJ.ndof;
-        // local frame: midpoint of the two chunk centres
-        const double ox = 0.5 * (cmI.cx + cmJ.cx), oy = 0.5 * (cmI.cy + cmJ.cy), oz = 0.5 * (cmI.cz + cmJ.cz);
-        float delta;
-        {
-          const double hx = 0.5 * (cmI.cx - cmJ.cx), hy = 0.5 * (cmI.cy - cmJ.cy), hz = 0.5 * (cmI.cz - cmJ.cz);
-          const double X = sqrt(hx * hx + hy * hy + hz * hz) + fmax(cmI.rad, cmJ.rad);
-          delta = (float)(X * 1.21e-7);  // two operands, each rounded to FP32 (2^-24 relative), 1% slack
-        }
-#pragma unroll 1
-        for (int cbase = 0; cbase < ncI; cbase += CI) {  // row cells [cbase, cbase + nI1) of the chunk
-          const int nI1 = min(CI, ncI - cbase);
-          if (cbase > 0) __syncthreads();  // previous pass finished with T / U / lists
-          // ---------------- phase A0: FP32 local-frame vertices, list reset ---------------------------  // @region A0_fp32_stage
-          for (int i = tid; i < 9 * kCH; i += NT) {
-            const int k = i / kCH, d = k % 3;
-            const double o = d == 0 ? ox : (d == 1 ? oy : oz);
-            S.w.scr.vfJ[i] = (float)(S.gJ[i] - o);
-          }
-          for (int i = tid; i < 9 * CI; i += NT) {
-            const int k = i / CI, c = i - k * CI, d = k % 3;
-            const double o = d == 0 ? ox : (d == 1 ? oy : oz);
-            S.w.scr.vfI[i] = (float)(S.gI[k * kCH + cbase + c] - o);
-          }
-          for (int i = tid; i < kCH; i += NT) S.w.scr.flJ[i] = (float)(2.0 * S.gJ[9 * kCH + i]);
-          for (int i = tid; i < CI; i += NT) S.w.scr.flI[i] = (float)(2.0 * S.gI[9 * kCH + cbase + i]);
-          for (int i = tid; i < kListCap; i += NT) S.list[i] = 0xFFFFu;
-          if (tid < NCLS) {
-            S.cnt[tid] = 0;
-            S.fill[tid] = 0;
-          }
-          if (tid == 0) S.both_count = 0;
+        const ChunkState& I = S.I;
+        const ChunkState& J = S.J[js];
+        mbar_wait(&S.J[js].bar, (phJ >> js) & 1u);
+        phJ ^= 1u << js;
+        prep_stage(S, I, J, tid);
+        __syncthreads();  // pass barrier: FP32 copies ready; everybody is done with the previous pass
+        TW_MARK(S, 0, tid, 1)
+        // prefetch the next column chunk (its slot was used by the previous pass)
+        const bool lastj = cj + 1 == cj1, lasti = ci + 1 == ci1;
+        if (tid == 0 && !(lastj && lasti)) stage_issue(S.J[js ^ 1], 1, A, lastj ? cj0 : cj + 1);
+        prep_classify(S, A, I, J, flags, tid, st_far, st_eval);
+        TW_MARK(S, 0, tid, 2)
+        const bool two_pass = S.pb.both_count > 0;
+        eval_pass(S, A, I, J, tid, st_near, st_phi);
+        __syncthreads();  // T complete; the table region is free for the contraction scratch
+        TW_MARK(S, 0, tid, 3)
+        if (!(A.debug_skip & 4)) drain_pass(S, A, I, J, flags, two_pass ? 1 : 0, tid);
+        if (two_pass) {
+          if (tid == 0) S.pb.qhead = 0;
+          __syncthreads();  // first contraction done with T
+          eval_role2(S, A, I, J, tid, st_near, st_phi);
           __syncthreads();
-          // ---------------- phase A: classification ----------------------------------------------------  // @region A_classify
-          // warp w handles rows c1l = (w>>1) + (NW/2) m, columns lane + 32 (w&1)
-          unsigned mycls = 0;  // 4 bits per iteration: class + 1, 0 = no pair
-          {
-            const int c2 = lane + 32 * (warp & 1);
-#pragma unroll 1
-            for (int m = 0; m < CI / (NW / 2); m++) {
-              const int c1l = (warp >> 1) + (NW / 2) * m, c1 = cbase + c1l;
-              unsigned code = 0;
-              int cls = -1;
-              if (c1l < nI1 && c2 < ncJ) {
-                bool n1, n2 = false;
-                if (A.self) {
-                  n1 = S.dminI[c1] <= S.dmaxJ[c2];
-                  n2 = want2 && !diag && (S.dmaxI[c1] > S.dminJ[c2]);
-                } else {
-                  n1 = true;
-                }
-                if (n1 || n2) {
-                  int iq = iquad_screen(S.w.scr.vfI, CI, c1l, S.w.scr.vfJ, c2, fmaxf(S.w.scr.flI[c1l], S.w.scr.flJ[c2]), delta);
-                  if (iq < 0) iq = iquad_exact_cells(S.gI, c1, S.gJ, c2);
-                  code = (unsigned)iq | (n1 ? 32u : 0u) | (n2 ? 64u : 0u);
-                  cls = cls_of(iq);
-                }
-              }
-              S.iqmap[c1l * kCH + c2] = (unsigned char)code;  // (T of unused pairs is never read by a used entry)
-              const unsigned grp = __match_any_sync(0xffffffffu, cls);
-              if (cls >= 0 && lane == __ffs(grp) - 1) atomicAdd(&S.cnt[cls], __popc(grp));
-              if (cls >= 7 && (code & 96u) == 96u) atomicAdd(&S.both_count, 1);
-              mycls |= (unsigned)(cls + 1) << (4 * m);
-            }
-          }
-          __syncthreads();
-          // ---------------- phase B: bin offsets, work queue(s), scatter, point tables -------------------  // @region B_bin
-          // Queue items: near classes (largest rules first), far bins too small for a table (evaluated
-          // from the vertices), then the table rules by decreasing size.  Table rules are packed into
-          // groups whose point tables fit the shared-memory pool together; a group is one barrier
-          // interval with one dynamic queue, so a pass normally has a single evaluation phase.
-          if (tid == 0) {
-            const int order[NCLS] = {11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0};
-            int o = 0, nb = 0, nq = 0, ng = 0, pts = 0;
-            unsigned long long fp = 0, ev = 0;
-            S.gq0[0] = 0;
-            for (int k = 0; k < NCLS; k++) {
-              const int c = order[k], n = S.cnt[c];
-              S.off[c] = o;
-              const bool near_c = c >= 7;
-              const bool c0 = near_c || c > kTabClsMax || n < kTabMin;  // evaluated analytically / from the vertices
-              if (n > 0 && c0) {
-                S.qcls[nq] = c;
-                S.qnb[nq] = near_c ? (n + 1) / 2 : (n + 31) / 32;
-                nb += S.qnb[nq];
-                nq++;
-              }
-              o += near_c ? ((n + 1) & ~1) : ((n + 31) & ~31);
-              if (!near_c) {
-                fp += n;
-                ev += (unsigned long long)n * c_cls_np[c] * c_cls_np[c];
-              }
-            }
-            for (int c = kTabClsMax; c >= 0; c--) {
-              const int n = S.cnt[c];
-              if (n < kTabMin) continue;
-              const int np = c_cls_np[c];
-              if (pts + np > kTabPts) {  // close the group
-                S.gq1[ng] = nq;
-                S.gnb[ng] = nb;
-                ng++;
-                S.gq0[ng] = nq;
-                nb = 0;
-                pts = 0;
-              }
-              S.qcls[nq] = c | 16;  // bit 4: evaluate from the tables
-              S.qnb[nq] = (n + 31) / 32;
-              S.qpt[nq] = pts;
-              nb += S.qnb[nq];
-              pts += np;
-              nq++;
-            }
-            S.gq1[ng] = nq;
-            S.gnb[ng] = nb;
-            S.ng = ng + 1;
-            S.qhead = 0;
-            st_far += fp;
-            st_eval += ev;
-          }
-          __syncthreads();  // (also: the FP32 scratch is dead, the table region may be written)
-          {
-#pragma unroll 1
-            for (int m = 0; m < CI / (NW / 2); m++) {
-              const int cls = (int)((mycls >> (4 * m)) & 15u) - 1;
-              const unsigned grp = __match_any_sync(0xffffffffu, cls);
-              int base = 0;
-              const int leader = __ffs(grp) - 1;
-              if (cls >= 0 && lane == leader) base = atomicAdd(&S.fill[cls], __popc(grp));
-              base = __shfl_sync(0xffffffffu, base, leader);
-              if (cls >= 0) {
-                const int c1l = (warp >> 1) + (NW / 2) * m, c2 = lane + 32 * (warp & 1);
-                S.list[S.off[cls] + base + __popc(grp & ((1u << lane) - 1u))] = (unsigned short)(c1l * kCH + c2);
-              }
-            }
-          }
-          // ---------------- phase C: evaluation, one dynamic queue per table group --------------------------  // @region C_eval
-          const int ngroups = S.ng;
-#pragma unroll 1
-          for (int g = 0; g < ngroups; g++) {
-            if (g > 0) {
-              __syncthreads();  // previous group is done with the table pool
-              if (tid == 0) S.qhead = 0;
-            }
-            const int q0 = S.gq0[g], q1 = S.gq1[g], total = S.gnb[g];
-            for (int k = q0; k < q1; k++) {
-              const int qc = S.qcls[k];
-              if (!(qc & 16)) continue;
-              const int cls = qc & 15, pt = S.qpt[k];
-              build_table(S.w.tab.tabI + pt * 2 * CI, CI, S.gI, cbase, nI1, cls + 4, c_cls_np[cls], ox, oy, oz, true, tid, NT);
-              build_table(S.w.tab.tabJ + pt * 2 * kCH, kCH, S.gJ, 0, ncJ, cls + 4, c_cls_np[cls], ox, oy, oz, false, tid, NT);
-            }
-            __syncthreads();
-            for (;;) {
-              int b = 0;
-              if (lane == 0) b = atomicAdd(&S.qhead, 1);
-              b = __shfl_sync(0xffffffffu, b, 0);
-              if (b >= total) break;
-              int k = q0, lb = b;
-              while (lb >= S.qnb[k]) {
-                lb -= S.qnb[k];
-                k++;
-              }
-              const int qc = S.qcls[k], cls = qc & 15;
-              if (A.debug_skip && ((cls >= 7) ? (A.debug_skip & 1) : (A.debug_skip & 2))) continue;
-              if (qc & 16) {
-                const unsigned e = S.list[S.off[cls] + lb * 32 + lane];
-                if (e != 0xFFFFu) {
-                  const int c1l = e >> 6, c2 = e & 63, pt = S.qpt[k];
-                  S.T[c1l * TS + c2] = far_tab_dispatch(S.w.tab.tabI + pt * 2 * CI, S.w.tab.tabJ + pt * 2 * kCH, c1l, c2, cls) *
-                                       S.gI[9 * kCH + cbase + c1l] * S.gJ[9 * kCH + c2];
-                }
-              } else {
-                run_batch_c0(S, cbase, cls, S.off[cls] + lb * (cls >= 7 ? 2 : 32), lane, false, st_near, st_phi);
-              }
-            }
-          }
-          // ---------------- phase D: contraction onto DOFs (two passes when both roles are needed) ------  // @region D_contract_ctl
-          const bool two_pass = S.both_count > 0;  // written before the phase-A barrier
-          for (int pass = 0; pass < (two_pass ? 2 : 1); pass++) {
-            __syncthreads();  // T complete (and the table region free for U)
-            if (pass == 1) {
-              // role-2 values of the near pairs that need both roles
-              if (tid == 0) S.qhead = 0;
-              __syncthreads();
-              int nearb = 0, first_cls_off[5], first_cls_nb[5];
-#pragma unroll
-              for (int k = 0; k < 5; k++) {
-                first_cls_off[k] = S.off[11 - k];
-                first_cls_nb[k] = (S.cnt[11 - k] + 1) / 2;
-                nearb += first_cls_nb[k];
-              }
-              for (;;) {
-                int b = 0;
-                if (lane == 0) b = atomicAdd(&S.qhead, 1);
-                b = __shfl_sync(0xffffffffu, b, 0);
-                if (b >= nearb) break;
-                int k = 0, lb = b;
-                while (lb >= first_cls_nb[k]) {
-                  lb -= first_cls_nb[k];
-                  k++;
-                }
-                if (A.debug_skip & 1) continue;
-                run_batch_c0(S, cbase, 11 - k, first_cls_off[k] + lb * 2, lane, true, st_near, st_phi);
-              }
-              __syncthreads();
-            }
-            for (int b0 = 0; b0 < ndJ; b0 += UB) {  // @region D_stage1
-              const int nb = min(UB, ndJ - b0);
-              if (b0 > 0) __syncthreads();  // stage 2 of the previous block finished with U
-              // stage 1: U[c1][b] = sum_{(c2,k2) of b} +-E2[c2][k2] T[c1][c2]; lanes over c1
-              for (int it = tid; it < nb * CI; it += NT) {
-                const int bl = it / CI, c1l = it - bl * CI;
-                double ux = 0.0, uy = 0.0, uz = 0.0;
-                const int ib = b0 + bl;
-                for (int i2 = S.iptrJ[ib]; i2 < S.iptrJ[ib + 1]; i2++) {
-                  const unsigned w2 = S.incJ[i2];
-                  const int c2 = w2 & 63, k2 = (w2 >> 6) & 3;
-                  double tv = S.T[c1l * TS + c2];
-                  if (w2 & 256) tv = -tv;
-                  ux = fma(S.gJ[(10 + 3 * k2) * kCH + c2], tv, ux);
-                  uy = fma(S.gJ[(11 + 3 * k2) * kCH + c2], tv, uy);
-                  uz = fma(S.gJ[(12 + 3 * k2) * kCH + c2], tv, uz);
-                }
-                S.w.U[(0 * CI + c1l) * US + bl] = ux;
-                S.w.U[(1 * CI + c1l) * US + bl] = uy;
-                S.w.U[(2 * CI + c1l) * US + bl] = uz;
-              }
-              __syncthreads();
-              // stage 2: L[a][b] += sum_{(c1,k1) of a, c1 in this pass} +-E1[c1][k1] . U[c1][b]; lanes over b.  // @region D_stage2
-              // Entries are handled in groups of G: all loads of the old values are issued first, the
-              // sums are formed while they are in flight, then the stores (one exposed latency per group).
-              constexpr int G = 4;
-              for (int it0 = tid; it0 < ndI * UB; it0 += G * NT) {
-                double* pa[G];
-                double* pb[G];
-                double olda[G], oldb[G], accv[G];
-#pragma unroll
-                for (int g = 0; g < G; g++) {
-                  pa[g] = nullptr;
-                  pb[g] = nullptr;
-                  const int it = it0 + g * NT;
-                  if (it >= ndI * UB) continue;
-                  const int ia = it >> 5, bl = it & 31;
-                  if (bl >= nb) continue;
-                  const int ib = b0 + bl;
-                  const int oa = S.origI[ia], ob = S.origJ[ib];
-                  if (A.self) {
-                    const bool role1 = oa <= ob;
-                    if (diag && !role1) continue;
-                    if (two_pass && role1 != (pass == 0)) continue;
-                  }
-                  if (!((S.hasI[ia] >> (cbase / CI)) & 1)) continue;  // no cell of this DOF in the pass
-                  const int ra = S.rowI[ia];
-                  if (ra >= 0) pa[g] = A.out + (long long)ra * A.ld + ob;
-                  if (A.self && (mirror || diag) && oa != ob) {
-                    const int rb = S.rowJ[ib];
-                    if (rb >= 0) pb[g] = A.out + (long long)rb * A.ld + oa;
-                  }
-                }
-#pragma unroll
-                for (int g = 0; g < G; g++) {
-                  olda[g] = pa[g] ? __ldcg(pa[g]) : 0.0;
-                  oldb[g] = pb[g] ? __ldcg(pb[g]) : 0.0;
-                }
-#pragma unroll
-                for (int g = 0; g < G; g++) {
-                  accv[g] = 0.0;
-                  if (!pa[g] && !pb[g]) continue;
-                  const int it = it0 + g * NT;
-                  const int ia = it >> 5, bl = it & 31;
-                  double acc = 0.0;
-                  for (int i1 = S.iptrI[ia]; i1 < S.iptrI[ia + 1]; i1++) {
-                    const unsigned w1 = S.incI[i1];
-                    const int c1l = (int)(w1 & 63) - cbase, k1 = (w1 >> 6) & 3;
-                    if (c1l < 0 || c1l >= CI) continue;
-                    const int c1 = w1 & 63;
-                    double dsum = S.gI[(10 + 3 * k1) * kCH + c1] * S.w.U[(0 * CI + c1l) * US + bl];
-                    dsum = fma(S.gI[(11 + 3 * k1) * kCH + c1], S.w.U[(1 * CI + c1l) * US + bl], dsum);
-                    dsum = fma(S.gI[(12 + 3 * k1) * kCH + c1], S.w.U[(2 * CI + c1l) * US + bl], dsum);
-                    acc += (w1 & 256) ? -dsum : dsum;
-                  }
-                  accv[g] = acc * A.scale;
-                }
-#pragma unroll
-                for (int g = 0; g < G; g++) {
-                  if (pa[g]) __stcg(pa[g], olda[g] + accv[g]);
-                  if (pb[g]) __stcg(pb[g], oldb[g] + accv[g]);
-                }
-              }
-            }
-          }
+          if (!(A.debug_skip & 4)) drain_pass(S, A, I, J, flags, 2, tid);
         }
+        TW_MARK(S, 0, tid, 4)
+        js ^= 1;
+      }
+      if (ci + 1 < ci1) {
+        __syncthreads();  // everybody is done with the row chunk
+        if (tid == 0) stage_issue(S.I, 0, A, ci + 1);
+        __syncthreads();
+        mbar_wait(&S.I.bar, phI);
+        phI ^= 1;
       }
     }
   }
+#ifdef TW_LMAT_PROF
+  __syncthreads();
+  if (A.stats && blockIdx.x == 0 && tid < 16) A.stats[8 + tid] = (unsigned long long)S.prof[tid];
+#endif
   if (A.stats && tid == 0) {  // load balance: first / last CTA finish time (ns, globaltimer)  // @region tail
     unsigned long long tend;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tend));
@@ -817,13 +962,24 @@ __global__ void __launch_bounds__(NT, kCtasPerSM) lmat_tile_kernel(const LmatArg
   if (A.stats) {
     st_near = (unsigned long long)warp_sum((double)st_near);  // counts are < 2^53
     st_phi = (unsigned long long)warp_sum((double)st_phi);
+    st_far = (unsigned long long)warp_sum((double)st_far);
+    st_eval = (unsigned long long)warp_sum((double)st_eval);
     if (lane == 0) {
       if (st_far) atomicAdd(&A.stats[0], st_far);
-      atomicAdd(&A.stats[1], st_near);
+      if (st_near) atomicAdd(&A.stats[1], st_near);
       if (st_eval) atomicAdd(&A.stats[2], st_eval);
-      atomicAdd(&A.stats[3], st_phi);
+      if (st_phi) atomicAdd(&A.stats[3], st_phi);
     }
   }
+}
+
+// output row of every local DOF of every chunk for this launch (row_out: internal DOF -> row or -1)
+__global__ void chunk_rows_kernel(int nchunk, const tw::ChunkMeta* __restrict__ chunks, const int* __restrict__ chunk_dof,
+                                  const int* __restrict__ row_out, int* __restrict__ chunk_row) {
+  const int ch = blockIdx.x, i = threadIdx.x;
+  if (ch >= nchunk) return;
+  const tw::ChunkMeta cm = chunks[ch];
+  chunk_row[(size_t)ch * tw::kMaxChunkDof + i] = i < cm.ndof ? row_out[chunk_dof[cm.dof_off + i]] : -1;
 }
 
 }  // namespace twk
@@ -906,6 +1062,30 @@ std::string DevicePatchSet::upload_from(const PatchSet& ps) {
   if (!(e = upload(ps.inc, &inc)).empty()) return e;
   if (!(e = upload(ps.patch_chunk_ptr, &patch_chunk_ptr)).empty()) return e;
   if (!(e = upload(ps.dof_orig, &dof_orig)).empty()) return e;
+  {
+    std::vector<ChunkAux> ax(ps.nchunk);
+    std::memset(ax.data(), 0, ax.size() * sizeof(ChunkAux));
+    for (int ch = 0; ch < ps.nchunk; ch++) {
+      const ChunkMeta& cm = ps.chunks[ch];
+      ChunkAux& x = ax[ch];
+      for (int c = 0; c < kCH; c++) {
+        x.dmin[c] = ps.cell_dmin[(size_t)ch * kCH + c];
+        x.dmax[c] = ps.cell_dmax[(size_t)ch * kCH + c];
+      }
+      const int* ip = ps.chunk_inc_ptr.data() + cm.dof_off + ch;
+      for (int i = 0; i <= cm.ndof; i++) x.iptr[i] = ip[i];
+      for (int i = 0; i < ip[cm.ndof]; i++) x.inc[i] = ps.inc[(size_t)cm.inc_off + i];
+      for (int i = 0; i < cm.ndof; i++) {
+        x.orig[i] = ps.dof_orig[ps.chunk_dof[cm.dof_off + i]];
+        unsigned hm = 0;
+        for (int k = ip[i]; k < ip[i + 1]; k++) hm |= 1u << ((x.inc[k] & 63) / kRowHalf);
+        for (int h = 0; h < kCH / kRowHalf; h++)
+          if ((hm >> h) & 1u) x.act[h][x.nact[h]++] = (unsigned char)i;
+      }
+    }
+    if (!(e = upload(ax, &aux)).empty()) return e;
+    nchunk = ps.nchunk;
+  }
   bytes = ps.chunks.size() * sizeof(ChunkMeta) + ps.geom.size() * 8 + (ps.cell_dmin.size() + ps.cell_dmax.size()) * 4 +
           (ps.chunk_dof.size() + ps.chunk_inc_ptr.size() + ps.patch_chunk_ptr.size() + ps.dof_orig.size()) * 4 + ps.inc.size() * 2;
   return "";
@@ -920,6 +1100,8 @@ void DevicePatchSet::release() {
   cudaFree(inc);
   cudaFree(patch_chunk_ptr);
   cudaFree(dof_orig);
+  cudaFree(aux);
+  aux = nullptr;
   chunks = nullptr;
   geom = nullptr;
   dmin = dmax = chunk_dof = inc_ptr = patch_chunk_ptr = dof_orig = nullptr;
@@ -939,22 +1121,23 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   CK(cudaMalloc((void**)&d_tiles, tiles.size() * sizeof(Tile)));
   CK(cudaMalloc((void**)&d_row_out, std::max<size_t>(row_out.size(), 1) * sizeof(int)));
   CK(cudaMalloc((void**)&d_counter, sizeof(int)));
-  CK(cudaMalloc((void**)&d_stats, 8 * sizeof(unsigned long long)));
+  CK(cudaMalloc((void**)&d_stats, 24 * sizeof(unsigned long long)));
   CK(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(d_row_out, row_out.data(), row_out.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
   CK(cudaMemsetAsync(d_counter, 0, sizeof(int), stream));
-  CK(cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), stream));
+  CK(cudaMemsetAsync(d_stats, 0, 24 * sizeof(unsigned long long), stream));
   CK(cudaMemsetAsync(d_stats + 7, 0xff, sizeof(unsigned long long), stream));
+  int* d_chunk_row = nullptr;
+  CK(cudaMalloc((void**)&d_chunk_row, (size_t)std::max(A.nchunk, 1) * kMaxChunkDof * sizeof(int)));
+  twk::chunk_rows_kernel<<<std::max(A.nchunk, 1), kMaxChunkDof, 0, stream>>>(A.nchunk, A.chunks, A.chunk_dof, d_row_out, d_chunk_row);
+  CK(cudaGetLastError());
+  note_launch();
   twk::LmatArgs a;
   a.chunksA = A.chunks; a.chunksB = B.chunks;
   a.geomA = A.geom; a.geomB = B.geom;
-  a.dminA = A.dmin; a.dmaxA = A.dmax; a.dminB = B.dmin; a.dmaxB = B.dmax;
-  a.chunk_dofA = A.chunk_dof; a.chunk_dofB = B.chunk_dof;
-  a.inc_ptrA = A.inc_ptr; a.inc_ptrB = B.inc_ptr;
-  a.incA = A.inc; a.incB = B.inc;
   a.patch_chunk_ptrA = A.patch_chunk_ptr; a.patch_chunk_ptrB = B.patch_chunk_ptr;
-  a.dof_origA = A.dof_orig; a.dof_origB = B.dof_orig;
-  a.row_out = d_row_out;
+  a.auxA = A.aux; a.auxB = B.aux;
+  a.chunk_row = d_chunk_row;
   a.tiles = d_tiles;
   a.ntiles = (int)tiles.size();
   a.tile_counter = d_counter;
@@ -967,17 +1150,28 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   int dev = 0, nsm = 148;
   CK(cudaGetDevice(&dev));
   CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  int grid = (int)std::min<size_t>(tiles.size(), (size_t)twk::kCtasPerSM * nsm);
+  int grid = (int)std::min<size_t>(tiles.size(), (size_t)nsm);
   twk::lmat_tile_kernel<<<grid, twk::NT, sizeof(twk::Smem), stream>>>(a);
   CK(cudaGetLastError());
   note_launch();
   if (h_stats) {
-    CK(cudaMemcpyAsync(h_stats, d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    unsigned long long hs[24];
+    CK(cudaMemcpyAsync(hs, d_stats, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    std::memcpy(h_stats, hs, 8 * sizeof(unsigned long long));
+#ifdef TW_LMAT_PROF
+    {
+      static const char* nm[13] = {"tile_fetch", "wait+A0", "scatter+queue+bar", "eval", "drain", "classify_loop", "bins+bar", "-", "-", "-", "-", "-", "-"};
+      std::fprintf(stderr, "[lmat prof, CTA 0, Mcycles]");
+      for (int i = 0; i < 13; i++) std::fprintf(stderr, " %s=%.1f", nm[i], hs[8 + i] * 1e-6);
+      std::fprintf(stderr, "\n");
+    }
+#endif
   }
   // stream-ordered frees keep the call asynchronous
   CK(cudaFreeAsync(d_tiles, stream));
   CK(cudaFreeAsync(d_row_out, stream));
+  CK(cudaFreeAsync(d_chunk_row, stream));
   CK(cudaFreeAsync(d_counter, stream));
   CK(cudaFreeAsync(d_stats, stream));
   return "";

@@ -416,9 +416,9 @@ __global__ void __launch_bounds__(BNT, 1) bel_tile_kernel(const BelArgs A) {
 #pragma unroll
         for (int q = 0; q < 9; q++) P[q] = S.g[q * CH + c];
         tri_normal(P, nh);
-        nrm[0] = S.g[19 * CH + c];
-        nrm[1] = S.g[20 * CH + c];
-        nrm[2] = S.g[21 * CH + c];
+        nrm[0] = S.g[22 * CH + c];
+        nrm[1] = S.g[23 * CH + c];
+        nrm[2] = S.g[24 * CH + c];
         bel_near(P, nh, nrm, S.vx[p], S.vy[p], S.vz[p], (e & 4096u) != 0, Hn);
         S.H[0][c * CH + p] = Hn[0];
         S.H[1][c * CH + p] = Hn[1];

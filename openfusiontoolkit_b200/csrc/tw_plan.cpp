@@ -154,7 +154,14 @@ std::string build_patches(const Model& m, int P, PatchSet& ps) {
             ps.geom[g0 + (size_t)(10 + k * 3 + d) * kCH + s] = m.qbasis[9 * (size_t)c + 3 * k + d];
           }
         ps.geom[g0 + (size_t)9 * kCH + s] = m.ca[c];
-        for (int d = 0; d < 3; d++) ps.geom[g0 + (size_t)(19 + d) * kCH + s] = m.norm[3 * (size_t)c + d];
+        double P9[9], nh[3];
+        for (int k = 0; k < 3; k++)
+          for (int d = 0; d < 3; d++) P9[3 * k + d] = m.r[3 * (size_t)m.lc[3 * c + k] + d];
+        phipot_normal(P9, nh);
+        for (int d = 0; d < 3; d++) {
+          ps.geom[g0 + (size_t)(19 + d) * kCH + s] = nh[d];
+          ps.geom[g0 + (size_t)(22 + d) * kCH + s] = m.norm[3 * (size_t)c + d];
+        }
       }
       {
         double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
@@ -275,6 +282,23 @@ float tile_cost(const PatchSet& A, const PatchSet& B, const std::vector<Ball>& b
   return (float)(pairs * w);
 }
 }  // namespace
+
+#if defined(__GNUC__)
+__attribute__((optimize("fp-contract=off")))
+#endif
+void phipot_normal(const double* P, double* n) {
+  volatile double a0 = P[3] - P[0], a1 = P[4] - P[1], a2 = P[5] - P[2];
+  volatile double b0 = P[6] - P[3], b1 = P[7] - P[4], b2 = P[8] - P[5];
+  volatile double t0 = a1 * b2, t1 = a2 * b1, t2 = a2 * b0, t3 = a0 * b2, t4 = a0 * b1, t5 = a1 * b0;
+  volatile double n0 = t0 - t1, n1 = t2 - t3, n2 = t4 - t5;
+  volatile double s0 = n0 * n0, s1 = n1 * n1, s2 = n2 * n2;
+  volatile double s01 = s0 + s1;
+  volatile double ss = s01 + s2;
+  const double m = std::sqrt(ss);
+  n[0] = n0 / m;
+  n[1] = n1 / m;
+  n[2] = n2 / m;
+}
 
 void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles) {
   tiles.clear();

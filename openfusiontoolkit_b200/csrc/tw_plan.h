@@ -18,7 +18,21 @@ namespace tw {
 constexpr int kCH = 64;        // cells per chunk
 constexpr int kMaxChunkDof = 3 * kCH;   // DOFs with incidences in one chunk
 constexpr int kMaxChunkInc = 4 * kCH;   // incidences in one chunk
-constexpr int kGeomRows = 24;  // doubles per cell in the SoA chunk record (0-8 verts, 9 area, 10-18 qbasis, 19-21 normal)
+constexpr int kGeomRows = 25;  // doubles per cell in the SoA chunk record: 0-8 vertices, 9 area, 10-18 qbasis,
+                               // 19-21 unit normal as tw_compute_phipot forms it, 22-24 mesh normal (trimesh_norm)
+
+constexpr int kRowHalf = 64;   // row cells per pass of the L kernel (a chunk is swept in kCH/kRowHalf passes)
+
+// Per-chunk index record the L kernel stages with one bulk copy (size is a multiple of 16 bytes).
+struct alignas(16) ChunkAux {
+  int dmin[kCH], dmax[kCH];          // min / max reference DOF id per cell (in-patch incidences)
+  int orig[kMaxChunkDof];            // reference DOF id per local DOF
+  int iptr[kMaxChunkDof + 4];        // CSR offsets of the incidence list (ndof+1 used)
+  uint16_t inc[kMaxChunkInc];        // cell(6b) | local vertex(2b)<<6 | negative<<8
+  int nact[kCH / kRowHalf];          // local DOFs that have a cell in row half h ...
+  unsigned char act[kCH / kRowHalf][kMaxChunkDof];  // ... and their list
+};
+static_assert(sizeof(ChunkAux) % 16 == 0, "ChunkAux must be a multiple of 16 bytes (bulk copy)");
 
 struct ChunkMeta {
   int ncell;    // valid cells in the chunk
@@ -60,6 +74,9 @@ struct Plan {
 
 // Build the patch decomposition of a model; P = target DOFs per patch (0 = choose automatically)
 std::string build_patches(const Model& m, int P, PatchSet& out);
+// Unit normal of a triangle exactly as tw_compute_phipot evaluates it (thin_wall.F90:1942-1943): IEEE operations
+// in the reference's order, no contraction (the device reads these values instead of recomputing them).
+void phipot_normal(const double* P /*[3][3]*/, double* n);
 // Contiguous patch range [p0,p1) of shard `shard` out of `nshards`, balanced by pair count
 void shard_range(const PatchSet& ps, int nshards, int shard, int& p0, int& p1);
 // Tiles of a self-inductance build for row patches [p0,p1)

@@ -70,7 +70,13 @@ __global__ void probe_pairs_kernel(int n, int mode, const double* __restrict__ P
         vfJ[lane * kCH] = (float)(gJ[lane * kCH] - o);
       }
       __syncwarp();
-      iq = iquad_screen(vfI, kCH, 0, vfJ, 0, fmaxf((float)(2.0 * gI[9 * kCH]), (float)(2.0 * gJ[9 * kCH])), (float)(X * 1.21e-7));
+      float pi_[9], pj_[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        pi_[k] = vfI[k * kCH];
+        pj_[k] = vfJ[k * kCH];
+      }
+      iq = iquad_screen(pi_, pj_, fmaxf((float)(2.0 * gI[9 * kCH]), (float)(2.0 * gJ[9 * kCH])), (float)(X * 1.21e-7));
       if (iq < 0) iq = iquad_exact_cells(gI, 0, gJ, 0) | 64;  // bit 6: the exact path was taken
     }
     const int iqv = iq & 31;
