@@ -625,21 +625,36 @@ int thincurr_b200_Lmat_shard(void* tw_ptr, int nshards, int shard, double* d_out
 int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* h_out, int64_t ld, int64_t* stats) {
   // end-to-end: (re)upload the model, build the rows, bring them back to host memory
   Model& m = *(Model*)tw_ptr;
+  const bool trace = std::getenv("THINCURR_B200_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  auto t0 = now();
   drop_device_state(m);
   m.plan.reset();
   std::string err = ensure_plan(m);
   if (!err.empty()) return fail(err);
+  auto t1 = now();
   int p0, p1;
   std::vector<int> rows;
   shard_rows(m, nshards, shard, p0, p1, rows);
   double* d = nullptr;
   size_t bytes = rows.size() * (size_t)ld * 8;
   if (cudaMalloc((void**)&d, std::max<size_t>(bytes, 8)) != cudaSuccess) return fail("Device allocation failed");
+  auto t2 = now();
   unsigned long long st[8] = {0};
   err = lmat_shard_device(m, nshards, shard, d, ld, 0, stats ? st : nullptr);
+  if (err.empty() && cudaDeviceSynchronize() != cudaSuccess) err = std::string("Kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+  auto t3 = now();
   if (err.empty() && cudaMemcpy(h_out, d, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
     err = std::string("Device->host copy failed: ") + cudaGetErrorString(cudaGetLastError());
+  auto t4 = now();
   cudaFree(d);
+  auto t5 = now();
+  if (trace)
+    std::fprintf(stderr, "[Lmat_shard_host] plan %.1f ms, alloc %.1f, upload+build %.1f, d2h %.1f (%.2f GB), free %.1f\n", ms(t0, t1), ms(t1, t2),
+                 ms(t2, t3), ms(t3, t4), bytes * 1e-9, ms(t4, t5));
   if (!err.empty()) return fail(err);
   if (stats) {
     for (int k = 0; k < 8; k++) stats[k] = (int64_t)st[k];

@@ -19,6 +19,7 @@ struct DevicePatchSet {
   ChunkAux* aux = nullptr;   // [nchunk] index records of the L kernel
   int nchunk = 0;
   int *patch_chunk_ptr = nullptr, *dof_orig = nullptr;
+  int* dof_patch = nullptr;  // [ndof] patch of every internal DOF
   size_t bytes = 0;  // host->device bytes of the last upload
   std::string upload_from(const PatchSet& ps);
   void release();

@@ -41,7 +41,11 @@ namespace twk {
 
 using tw::kCH;
 using tw::kGeomRows;
-constexpr int NT = 512;            // threads per CTA (one persistent CTA per SM, 128 registers per thread)
+#ifndef TW_LMAT_NT
+#define TW_LMAT_NT 512
+#endif
+constexpr int NT = TW_LMAT_NT;     // threads per CTA (one persistent CTA per SM; 512 threads x 128 registers)
+constexpr int NTC = 512;           // threads that classify pairs (8 per row cell)
 constexpr int NW = NT / 32;
 constexpr int CI = kCH;            // row cells per pass: a pass evaluates one pair of chunks, CI x kCH cell pairs
 constexpr int kGeomL = 22;         // geometry rows the L kernel stages (vertices, area, qbasis, phipot normal)
@@ -460,13 +464,13 @@ __device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const 
   // a thread owns one row cell c1 and the kCH/TPR columns c2 = NIT * (t % TPR) + m: the pairs of a thread,
   // and of the TPR threads of a row, are consecutive in a bin, so a batch of 32 pairs of the evaluation
   // reads few distinct row-side table entries (broadcast) and consecutive column-side entries
-  constexpr int TPR = NT / CI, NIT = kCH / TPR;
-  static_assert(NIT <= 8 && TPR * CI == NT && NIT * TPR == kCH, "4-bit per-thread class counts");
+  constexpr int TPR = NTC / CI, NIT = kCH / TPR;
+  static_assert(NIT <= 8 && TPR * CI == NTC && NTC <= NT && NIT * TPR == kCH, "4-bit per-thread class counts");
   unsigned mycls = 0;            // 4 bits per iteration: class + 1, 0 = no pair
   unsigned long long hist = 0;   // 4 bits per class: pairs of this thread
   int nboth = 0;
   const int c1 = tid / TPR, c2b = NIT * (tid % TPR);
-  if (c1 < ncI) {
+  if (tid < NTC && c1 < ncI) {
     float pi_[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) pi_[k] = S.u.w.vfI[k * CI + c1];
@@ -749,7 +753,7 @@ __device__ __forceinline__ void eval_role2(Smem& S, const LmatArgs& A, const Chu
 // role_sel 0: all entries; 1: only entries with a <= b (a second-role pass follows); 2: only a > b
 struct DrainSel {
   const LmatArgs* A;
-  bool diag, mirror;
+  bool diag, mirror;  // mirror: write the transposed entry too
   int role_sel;
   // output addresses of entry (ia, ib) and of its mirror; false if the entry is not written in this pass
   __device__ __forceinline__ bool addr(const ChunkState& I, const ChunkState& J, int ia, int ib, double*& pa, double*& pm) const {
@@ -762,7 +766,7 @@ struct DrainSel {
     }
     const int ra = I.row[ia];
     if (ra >= 0) pa = A->out + (long long)ra * A->ld + ob;
-    if (A->self && (mirror || diag) && oa != ob) {
+    if (A->self && mirror && oa != ob) {
       const int rb = J.row[ib];
       if (rb >= 0) pm = A->out + (long long)rb * A->ld + oa;
     }
@@ -776,7 +780,7 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
   DrainSel sel;
   sel.A = &A;
   sel.diag = flags & 1;
-  sel.mirror = flags & 2;
+  sel.mirror = (flags & 3) && !(flags & 8);
   sel.role_sel = role_sel;
   const int ndI = I.ndof, ndJ = J.ndof;
   const int lane = tid & 31, warp = tid >> 5;
@@ -801,6 +805,7 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
           }
         }
       }
+    TW_MARK(S, 0, tid, 7)
 #pragma unroll
     for (int j = 0; j < DB; j++) {
       const int ib = ib0 + j * NW;
@@ -823,6 +828,7 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
         uy1 = fma(qy, t1, uy1);
         uz1 = fma(qz, t1, uz1);
       }
+      TW_MARK(S, 0, tid, 8)
       __syncwarp();  // stage 2 of the previous column DOF is done with the scratch
 #pragma unroll
       for (int k = 0; k < 3; k++) {
@@ -831,6 +837,7 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
             fma(I.g[(12 + 3 * k) * kCH + lane + 32], uz1, fma(I.g[(11 + 3 * k) * kCH + lane + 32], uy1, I.g[(10 + 3 * k) * kCH + lane + 32] * ux1));
       }
       __syncwarp();
+      TW_MARK(S, 0, tid, 9)
       // stage 2: row DOFs lane, lane+32 from the preloaded values, further row DOFs (rare) directly
 #pragma unroll
       for (int r = 0; r < 2; r++) {
@@ -863,6 +870,7 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
         if (pa) __stcg(pa, oa_ + acc);
         if (pm) __stcg(pm, om_ + acc);
       }
+      TW_MARK(S, 0, tid, 10)
     }
   }
 }
@@ -973,6 +981,20 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {  /
   }
 }
 
+// Symmetrisation of the owned diagonal block: for internal DOFs i, j in [i0, i1) the tile kernel computed entry
+// [i][j] iff patch(i) < patch(j), or the patches are equal and orig(i) <= orig(j); the other one is its copy
+// (thin_wall.F90:1146-1151).  One block per row.
+__global__ void symmetrize_kernel(int i0, int i1, const int* __restrict__ dof_orig, const int* __restrict__ dof_patch,
+                                  double* __restrict__ out, long long ld) {
+  const int i = i0 + blockIdx.x;
+  const int oi = dof_orig[i], pi = dof_patch[i];
+  double* row = out + (long long)blockIdx.x * ld;
+  for (int j = i0 + threadIdx.x; j < i1; j += blockDim.x) {
+    const int pj = dof_patch[j], oj = dof_orig[j];
+    if (pj < pi || (pj == pi && oj < oi)) row[oj] = __ldcg(out + (long long)(j - i0) * ld + oi);
+  }
+}
+
 // output row of every local DOF of every chunk for this launch (row_out: internal DOF -> row or -1)
 __global__ void chunk_rows_kernel(int nchunk, const tw::ChunkMeta* __restrict__ chunks, const int* __restrict__ chunk_dof,
                                   const int* __restrict__ row_out, int* __restrict__ chunk_row) {
@@ -1063,6 +1085,12 @@ std::string DevicePatchSet::upload_from(const PatchSet& ps) {
   if (!(e = upload(ps.patch_chunk_ptr, &patch_chunk_ptr)).empty()) return e;
   if (!(e = upload(ps.dof_orig, &dof_orig)).empty()) return e;
   {
+    std::vector<int> dp(ps.ndof, 0);
+    for (int p = 0; p < ps.npatch; p++)
+      for (int i = ps.patch_dof_ptr[p]; i < ps.patch_dof_ptr[p + 1]; i++) dp[i] = p;
+    if (!(e = upload(dp, &dof_patch)).empty()) return e;
+  }
+  {
     std::vector<ChunkAux> ax(ps.nchunk);
     std::memset(ax.data(), 0, ax.size() * sizeof(ChunkAux));
     for (int ch = 0; ch < ps.nchunk; ch++) {
@@ -1100,6 +1128,8 @@ void DevicePatchSet::release() {
   cudaFree(inc);
   cudaFree(patch_chunk_ptr);
   cudaFree(dof_orig);
+  cudaFree(dof_patch);
+  dof_patch = nullptr;
   cudaFree(aux);
   aux = nullptr;
   chunks = nullptr;
@@ -1154,6 +1184,20 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   twk::lmat_tile_kernel<<<grid, twk::NT, sizeof(twk::Smem), stream>>>(a);
   CK(cudaGetLastError());
   note_launch();
+  if (self) {
+    // owned internal DOFs form one contiguous range (rows are numbered along it)
+    int i0 = -1, i1 = -1;
+    for (int i = 0; i < (int)row_out.size(); i++)
+      if (row_out[i] >= 0) {
+        if (i0 < 0) i0 = i;
+        i1 = i + 1;
+      }
+    if (i0 >= 0 && i1 - i0 > 1) {
+      twk::symmetrize_kernel<<<i1 - i0, 256, 0, stream>>>(i0, i1, A.dof_orig, A.dof_patch, d_out, ld);
+      CK(cudaGetLastError());
+      note_launch();
+    }
+  }
   if (h_stats) {
     unsigned long long hs[24];
     CK(cudaMemcpyAsync(hs, d_stats, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -1161,7 +1205,7 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
     std::memcpy(h_stats, hs, 8 * sizeof(unsigned long long));
 #ifdef TW_LMAT_PROF
     {
-      static const char* nm[13] = {"tile_fetch", "wait+A0", "scatter+queue+bar", "eval", "drain", "classify_loop", "bins+bar", "-", "-", "-", "-", "-", "-"};
+      static const char* nm[13] = {"tile_fetch", "wait+A0", "scatter+queue+bar", "eval", "drain_rest", "classify_loop", "bins+bar", "D:issue_loads", "D:stage1", "D:products", "D:stage2", "-", "-"};
       std::fprintf(stderr, "[lmat prof, CTA 0, Mcycles]");
       for (int i = 0; i < 13; i++) std::fprintf(stderr, " %s=%.1f", nm[i], hs[8 + i] * 1e-6);
       std::fprintf(stderr, "\n");

@@ -326,8 +326,8 @@ void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& til
       } else {
         t.pa = pa;
         t.pb = pb;
-        if (pa == pb) t.flags |= 1;
-        else if (owned) t.flags |= 2;
+        if (pa == pb) t.flags |= 1 | 8;
+        else if (owned) t.flags |= 2 | 8;  // both row blocks owned: the transposed entries are filled by the symmetrisation pass
       }
       if (t.pa != t.pb && omax[t.pa] > omin[t.pb]) t.flags |= 4;
       t.cost = tile_cost(ps, ps, balls, balls, t.pa, t.pb, h) * ((t.flags & 1) ? 0.5f : 1.0f);

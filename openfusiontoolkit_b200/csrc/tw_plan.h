@@ -64,6 +64,8 @@ struct Tile {
   int flags;    // bit0: diagonal (pa==pb, only entries a<=b computed, mirrored)
                 // bit1: mirror-write the transposed entries (pb rows are owned too)
                 // bit2: second role (T with the column cell analytic) may be needed
+                // bit3: the transposed entries are not written by the tile kernel (rows of both patches are in
+                //       the output block: one symmetrisation pass copies them afterwards)
   float cost;
 };
 
