@@ -131,6 +131,15 @@ int thincurr_b200_plan_info(void* tw_ptr, int64_t* info);
  * bytes of the model upload and [6] device->host bytes of the rows. */
 int thincurr_b200_Lmat_shard(void* tw_ptr, int nshards, int shard, double* d_out, int64_t ld, void* stream,
                              int64_t* stats);
+/* Symmetric multi-device build.  The row partition equalises the work of the UPPER trapezoid: shard s builds
+ * d_out[nrows][ld] for its rows against the DOFs of shards >= s only; the columns of the DOFs of earlier shards are
+ * left zero and are the transposes of blocks earlier shards computed (L is symmetric, thin_wall.F90:1146-1151).  The
+ * caller completes them with one exchange after the assembly (ThinCurr.exchange_symmetric: NCCL send/recv of the
+ * blocks), so no pair integral is evaluated twice across devices.  thincurr_b200_shard_rows_sym: row count and/or
+ * reference DOF ids of the rows of a shard (either pointer may be NULL). */
+int thincurr_b200_shard_rows_sym(void* tw_ptr, int nshards, int shard, int* nrows, int* row_ids);
+int thincurr_b200_Lmat_shard_sym(void* tw_ptr, int nshards, int shard, double* d_out, int64_t ld, void* stream,
+                                 int64_t* stats);
 /* Same from HOST mesh each call (uploads model, builds, copies rows back to h_out[nrows][ld]);
  * the end-to-end path used by bench.py's e2e leg. */
 int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* h_out, int64_t ld,

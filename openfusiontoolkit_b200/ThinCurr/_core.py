@@ -12,7 +12,7 @@ from ctypes import c_bool, c_double, c_int, c_void_p
 import numpy
 import scipy.sparse
 
-from .._interface import (b200_Bel_shard, b200_Lmat_shard, b200_Lmat_shard_host, b200_destroy, b200_get_model,
+from .._interface import (b200_Bel_shard, b200_Lmat_shard, b200_Lmat_shard_host, b200_Lmat_shard_sym, b200_shard_rows_sym, b200_destroy, b200_get_model,
                           b200_hashes, b200_last_error, b200_msensor, b200_pair_stats, b200_plan, b200_set_coils,
                           b200_set_sensors, b200_setup, b200_shard_rows, c_double_ptr, c_int_ptr, mu0, oftpy_load_xml,
                           thincurr_Bmat, thincurr_cross_coupling, thincurr_get_eta, thincurr_get_sensor_name,
@@ -295,6 +295,53 @@ class ThinCurr():
         _check(b200_Lmat_shard(self.tw_obj, nshards, shard, c_void_p(out.data_ptr()), out.stride(0), sptr,
                                st.ctypes.data_as(c_void_p) if stats else None))
         return st
+
+    # symmetric multi-device build: upper trapezoid per shard + one exchange of the transposed blocks
+    def shard_rows_sym(self, nshards, shard):
+        '''! Rows (reference 0-based DOF ids) of `shard` in the symmetric partition, which equalises the work of
+        the upper trapezoid (rows of the shard x DOFs of this and later shards).'''
+        n = c_int()
+        _check(b200_shard_rows_sym(self.tw_obj, nshards, shard, ctypes.byref(n), None))
+        rows = numpy.zeros(max(n.value, 1), dtype=numpy.int32)
+        _check(b200_shard_rows_sym(self.tw_obj, nshards, shard, None, rows.ctypes.data_as(c_void_p)))
+        return rows[:n.value]
+
+    def compute_Lmat_shard_sym(self, nshards, shard, out, stream=None, stats=False):
+        '''! Build rows `shard_rows_sym(nshards, shard)` of L into the CUDA tensor `out[nrows, ld]` for the columns of
+        this and later shards; the columns of earlier shards' DOFs stay zero until `exchange_symmetric`.'''
+        st = numpy.zeros(8, dtype=numpy.int64)
+        sptr = c_void_p(stream) if stream else c_void_p()
+        _check(b200_Lmat_shard_sym(self.tw_obj, nshards, shard, c_void_p(out.data_ptr()), out.stride(0), sptr,
+                                   st.ctypes.data_as(c_void_p) if stats else None))
+        return st
+
+    def exchange_symmetric(self, out, nshards, shard, group=None, row_ids=None):
+        '''! Complete the rows built by `compute_Lmat_shard_sym`: L[rows of shard r][DOFs of shard s] for s < r is the
+        transpose of the block shard s computed (thin_wall.F90:1146-1151 mirrors the same way).  One send/recv per pair
+        of ranks over the process group (NCCL on GPUs), in nshards-1 rounds so that only one block is staged at a
+        time.  `out` is this rank's [nrows, ld] tensor; `row_ids[s]` (optional) the DOF ids of every shard.'''
+        import torch
+        import torch.distributed as dist
+        if nshards == 1:
+            return
+        if row_ids is None:
+            row_ids = [self.shard_rows_sym(nshards, s) for s in range(nshards)]
+        ids = [torch.as_tensor(numpy.ascontiguousarray(r, dtype=numpy.int64), device=out.device) for r in row_ids]
+        nmine = len(row_ids[shard])
+        for d in range(1, nshards):
+            dst, src = shard + d, shard - d
+            ops, recv = [], None
+            if dst < nshards and nmine and len(row_ids[dst]):
+                send = out[:nmine].index_select(1, ids[dst]).contiguous()   # [my rows, DOFs of the later shard]
+                ops.append(dist.P2POp(dist.isend, send, dst, group=group))
+            if src >= 0 and nmine and len(row_ids[src]):
+                recv = torch.empty((len(row_ids[src]), nmine), dtype=out.dtype, device=out.device)
+                ops.append(dist.P2POp(dist.irecv, recv, src, group=group))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            if recv is not None:
+                out[:nmine].index_copy_(1, ids[src], recv.t())
 
     def compute_Lmat_shard_host(self, nshards, shard, out, stats=False):
         '''! End-to-end variant: host mesh -> device build -> host rows (`out` is a numpy array).'''

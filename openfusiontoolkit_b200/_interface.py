@@ -83,6 +83,9 @@ b200_plan = ctypes_subroutine(oftpy_lib.thincurr_b200_plan, [c_void_p, c_int, c_
 b200_shard_rows = ctypes_subroutine(oftpy_lib.thincurr_b200_shard_rows, [c_void_p, c_int, c_int, ctypes_numpy_array(int32, 1)], c_int)
 b200_Lmat_shard = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard,
     [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p], c_int)
+b200_shard_rows_sym = ctypes_subroutine(oftpy_lib.thincurr_b200_shard_rows_sym, [c_void_p, c_int, c_int, c_int_ptr, c_void_p], c_int)
+b200_Lmat_shard_sym = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard_sym,
+    [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p], c_int)
 b200_Lmat_shard_host = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard_host,
     [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p], c_int)
 b200_Bel_shard = ctypes_subroutine(oftpy_lib.thincurr_b200_Bel_shard, [c_void_p, c_int, c_int, c_void_p, c_void_p], c_int)

@@ -136,9 +136,10 @@ void drop_device_state(Model& m) {
 }
 
 // rows of a shard: internal DOF range of its patches (+ the V-coil rows on the last shard)
-void shard_rows(const Model& m, int nshards, int shard, int& p0, int& p1, std::vector<int>& row_ids) {
+void shard_rows(const Model& m, int nshards, int shard, int& p0, int& p1, std::vector<int>& row_ids, bool sym) {
   const PatchSet& ps = m.plan->ps;
-  shard_range(ps, nshards, shard, p0, p1);
+  if (sym) shard_range_sym(ps, nshards, shard, p0, p1);
+  else shard_range(ps, nshards, shard, p0, p1);
   row_ids.clear();
   for (int i = ps.patch_dof_ptr[p0]; i < ps.patch_dof_ptr[p1]; i++) row_ids.push_back(ps.dof_orig[i]);
   if (shard == nshards - 1)
@@ -147,8 +148,9 @@ void shard_rows(const Model& m, int nshards, int shard, int& p0, int& p1, std::v
 
 // Build the self-inductance rows of one shard on the current device into d_out[nrows][ld]
 // (zeroed here).  Asynchronous on `stream` unless stats are requested.
+// sym: symmetric partition, only the blocks against this and later shards are computed (upper trapezoid)
 std::string lmat_shard_device(Model& m, int nshards, int shard, double* d_out, long long ld, cudaStream_t stream,
-                              unsigned long long* stats) {
+                              unsigned long long* stats, bool sym) {
   int device = 0;
   if (cudaGetDevice(&device) != cudaSuccess) return "No CUDA device available (there is no CPU fallback)";
   std::shared_ptr<DeviceState> ds;
@@ -158,11 +160,11 @@ std::string lmat_shard_device(Model& m, int nshards, int shard, double* d_out, l
   const PatchSet& ps = m.plan->ps;
   int p0, p1;
   std::vector<int> row_ids;
-  shard_rows(m, nshards, shard, p0, p1, row_ids);
+  shard_rows(m, nshards, shard, p0, p1, row_ids, sym);
   std::vector<int> row_out(ps.ndof, -1);
   for (int i = ps.patch_dof_ptr[p0], r = 0; i < ps.patch_dof_ptr[p1]; i++, r++) row_out[i] = r;
   std::vector<Tile> tiles;
-  build_self_tiles(ps, p0, p1, tiles);
+  build_self_tiles(ps, p0, p1, tiles, sym);
   if (cudaMemsetAsync(d_out, 0, (size_t)row_ids.size() * ld * sizeof(double), stream) != cudaSuccess)
     return "cudaMemsetAsync failed on the output block";
   err = gpu_lmat_tiles(ds->ps, ds->ps, tiles, row_out, true, d_out, ld, stream, stats);
@@ -616,6 +618,28 @@ int thincurr_b200_Lmat_shard(void* tw_ptr, int nshards, int shard, double* d_out
   Model& m = *(Model*)tw_ptr;
   unsigned long long st[8] = {0};
   std::string err = lmat_shard_device(m, nshards, shard, d_out, ld, (cudaStream_t)stream, stats ? st : nullptr);
+  if (!err.empty()) return fail(err);
+  if (stats)
+    for (int k = 0; k < 8; k++) stats[k] = (int64_t)st[k];
+  return 0;
+}
+
+int thincurr_b200_shard_rows_sym(void* tw_ptr, int nshards, int shard, int* nrows, int* row_ids) {
+  Model& m = *(Model*)tw_ptr;
+  std::string err = ensure_plan(m);
+  if (!err.empty()) return fail(err);
+  int p0, p1;
+  std::vector<int> rows;
+  shard_rows(m, nshards, shard, p0, p1, rows, true);
+  if (nrows) *nrows = (int)rows.size();
+  if (row_ids) std::copy(rows.begin(), rows.end(), row_ids);
+  return 0;
+}
+
+int thincurr_b200_Lmat_shard_sym(void* tw_ptr, int nshards, int shard, double* d_out, int64_t ld, void* stream, int64_t* stats) {
+  Model& m = *(Model*)tw_ptr;
+  unsigned long long st[8] = {0};
+  std::string err = lmat_shard_device(m, nshards, shard, d_out, ld, (cudaStream_t)stream, stats ? st : nullptr, true);
   if (!err.empty()) return fail(err);
   if (stats)
     for (int k = 0; k < 8; k++) stats[k] = (int64_t)st[k];

@@ -14,9 +14,9 @@ int visible_devices();
 std::string ensure_plan(Model& m);
 std::string ensure_device(Model& m, int device, std::shared_ptr<DeviceState>& out);
 void drop_device_state(Model& m);
-void shard_rows(const Model& m, int nshards, int shard, int& p0, int& p1, std::vector<int>& row_ids);
+void shard_rows(const Model& m, int nshards, int shard, int& p0, int& p1, std::vector<int>& row_ids, bool sym = false);
 std::string lmat_shard_device(Model& m, int nshards, int shard, double* d_out, long long ld, cudaStream_t stream,
-                              unsigned long long* stats);
+                              unsigned long long* stats, bool sym = false);
 
 // V-coil rows/columns of L from Ael2coil / Acoil2coil (thin_wall.F90:1128-1145), scaled by 1/4pi
 std::string gpu_fill_vcoil_block(const Model& m, const std::vector<int>& row_ids, double* d_out, long long ld,

@@ -9,15 +9,12 @@
 namespace tw {
 
 namespace {
-// kd-order of points: recursive median split along the longest bounding-box axis.  Leaves of
-// size <= P become patches; recursion continues below that only to order DOFs inside a patch.
-void rcb(std::vector<int>& idx, int lo, int hi, const std::vector<double>& xyz, int P, std::vector<int>& cuts,
-         bool emitted) {
+// kd-order of points: recursive split along the longest bounding-box axis.  `npatch` leaves of (nearly) equal
+// size become patches (the split point is proportional to the leaf counts of the two halves, so any patch count
+// works, not only powers of two); recursion continues below a leaf only to order the DOFs inside the patch.
+void rcb(std::vector<int>& idx, int lo, int hi, const std::vector<double>& xyz, int npatch, std::vector<int>& cuts) {
   int n = hi - lo;
-  if (!emitted && n <= P) {
-    cuts.push_back(lo);
-    emitted = true;
-  }
+  if (npatch == 1) cuts.push_back(lo);
   if (n <= 4) return;
   double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
   for (int i = lo; i < hi; i++)
@@ -29,13 +26,14 @@ void rcb(std::vector<int>& idx, int lo, int hi, const std::vector<double>& xyz, 
   int ax = 0;
   for (int d = 1; d < 3; d++)
     if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
-  int mid = lo + n / 2;
+  const int left = npatch > 1 ? npatch / 2 : 0;
+  int mid = npatch > 1 ? lo + (int)((long long)n * left / npatch) : lo + n / 2;
   std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) {
     double va = xyz[3 * (size_t)a + ax], vb = xyz[3 * (size_t)b + ax];
     return va < vb || (va == vb && a < b);
   });
-  rcb(idx, lo, mid, xyz, P, cuts, emitted);
-  rcb(idx, mid, hi, xyz, P, cuts, emitted);
+  rcb(idx, lo, mid, xyz, npatch > 1 ? left : 0, cuts);
+  rcb(idx, mid, hi, xyz, npatch > 1 ? npatch - left : 0, cuts);
 }
 }  // namespace
 
@@ -44,16 +42,13 @@ std::string build_patches(const Model& m, int P, PatchSet& ps) {
   ps = PatchSet();
   ps.ndof = nv + nh;
   if (P <= 0) {
-    // Large patches keep the halo (cells shared by neighbouring patches are evaluated once per
-    // patch) small; the tile count must still fill 148 SMs many times over for load balance.
-    // The bisection produces 2^k patches, so count those.
-    P = 1024;
-    for (;;) {
-      long np2 = 1;
-      while (np2 * P < nv) np2 *= 2;
-      if (P <= 32 || np2 * np2 / 2 >= 1500) break;
-      P /= 2;
-    }
+    // Large patches keep the halo (cells shared by neighbouring patches are evaluated once per patch) small, but
+    // the near-field-heavy diagonal tiles must stay short against a CTA's share of the build and the tile count
+    // must fill 148 SMs many times over: ~300 DOFs per patch (measured on the 20k vessel: 150 -> 186 ms,
+    // 300 -> 169 ms, 600 -> 235 ms), fewer on small meshes (>= ~1500 tiles, >= 32 DOFs).
+    P = 300;
+    while (P > 32 && ((long)((nv + P - 1) / P) * ((nv + P - 1) / P)) / 2 < 1500) P = P * 3 / 4;
+    P = std::max(P, 32);
   }
   // dof -> vertices (periodic meshes map several vertices to one DOF)
   std::vector<int> kdv(nv + 1, 0), ldv;
@@ -73,7 +68,7 @@ std::string build_patches(const Model& m, int P, PatchSet& ps) {
     for (int k = 0; k < 3; k++) xyz[3 * (size_t)d + k] = m.r[3 * (size_t)ldv[kdv[d]] + k];
   std::vector<int> idx(nv), cuts;
   std::iota(idx.begin(), idx.end(), 0);
-  if (nv > 0) rcb(idx, 0, nv, xyz, P, cuts, false);
+  if (nv > 0) rcb(idx, 0, nv, xyz, std::max(1, (nv + P - 1) / P), cuts);
   cuts.push_back(nv);
   ps.nvert_patch = (int)cuts.size() - 1;
   ps.npatch = ps.nvert_patch + nh;
@@ -300,7 +295,32 @@ void phipot_normal(const double* P, double* n) {
   n[2] = n2 / m;
 }
 
-void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles) {
+void shard_range_sym(const PatchSet& ps, int nshards, int shard, int& p0, int& p1) {
+  // work of row patch p in the upper-trapezoid build = cost of its tiles against the patches >= p (the same cost
+  // model that orders the tile queue: near-field tiles weigh more)
+  auto balls = patch_balls(ps);
+  const double h = mean_cell_size(ps);
+  std::vector<double> w(ps.npatch, 0.0);
+  double total = 0.0;
+  for (int p = 0; p < ps.npatch; p++) {
+    for (int q = p; q < ps.npatch; q++) w[p] += (double)tile_cost(ps, ps, balls, balls, p, q, h) * (q == p ? 0.5 : 1.0);
+    total += w[p];
+  }
+  auto cut = [&](int s) {
+    if (s <= 0) return 0;
+    if (s >= nshards) return ps.npatch;
+    double target = total * s / nshards, acc = 0;
+    for (int p = 0; p < ps.npatch; p++) {
+      if (acc + 0.5 * w[p] >= target) return p;
+      acc += w[p];
+    }
+    return ps.npatch;
+  };
+  p0 = cut(shard);
+  p1 = cut(shard + 1);
+}
+
+void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles, bool upper_only) {
   tiles.clear();
   auto balls = patch_balls(ps);
   double h = mean_cell_size(ps);
@@ -314,6 +334,7 @@ void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& til
     for (int pb = 0; pb < ps.npatch; pb++) {
       bool owned = pb >= p0 && pb < p1;
       if (owned && pb < pa) continue;  // produced by the mirror write of tile (pb,pa)
+      if (upper_only && !owned && pb < pa) continue;  // transposed block of an earlier shard (exchanged afterwards)
       Tile t;
       t.flags = 0;
       if (!owned && pb < pa) {

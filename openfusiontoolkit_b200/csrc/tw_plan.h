@@ -81,8 +81,13 @@ std::string build_patches(const Model& m, int P, PatchSet& out);
 void phipot_normal(const double* P /*[3][3]*/, double* n);
 // Contiguous patch range [p0,p1) of shard `shard` out of `nshards`, balanced by pair count
 void shard_range(const PatchSet& ps, int nshards, int shard, int& p0, int& p1);
+// Same for the symmetric (upper-trapezoid) build: shard s computes rows [p0,p1) x columns of patches >= p0 only, so the
+// ranges equalise ncell(p) * (sum_{q>p} ncell(q) + ncell(p)/2); the missing blocks are the transposes of blocks computed
+// by earlier shards (one exchange after the assembly).
+void shard_range_sym(const PatchSet& ps, int nshards, int shard, int& p0, int& p1);
 // Tiles of a self-inductance build for row patches [p0,p1)
-void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles);
+// upper_only: skip the tiles against earlier (unowned) patches
+void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles, bool upper_only = false);
 // Tiles of a mutual build (all row patches x all column patches)
 void build_mutual_tiles(const PatchSet& rows, const PatchSet& cols, std::vector<Tile>& tiles);
 

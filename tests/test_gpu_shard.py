@@ -49,6 +49,31 @@ def test_sharded_equals_full(env, nshards):
     assert seen.all()
 
 
+@pytest.mark.parametrize('nshards', [2, 5])
+def test_symmetric_shards_equal_full(env, nshards):
+    """upper-trapezoid shards (thincurr_b200_Lmat_shard_sym): the computed part is bitwise the single-device
+    matrix, the part left to the exchange is zero, the row sets partition the DOFs."""
+    import torch
+    from openfusiontoolkit_b200.ThinCurr import ThinCurr
+    m = load_mesh('ex_torus')
+    T = ThinCurr(env)
+    T.setup_model(r=m['r'], lc=m['lc'], reg=m['reg'], nodesets=m['nodesets'], closures=m['sidesets'][0] if m['sidesets'] else None)
+    T.compute_Lmat()
+    full = np.array(T.Lmat)
+    ids = [T.shard_rows_sym(nshards, s) for s in range(nshards)]
+    assert np.array_equal(np.sort(np.concatenate(ids)), np.arange(T.nelems))
+    for s in range(nshards):
+        out = torch.empty((len(ids[s]), T.nelems), dtype=torch.float64, device='cuda')
+        T.compute_Lmat_shard_sym(nshards, s, out)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        later = np.concatenate(ids[s:])
+        assert np.array_equal(got[:, later], full[np.ix_(ids[s], later)]), 'shard %d' % s
+        if s:
+            earlier = np.concatenate(ids[:s])
+            assert not got[:, earlier].any()
+
+
 def test_ports_mesh_rows(env):
     """BASELINE config 2 (ports mesh, 22 580 vertices / 44 560 triangles, 11 holes): full dense L on
     one GPU; 40 random vertex rows and all hole rows against the oracle."""

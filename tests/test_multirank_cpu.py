@@ -49,6 +49,58 @@ def test_two_rank_row_partition():
     assert abs(len(gathered[0]) - len(gathered[1])) < 0.2 * nelems
 
 
+def _worker_sym(rank, world, port, q):
+    """symmetric partition + exchange on CPU tensors (gloo): every rank holds the upper trapezoid of a known
+    symmetric matrix and must end up with its complete rows."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from openfusiontoolkit_b200 import OFT_env
+    from openfusiontoolkit_b200.ThinCurr import ThinCurr
+    from openfusiontoolkit_b200.ThinCurr.meshing import build_torus_vessel
+    m = build_torus_vessel(40, 80, nports=4)
+    T = ThinCurr(OFT_env(nthreads=-1))
+    T.setup_model(r=m['r'], lc=m['lc'], nodesets=m['nodesets'], closures=m['closures'])
+    N = T.nelems
+    ids = [T.shard_rows_sym(world, s) for s in range(world)]
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((N, N))
+    A = A + A.T
+    mine = ids[rank]
+    out = torch.from_numpy(A[mine].copy())
+    for s in range(rank):                      # what the upper-trapezoid build leaves empty
+        out[:, torch.as_tensor(ids[s].astype(np.int64))] = 0.0
+    T.exchange_symmetric(out, world, rank, row_ids=ids)
+    ok = bool(np.array_equal(out.numpy(), A[mine]))
+    res = [None] * world
+    dist.all_gather_object(res, (ok, [len(i) for i in ids], int(sum(len(i) for i in ids)), N))
+    if rank == 0:
+        q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_symmetric_exchange(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + 17 * world) % 2000
+    procs = [ctx.Process(target=_worker_sym, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for ok, sizes, total, N in res:
+        assert ok, 'rows incomplete after the exchange'
+        assert total == N
+        assert sizes[0] < sizes[-1], 'earlier shards own fewer rows (their rows are longer in the upper trapezoid)'
+
+
 def test_weak_scaling_mesh_sizes():
     sys.path.insert(0, ROOT)
     from bench import vessel_dims
