@@ -67,6 +67,28 @@ INTERFACE
     INTEGER(c_int), INTENT(out) :: row_ids(*)
     INTEGER(c_int) :: ierr
   END FUNCTION thincurr_b200_shard_rows
+  !> Symmetric multi-device partition: row count and/or 0-based reference DOF ids of a shard (either may be c_null_ptr)
+  FUNCTION thincurr_b200_shard_rows_sym(tw_ptr,nshards,shard,nrows,row_ids) BIND(C,NAME="thincurr_b200_shard_rows_sym") RESULT(ierr)
+    IMPORT :: c_int, c_ptr
+    TYPE(c_ptr), VALUE :: tw_ptr
+    INTEGER(c_int), VALUE, INTENT(in) :: nshards,shard
+    TYPE(c_ptr), VALUE :: nrows   !< c_null_ptr or C_LOC of an INTEGER(c_int)
+    TYPE(c_ptr), VALUE :: row_ids !< c_null_ptr or C_LOC of INTEGER(c_int) :: row_ids(nrows)
+    INTEGER(c_int) :: ierr
+  END FUNCTION thincurr_b200_shard_rows_sym
+  !> Upper-trapezoid rows of a shard into DEVICE memory d_out(ld,nrows): columns of the DOFs of earlier shards stay zero
+  !> and are the transposes of blocks those shards computed (exchange once after the assembly)
+  FUNCTION thincurr_b200_Lmat_shard_sym(tw_ptr,nshards,shard,d_out,ld,stream,stats) &
+    BIND(C,NAME="thincurr_b200_Lmat_shard_sym") RESULT(ierr)
+    IMPORT :: c_int, c_int64_t, c_ptr
+    TYPE(c_ptr), VALUE :: tw_ptr
+    INTEGER(c_int), VALUE, INTENT(in) :: nshards,shard
+    TYPE(c_ptr), VALUE :: d_out   !< device pointer
+    INTEGER(c_int64_t), VALUE, INTENT(in) :: ld
+    TYPE(c_ptr), VALUE :: stream  !< cudaStream_t or c_null_ptr
+    TYPE(c_ptr), VALUE :: stats   !< c_null_ptr or INTEGER(c_int64_t) :: stats(8)
+    INTEGER(c_int) :: ierr
+  END FUNCTION thincurr_b200_Lmat_shard_sym
   !> Rows of one shard into host memory h_out(ld,nrows) (row r = Lmat(:,row_ids(r)+1))
   FUNCTION thincurr_b200_Lmat_shard_host(tw_ptr,nshards,shard,h_out,ld,stats) &
     BIND(C,NAME="thincurr_b200_Lmat_shard_host") RESULT(ierr)
