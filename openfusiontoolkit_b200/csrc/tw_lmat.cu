@@ -117,7 +117,10 @@ struct Smem {
     struct {
       float vfI[9 * CI], vfJ[9 * kCH];  // vertices in the local frame, FP32 (order screening)
       float flI[CI], flJ[kCH];          // 2 * area
-      char pad[kTabPts * 2 * CI * 16 - (9 * CI + 9 * kCH + CI + kCH) * 4];  // (the contraction scratch starts at tabJ)
+      float4 cenI[CI], cenJ[kCH];       // centroid (local frame) and the radius covering the vertices
+      char pad0[8192 - (9 * CI + 9 * kCH + CI + kCH) * 4 - (CI + kCH) * 16];
+      double E[CI * TS];                // contraction: contribution of the pass to L[row DOF][column DOF] (first 64 x 64)
+      char pad1[kTabPts * 2 * CI * 16 - 8192 - CI * TS * 8];  // (the per-warp scratch starts at tabJ)
       double P[NW][3 * CI];             // per warp: products of the contraction
     } w;
   } u;
@@ -438,6 +441,25 @@ __device__ __forceinline__ void prep_stage(Smem& S, const ChunkState& I, const C
     S.u.w.flJ[i] = (float)(2.0 * J.g[9 * kCH + i]);
     S.u.w.flI[i] = (float)(2.0 * I.g[9 * kCH + i]);
   }
+  if (tid < 2 * kCH) {  // bounding sphere of every cell (order-4 prefilter of the classification)
+    const int c = tid & (kCH - 1);
+    const double* g = tid < kCH ? I.g : J.g;
+    double P[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) P[k] = g[k * kCH + c];
+    const double mx = (P[0] + P[3] + P[6]) * (1.0 / 3.0), my = (P[1] + P[4] + P[7]) * (1.0 / 3.0), mz = (P[2] + P[5] + P[8]) * (1.0 / 3.0);
+    // radius over the vertices; the dl_max floor sqrt(2 area) <= 1.62 x this radius needs no separate term: the test
+    // below implies D - R > 79 R
+    double r2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double dx = P[3 * k] - mx, dy = P[3 * k + 1] - my, dz = P[3 * k + 2] - mz;
+      r2 = fmax(r2, dx * dx + dy * dy + dz * dz);
+    }
+    const float4 v = make_float4((float)(mx - ox), (float)(my - oy), (float)(mz - oz), (float)(sqrt(r2) * 1.00001));
+    if (tid < kCH) S.u.w.cenI[c] = v;
+    else S.u.w.cenJ[c] = v;
+  }
   if (tid < NCLS) pb.cnt[tid] = 0;
   if (tid == 0) {
     pb.both_count = 0;
@@ -475,6 +497,7 @@ __device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const 
 #pragma unroll
     for (int k = 0; k < 9; k++) pi_[k] = S.u.w.vfI[k * CI + c1];
     const float fli = S.u.w.flI[c1];
+    const float4 ci = S.u.w.cenI[c1];
     const int dminI = I.x.dmin[c1], dmaxI = I.x.dmax[c1];
 #pragma unroll 2
     for (int m = 0; m < NIT; m++) {
@@ -488,11 +511,19 @@ __device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const 
           n1 = true;
         }
         if (n1 || n2) {
-          float pj_[9];
+          // order-4 prefilter: with D the centroid distance and R the sum of the cells' vertex radii,
+          // dl_min >= D-R, dl_max <= D+R (the floor sqrt(2 area) <= 1.62 R < D-R), so dl_min/dl_max > 0.975 > c_thr[0]
+          // as soon as D > 79 R (80 used: FP32 slack)
+          const float4 cj = S.u.w.cenJ[c2];
+          const float ddx = ci.x - cj.x, ddy = ci.y - cj.y, ddz = ci.z - cj.z, rr = ci.w + cj.w + 4.0f * delta;
+          int iq = 4;
+          if (!(fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) > 6400.0f * rr * rr)) {
+            float pj_[9];
 #pragma unroll
-          for (int k = 0; k < 9; k++) pj_[k] = S.u.w.vfJ[k * kCH + c2];
-          int iq = iquad_screen(pi_, pj_, fmaxf(fli, S.u.w.flJ[c2]), delta);
-          if (iq < 0) iq = iquad_exact_cells(I.g, c1, J.g, c2);
+            for (int k = 0; k < 9; k++) pj_[k] = S.u.w.vfJ[k * kCH + c2];
+            iq = iquad_screen(pi_, pj_, fmaxf(fli, S.u.w.flJ[c2]), delta);
+            if (iq < 0) iq = iquad_exact_cells(I.g, c1, J.g, c2);
+          }
           const int cls = cls_of(iq);
           if (cls >= 7) {  // near pairs carry their order and roles (T of unused pairs is never read by a used entry)
             pb.iqmap[c1 * kCH + c2] = (unsigned char)((unsigned)iq | (n1 ? 32u : 0u) | (n2 ? 64u : 0u));
@@ -785,94 +816,176 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
   const int ndI = I.ndof, ndJ = J.ndof;
   const int lane = tid & 31, warp = tid >> 5;
   double* __restrict__ P = S.u.w.P[warp];  // [3][CI] products of this warp
-  constexpr int DB = 4;
-#pragma unroll 1
-  for (int ib0 = warp; ib0 < ndJ; ib0 += NW * DB) {
-    // old values of the block's entries
-    double olda[DB][2], oldm[DB][2];
+  double* __restrict__ E = S.u.w.E;        // [row DOF < 64][column DOF < 64] contribution of this pass, stride TS
+  // ---- D1: contributions of the pass.  This lane's row DOFs a = lane, lane+32 with their incidence lists (scratch
+  // index k*64+cell = low 8 bits of the incidence code, bit 8 = negative) packed in registers (longer lists: slow path)
+  constexpr int MI = 8;
+  int ninc[2];
+  unsigned codes[2][MI / 2];
 #pragma unroll
-    for (int j = 0; j < DB; j++)
+  for (int r = 0; r < 2; r++) {
+    const int ia = lane + 32 * r;
+    ninc[r] = 0;
 #pragma unroll
-      for (int r = 0; r < 2; r++) {
-        olda[j][r] = 0.0;
-        oldm[j][r] = 0.0;
-        const int ib = ib0 + j * NW, ia = lane + 32 * r;
-        if (ib < ndJ && ia < ndI) {
-          double *pa, *pm;
-          if (sel.addr(I, J, ia, ib, pa, pm)) {
-            if (pa) olda[j][r] = __ldcg(pa);
-            if (pm) oldm[j][r] = __ldcg(pm);
-          }
-        }
-      }
-    TW_MARK(S, 0, tid, 7)
+    for (int i = 0; i < MI / 2; i++) codes[r][i] = 0;
+    if (ia < ndI) {
+      const int i0 = I.x.iptr[ia];
+      ninc[r] = I.x.iptr[ia + 1] - i0;
 #pragma unroll
-    for (int j = 0; j < DB; j++) {
-      const int ib = ib0 + j * NW;
-      if (ib >= ndJ) break;
-      // stage 1
-      double ux0 = 0.0, uy0 = 0.0, uz0 = 0.0, ux1 = 0.0, uy1 = 0.0, uz1 = 0.0;
-      for (int i2 = J.x.iptr[ib]; i2 < J.x.iptr[ib + 1]; i2++) {
-        const unsigned w2 = J.x.inc[i2];
-        const int c2 = w2 & 63, k2 = (w2 >> 6) & 3;
-        double t0 = T[lane * TS + c2], t1 = T[(lane + 32) * TS + c2];
-        if (w2 & 256) {
-          t0 = -t0;
-          t1 = -t1;
-        }
-        const double qx = J.g[(10 + 3 * k2) * kCH + c2], qy = J.g[(11 + 3 * k2) * kCH + c2], qz = J.g[(12 + 3 * k2) * kCH + c2];
-        ux0 = fma(qx, t0, ux0);
-        uy0 = fma(qy, t0, uy0);
-        uz0 = fma(qz, t0, uz0);
-        ux1 = fma(qx, t1, ux1);
-        uy1 = fma(qy, t1, uy1);
-        uz1 = fma(qz, t1, uz1);
-      }
-      TW_MARK(S, 0, tid, 8)
-      __syncwarp();  // stage 2 of the previous column DOF is done with the scratch
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        P[k * CI + lane] = fma(I.g[(12 + 3 * k) * kCH + lane], uz0, fma(I.g[(11 + 3 * k) * kCH + lane], uy0, I.g[(10 + 3 * k) * kCH + lane] * ux0));
-        P[k * CI + lane + 32] =
-            fma(I.g[(12 + 3 * k) * kCH + lane + 32], uz1, fma(I.g[(11 + 3 * k) * kCH + lane + 32], uy1, I.g[(10 + 3 * k) * kCH + lane + 32] * ux1));
-      }
-      __syncwarp();
-      TW_MARK(S, 0, tid, 9)
-      // stage 2: row DOFs lane, lane+32 from the preloaded values, further row DOFs (rare) directly
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        const int ia = lane + 32 * r;
-        if (ia >= ndI) continue;
-        double *pa, *pm;
-        if (!sel.addr(I, J, ia, ib, pa, pm)) continue;
-        double acc = 0.0;
-        for (int i1 = I.x.iptr[ia]; i1 < I.x.iptr[ia + 1]; i1++) {
-          const unsigned w1 = I.x.inc[i1];
-          const double v = P[((w1 >> 6) & 3) * CI + (w1 & 63)];
-          acc += (w1 & 256) ? -v : v;
-        }
-        acc *= A.scale;
-        if (pa) __stcg(pa, olda[j][r] + acc);
-        if (pm) __stcg(pm, oldm[j][r] + acc);
-      }
-#pragma unroll 1
-      for (int ia = lane + 64; ia < ndI; ia += 32) {
-        double *pa, *pm;
-        if (!sel.addr(I, J, ia, ib, pa, pm)) continue;
-        const double oa_ = pa ? __ldcg(pa) : 0.0, om_ = pm ? __ldcg(pm) : 0.0;
-        double acc = 0.0;
-        for (int i1 = I.x.iptr[ia]; i1 < I.x.iptr[ia + 1]; i1++) {
-          const unsigned w1 = I.x.inc[i1];
-          const double v = P[((w1 >> 6) & 3) * CI + (w1 & 63)];
-          acc += (w1 & 256) ? -v : v;
-        }
-        acc *= A.scale;
-        if (pa) __stcg(pa, oa_ + acc);
-        if (pm) __stcg(pm, om_ + acc);
-      }
-      TW_MARK(S, 0, tid, 10)
+      for (int i = 0; i < MI; i++)
+        if (i < ninc[r]) codes[r][i >> 1] |= (unsigned)I.x.inc[i0 + i] << (16 * (i & 1));
     }
   }
+#pragma unroll 1
+  for (int ib = warp; ib < ndJ; ib += NW) {
+    // stage 1
+    double ux0 = 0.0, uy0 = 0.0, uz0 = 0.0, ux1 = 0.0, uy1 = 0.0, uz1 = 0.0;
+    for (int i2 = J.x.iptr[ib]; i2 < J.x.iptr[ib + 1]; i2++) {
+      const unsigned w2 = J.x.inc[i2];
+      const int c2 = w2 & 63, k2 = (w2 >> 6) & 3;
+      double t0 = T[lane * TS + c2], t1 = T[(lane + 32) * TS + c2];
+      if (w2 & 256) {
+        t0 = -t0;
+        t1 = -t1;
+      }
+      const double qx = J.g[(10 + 3 * k2) * kCH + c2], qy = J.g[(11 + 3 * k2) * kCH + c2], qz = J.g[(12 + 3 * k2) * kCH + c2];
+      ux0 = fma(qx, t0, ux0);
+      uy0 = fma(qy, t0, uy0);
+      uz0 = fma(qz, t0, uz0);
+      ux1 = fma(qx, t1, ux1);
+      uy1 = fma(qy, t1, uy1);
+      uz1 = fma(qz, t1, uz1);
+    }
+    __syncwarp();  // stage 2 of the previous column DOF is done with the scratch
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      P[k * CI + lane] = fma(I.g[(12 + 3 * k) * kCH + lane], uz0, fma(I.g[(11 + 3 * k) * kCH + lane], uy0, I.g[(10 + 3 * k) * kCH + lane] * ux0));
+      P[k * CI + lane + 32] =
+          fma(I.g[(12 + 3 * k) * kCH + lane + 32], uz1, fma(I.g[(11 + 3 * k) * kCH + lane + 32], uy1, I.g[(10 + 3 * k) * kCH + lane + 32] * ux1));
+    }
+    __syncwarp();
+    // stage 2
+    const bool fast_b = ib < kCH;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int ia = lane + 32 * r;
+      if (ia >= ndI) continue;
+      double acc = 0.0;
+      if (ninc[r] <= MI) {
+#pragma unroll
+        for (int i = 0; i < MI; i++) {
+          const unsigned code = (codes[r][i >> 1] >> (16 * (i & 1))) & 0x1FFu;
+          if (i < ninc[r]) {
+            const double v = P[code & 255u];
+            acc += (code & 256u) ? -v : v;
+          }
+        }
+      } else {
+        for (int i1 = I.x.iptr[ia]; i1 < I.x.iptr[ia + 1]; i1++) {
+          const unsigned w1 = I.x.inc[i1];
+          const double v = P[w1 & 255u];
+          acc += (w1 & 256u) ? -v : v;
+        }
+      }
+      acc *= A.scale;
+      if (fast_b) {
+        E[ia * TS + ib] = acc;
+      } else {  // more than 64 column DOFs in the chunk (rare): write directly
+        double *pa, *pm;
+        if (sel.addr(I, J, ia, ib, pa, pm)) {
+          if (pa) __stcg(pa, __ldcg(pa) + acc);
+          if (pm) __stcg(pm, __ldcg(pm) + acc);
+        }
+      }
+    }
+    // more than 64 row DOFs in the chunk (rare): write directly
+#pragma unroll 1
+    for (int ia = lane + 64; ia < ndI; ia += 32) {
+      double *pa, *pm;
+      if (!sel.addr(I, J, ia, ib, pa, pm)) continue;
+      double acc = 0.0;
+      for (int i1 = I.x.iptr[ia]; i1 < I.x.iptr[ia + 1]; i1++) {
+        const unsigned w1 = I.x.inc[i1];
+        const double v = P[w1 & 255u];
+        acc += (w1 & 256u) ? -v : v;
+      }
+      acc *= A.scale;
+      if (pa) __stcg(pa, __ldcg(pa) + acc);
+      if (pm) __stcg(pm, __ldcg(pm) + acc);
+    }
+  }
+  __syncthreads();  // the block E is complete
+  TW_MARK(S, 0, tid, 7)
+  // ---- D2: add the block into L.  A warp takes rows a = warp, warp+16, ...; lanes run over the column DOFs, whose
+  // reference ids ascend within a chunk: neighbouring lanes touch neighbouring addresses of one matrix row.  The old
+  // values of all the warp's entries are loaded first (one memory latency), then added and stored.  Every entry is
+  // owned by this CTA: plain loads and stores, no atomics.
+  const int nbJ = min(ndJ, kCH), naI = min(ndI, kCH);
+  {
+    int ob[2];
+    ob[0] = lane < nbJ ? J.x.orig[lane] : 0;
+    ob[1] = lane + 32 < nbJ ? J.x.orig[lane + 32] : 0;
+    constexpr int RW = kCH / NW;  // rows per warp
+    double old[RW][2];
+    unsigned use = 0;
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+      const int ia = warp + NW * q;
+      double* rowp = nullptr;
+      int oa = 0;
+      if (ia < naI) {
+        const int ra = I.row[ia];
+        oa = I.x.orig[ia];
+        if (ra >= 0) rowp = A.out + (long long)ra * A.ld;
+      }
+#pragma unroll
+      for (int hb = 0; hb < 2; hb++) {
+        old[q][hb] = 0.0;
+        bool ok = rowp != nullptr && lane + 32 * hb < nbJ;
+        if (ok && A.self) {
+          const bool role1 = oa <= ob[hb];
+          if ((sel.diag && !role1) || (role_sel == 1 && !role1) || (role_sel == 2 && role1)) ok = false;
+        }
+        if (ok) {
+          use |= 1u << (2 * q + hb);
+          old[q][hb] = __ldcg(rowp + ob[hb]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+      const int ia = warp + NW * q;
+      if (ia >= naI) continue;
+      const int ra = I.row[ia];
+      double* rowp = A.out + (long long)(ra >= 0 ? ra : 0) * A.ld;
+#pragma unroll
+      for (int hb = 0; hb < 2; hb++)
+        if ((use >> (2 * q + hb)) & 1u) __stcg(rowp + ob[hb], old[q][hb] + E[ia * TS + lane + 32 * hb]);
+    }
+  }
+  if (sel.mirror) {  // transposed entries (rows of the column patch are in the output block, rows of this patch are not)
+    int oa[2];
+    oa[0] = lane < naI ? I.x.orig[lane] : 0;
+    oa[1] = lane + 32 < naI ? I.x.orig[lane + 32] : 0;
+#pragma unroll 1
+    for (int ib = warp; ib < nbJ; ib += NW) {
+      const int rb = J.row[ib];
+      if (rb < 0) continue;
+      const int ob = J.x.orig[ib];
+      double* rowp = A.out + (long long)rb * A.ld;
+#pragma unroll
+      for (int ha = 0; ha < 2; ha++) {
+        const int ia = lane + 32 * ha;
+        if (ia >= naI || oa[ha] == ob) continue;
+        if (A.self) {
+          const bool role1 = oa[ha] <= ob;
+          if ((sel.diag && !role1) || (role_sel == 1 && !role1) || (role_sel == 2 && role1)) continue;
+        }
+        __stcg(rowp + oa[ha], __ldcg(rowp + oa[ha]) + E[ia * TS + ib]);
+      }
+    }
+  }
+  TW_MARK(S, 0, tid, 8)
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------
@@ -1205,7 +1318,7 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
     std::memcpy(h_stats, hs, 8 * sizeof(unsigned long long));
 #ifdef TW_LMAT_PROF
     {
-      static const char* nm[13] = {"tile_fetch", "wait+A0", "scatter+queue+bar", "eval", "drain_rest", "classify_loop", "bins+bar", "D:issue_loads", "D:stage1", "D:products", "D:stage2", "-", "-"};
+      static const char* nm[13] = {"tile_fetch", "wait+A0", "scatter+queue+bar", "eval", "drain_rest", "classify_loop", "bins+bar", "D1:contract", "D2:add_into_L", "-", "-", "-", "-"};
       std::fprintf(stderr, "[lmat prof, CTA 0, Mcycles]");
       for (int i = 0; i < 13; i++) std::fprintf(stderr, " %s=%.1f", nm[i], hs[8 + i] * 1e-6);
       std::fprintf(stderr, "\n");

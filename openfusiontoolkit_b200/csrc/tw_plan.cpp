@@ -46,7 +46,10 @@ std::string build_patches(const Model& m, int P, PatchSet& ps) {
     // the near-field-heavy diagonal tiles must stay short against a CTA's share of the build and the tile count
     // must fill 148 SMs many times over: ~300 DOFs per patch (measured on the 20k vessel: 150 -> 186 ms,
     // 300 -> 169 ms, 600 -> 235 ms), fewer on small meshes (>= ~1500 tiles, >= 32 DOFs).
-    P = 300;
+    // Larger meshes take larger patches (100k-vertex vessel: 300 -> 2261 ms, 650 -> 2120 ms, 1200 -> 2077 ms) as long as
+    // one device of eight still gets ~2000 tiles: P = nv / (66 sqrt(8)).  The rule depends on the mesh only, so every
+    // shard count works on the same patches and produces the same bits.
+    P = std::min(1200, std::max(300, nv / 187));
     while (P > 32 && ((long)((nv + P - 1) / P) * ((nv + P - 1) / P)) / 2 < 1500) P = P * 3 / 4;
     P = std::max(P, 32);
   }
@@ -180,7 +183,8 @@ std::string build_patches(const Model& m, int P, PatchSet& ps) {
         cm.rad = std::sqrt(r2) * (1.0 + 1e-12);
       }
       auto& L = by_chunk[ch];
-      std::stable_sort(L.begin(), L.end(), [](const Inc& a, const Inc& b) { return a.dof_local < b.dof_local; });
+      // local DOFs in ascending reference id: neighbouring lanes of the kernel's write-out touch neighbouring columns
+      std::stable_sort(L.begin(), L.end(), [&](const Inc& a, const Inc& b) { return ps.dof_orig[d0 + a.dof_local] < ps.dof_orig[d0 + b.dof_local]; });
       std::vector<int> ptr;
       int prev = -1;
       for (size_t k = 0; k < L.size(); k++) {
