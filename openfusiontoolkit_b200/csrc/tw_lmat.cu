@@ -1096,15 +1096,37 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {  /
 
 // Symmetrisation of the owned diagonal block: for internal DOFs i, j in [i0, i1) the tile kernel computed entry
 // [i][j] iff patch(i) < patch(j), or the patches are equal and orig(i) <= orig(j); the other one is its copy
-// (thin_wall.F90:1146-1151).  One block per row.
+// (thin_wall.F90:1146-1151).  32 x 32 blocks of internal DOFs through shared memory: internal order is spatial, so
+// the reference ids of a block are a few short runs and both the reads (rows j, columns orig(i)) and the writes
+// (rows i, columns orig(j)) touch a few sectors per row instead of one per element.
 __global__ void symmetrize_kernel(int i0, int i1, const int* __restrict__ dof_orig, const int* __restrict__ dof_patch,
                                   double* __restrict__ out, long long ld) {
-  const int i = i0 + blockIdx.x;
-  const int oi = dof_orig[i], pi = dof_patch[i];
-  double* row = out + (long long)blockIdx.x * ld;
-  for (int j = i0 + threadIdx.x; j < i1; j += blockDim.x) {
-    const int pj = dof_patch[j], oj = dof_orig[j];
-    if (pj < pi || (pj == pi && oj < oi)) row[oj] = __ldcg(out + (long long)(j - i0) * ld + oi);
+  __shared__ double tile[32][33];
+  __shared__ int oi_s[32], pi_s[32], oj_s[32], pj_s[32];
+  const int ib = i0 + 32 * blockIdx.x, jb = i0 + 32 * blockIdx.y;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  if (ty == 0) {
+    const int i = ib + tx;
+    oi_s[tx] = i < i1 ? dof_orig[i] : -1;
+    pi_s[tx] = i < i1 ? dof_patch[i] : -1;
+  } else if (ty == 1) {
+    const int j = jb + tx;
+    oj_s[tx] = j < i1 ? dof_orig[j] : -1;
+    pj_s[tx] = j < i1 ? dof_patch[j] : -1;
+  }
+  __syncthreads();
+  // does any entry of this block pair need a copy?  (block-uniform early exit: patches are contiguous DOF ranges)
+  if (pj_s[0] > pi_s[min(31, i1 - 1 - ib)]) return;
+  for (int jj = ty; jj < 32; jj += 8) {  // read [j][orig(i)], lanes over i
+    const int j = jb + jj;
+    if (j < i1 && oi_s[tx] >= 0) tile[jj][tx] = __ldcg(out + (long long)(j - i0) * ld + oi_s[tx]);
+  }
+  __syncthreads();
+  for (int ii = ty; ii < 32; ii += 8) {  // write [i][orig(j)], lanes over j
+    const int i = ib + ii;
+    if (i >= i1 || oj_s[tx] < 0) continue;
+    const int pi = pi_s[ii], oi = oi_s[ii], pj = pj_s[tx], oj = oj_s[tx];
+    if (pj < pi || (pj == pi && oj < oi)) out[(long long)(i - i0) * ld + oj] = tile[tx][ii];
   }
 }
 
@@ -1306,7 +1328,8 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
         i1 = i + 1;
       }
     if (i0 >= 0 && i1 - i0 > 1) {
-      twk::symmetrize_kernel<<<i1 - i0, 256, 0, stream>>>(i0, i1, A.dof_orig, A.dof_patch, d_out, ld);
+      const int nb = (i1 - i0 + 31) / 32;
+      twk::symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, stream>>>(i0, i1, A.dof_orig, A.dof_patch, d_out, ld);
       CK(cudaGetLastError());
       note_launch();
     }
