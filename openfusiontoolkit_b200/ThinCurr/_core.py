@@ -315,11 +315,12 @@ class ThinCurr():
                                    st.ctypes.data_as(c_void_p) if stats else None))
         return st
 
-    def exchange_symmetric(self, out, nshards, shard, group=None, row_ids=None):
+    def exchange_symmetric(self, out, nshards, shard, group=None, row_ids=None, one_shot=True):
         '''! Complete the rows built by `compute_Lmat_shard_sym`: L[rows of shard r][DOFs of shard s] for s < r is the
-        transpose of the block shard s computed (thin_wall.F90:1146-1151 mirrors the same way).  One send/recv per pair
-        of ranks over the process group (NCCL on GPUs), in nshards-1 rounds so that only one block is staged at a
-        time.  `out` is this rank's [nrows, ld] tensor; `row_ids[s]` (optional) the DOF ids of every shard.'''
+        transpose of the block shard s computed (thin_wall.F90:1146-1151 mirrors the same way).  `out` is this rank's
+        [nrows, ld] tensor; `row_ids[s]` (optional) the DOF ids of every shard.  `one_shot`: all blocks in a single
+        all-to-all (NCCL on GPUs; staging buffers as large as the exchanged blocks); otherwise nshards-1 rounds of one
+        send/recv per rank with a single block staged at a time.'''
         import torch
         import torch.distributed as dist
         if nshards == 1:
@@ -327,21 +328,38 @@ class ThinCurr():
         if row_ids is None:
             row_ids = [self.shard_rows_sym(nshards, s) for s in range(nshards)]
         ids = [torch.as_tensor(numpy.ascontiguousarray(r, dtype=numpy.int64), device=out.device) for r in row_ids]
-        nmine = len(row_ids[shard])
+        nr = [len(r) for r in row_ids]
+        nmine = nr[shard]
+        mine = out[:nmine]
+        if one_shot:
+            send_split = [nmine * nr[s] if s > shard else 0 for s in range(nshards)]
+            recv_split = [nr[s] * nmine if s < shard else 0 for s in range(nshards)]
+            later = torch.cat(ids[shard + 1:]) if shard + 1 < nshards else ids[shard][:0]
+            # [DOFs of later shards, my rows]: the receiver's layout (its rows x my rows), one contiguous piece per shard
+            send = mine.index_select(1, later).t().contiguous().view(-1) if sum(send_split) else out.new_empty(0)
+            recv = out.new_empty(sum(recv_split))
+            dist.all_to_all_single(recv, send, recv_split, send_split, group=group)
+            off = 0
+            for s in range(shard):
+                if recv_split[s]:
+                    # sender s packed [my rows, its rows]; L[my rows][its DOFs] = that block as it is
+                    mine.index_copy_(1, ids[s], recv[off:off + recv_split[s]].view(nmine, nr[s]))
+                    off += recv_split[s]
+            return
         for d in range(1, nshards):
             dst, src = shard + d, shard - d
             ops, recv = [], None
-            if dst < nshards and nmine and len(row_ids[dst]):
-                send = out[:nmine].index_select(1, ids[dst]).contiguous()   # [my rows, DOFs of the later shard]
+            if dst < nshards and nmine and nr[dst]:
+                send = mine.index_select(1, ids[dst]).contiguous()   # [my rows, DOFs of the later shard]
                 ops.append(dist.P2POp(dist.isend, send, dst, group=group))
-            if src >= 0 and nmine and len(row_ids[src]):
-                recv = torch.empty((len(row_ids[src]), nmine), dtype=out.dtype, device=out.device)
+            if src >= 0 and nmine and nr[src]:
+                recv = torch.empty((nr[src], nmine), dtype=out.dtype, device=out.device)
                 ops.append(dist.P2POp(dist.irecv, recv, src, group=group))
             if ops:
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()
             if recv is not None:
-                out[:nmine].index_copy_(1, ids[src], recv.t())
+                mine.index_copy_(1, ids[src], recv.t())
 
     def compute_Lmat_shard_host(self, nshards, shard, out, stats=False):
         '''! End-to-end variant: host mesh -> device build -> host rows (`out` is a numpy array).'''

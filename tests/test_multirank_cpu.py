@@ -72,8 +72,10 @@ def _worker_sym(rank, world, port, q):
     out = torch.from_numpy(A[mine].copy())
     for s in range(rank):                      # what the upper-trapezoid build leaves empty
         out[:, torch.as_tensor(ids[s].astype(np.int64))] = 0.0
-    T.exchange_symmetric(out, world, rank, row_ids=ids)
-    ok = bool(np.array_equal(out.numpy(), A[mine]))
+    out2 = out.clone()
+    T.exchange_symmetric(out, world, rank, row_ids=ids)                    # one all-to-all
+    T.exchange_symmetric(out2, world, rank, row_ids=ids, one_shot=False)   # rounds of send/recv
+    ok = bool(np.array_equal(out.numpy(), A[mine])) and bool(np.array_equal(out2.numpy(), A[mine]))
     res = [None] * world
     dist.all_gather_object(res, (ok, [len(i) for i in ids], int(sum(len(i) for i in ids)), N))
     if rank == 0:
