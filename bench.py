@@ -256,6 +256,16 @@ def main():
     if not (0.0 < kern_ms <= 1.05 * ms_step):
         kern_ms = ms_step
 
+    # N > 1: sanity check of the exchange outside the timed region -- block sums of L[rows r][DOFs s] and
+    # L[rows s][DOFs r] (its transpose, held by the other rank) must agree
+    exchange_check = None
+    if sym:
+        bs = torch.stack([out[:, torch.as_tensor(i.astype(np.int64), device='cuda')].sum() for i in ids_all])
+        allbs = [torch.empty_like(bs) for _ in range(world)]
+        dist.all_gather(allbs, bs)
+        M = torch.stack(allbs).cpu().numpy()
+        exchange_check = float(np.abs(M - M.T).max() / np.abs(M).max())
+
     # e2e through the host-buffer entry point
     e2e = None
     if not args.no_e2e:
@@ -305,6 +315,7 @@ def main():
                        'order_hist': {str(q): int(hist[q]) for q in range(4, 19)}, 'sharding': ('row blocks, 1 shard, no collective' if not sym else
                                     'row blocks balanced over the upper trapezoid, %d shards, no traffic during assembly; transposed blocks '
                                     'exchanged once afterwards (NCCL send/recv, inside the timed step)' % world),
+                       'exchange_check_rel': exchange_check,
                        'l2': 'flushed every step by the %.1f GB output memset' % (nrows * N * 8 / 1e9), 'plan': T.plan_info()},
             'wall_ms_per_step': ms_wall / args.steps, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'roofline': roofline, 'cpu_baseline': cpu}

@@ -1203,6 +1203,15 @@ std::string gpu_init_constants() {
   CK(cudaMemcpyToSymbol(twk::c_thr, thr, sizeof(thr)));
   CK(cudaMemcpyToSymbol(twk::c_thr2, thr2, sizeof(thr2)));
   CK(cudaFuncSetAttribute(twk::lmat_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(twk::Smem)));
+  {
+    // per-launch temporaries come from the stream-ordered pool (cudaMalloc would synchronise the device, which
+    // serialises against a peer's collective in multi-process runs); keep the pool's memory between launches
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   done_dev = dev;
   return "";
 }
@@ -1283,17 +1292,17 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   int* d_row_out = nullptr;
   int* d_counter = nullptr;
   unsigned long long* d_stats = nullptr;
-  CK(cudaMalloc((void**)&d_tiles, tiles.size() * sizeof(Tile)));
-  CK(cudaMalloc((void**)&d_row_out, std::max<size_t>(row_out.size(), 1) * sizeof(int)));
-  CK(cudaMalloc((void**)&d_counter, sizeof(int)));
-  CK(cudaMalloc((void**)&d_stats, 24 * sizeof(unsigned long long)));
+  CK(cudaMallocAsync((void**)&d_tiles, tiles.size() * sizeof(Tile), stream));
+  CK(cudaMallocAsync((void**)&d_row_out, std::max<size_t>(row_out.size(), 1) * sizeof(int), stream));
+  CK(cudaMallocAsync((void**)&d_counter, sizeof(int), stream));
+  CK(cudaMallocAsync((void**)&d_stats, 24 * sizeof(unsigned long long), stream));
   CK(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(d_row_out, row_out.data(), row_out.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
   CK(cudaMemsetAsync(d_counter, 0, sizeof(int), stream));
   CK(cudaMemsetAsync(d_stats, 0, 24 * sizeof(unsigned long long), stream));
   CK(cudaMemsetAsync(d_stats + 7, 0xff, sizeof(unsigned long long), stream));
   int* d_chunk_row = nullptr;
-  CK(cudaMalloc((void**)&d_chunk_row, (size_t)std::max(A.nchunk, 1) * kMaxChunkDof * sizeof(int)));
+  CK(cudaMallocAsync((void**)&d_chunk_row, (size_t)std::max(A.nchunk, 1) * kMaxChunkDof * sizeof(int), stream));
   twk::chunk_rows_kernel<<<std::max(A.nchunk, 1), kMaxChunkDof, 0, stream>>>(A.nchunk, A.chunks, A.chunk_dof, d_row_out, d_chunk_row);
   CK(cudaGetLastError());
   note_launch();
