@@ -77,6 +77,7 @@ struct LmatArgs {
   long long ld;
   double scale;                       // 1/(4 pi)
   int self;                           // 1: self inductance (role rule, mirror), 0: mutual
+  int fast_lim;                       // local DOFs per chunk side handled through the shared-memory block (64; 32 or 0 in tests of the direct path)
   int debug_skip;                     // profiling aid: bit0 skip near-field evaluation, bit1 skip far-field evaluation,
                                       // bit2 skip the contraction
   unsigned long long* stats;          // [0] far pairs, [1] near T evaluations, [2] 1/r evaluations, [3] phipot evals
@@ -817,6 +818,7 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
   const int lane = tid & 31, warp = tid >> 5;
   double* __restrict__ P = S.u.w.P[warp];  // [3][CI] products of this warp
   double* __restrict__ E = S.u.w.E;        // [row DOF < 64][column DOF < 64] contribution of this pass, stride TS
+  const int lim = A.fast_lim;              // 64 (tests of the direct-write path: 32 or 0)
   // ---- D1: contributions of the pass.  This lane's row DOFs a = lane, lane+32 with their incidence lists (scratch
   // index k*64+cell = low 8 bits of the incidence code, bit 8 = negative) packed in registers (longer lists: slow path)
   constexpr int MI = 8;
@@ -865,11 +867,11 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
     }
     __syncwarp();
     // stage 2
-    const bool fast_b = ib < kCH;
+    const bool fast_b = ib < lim;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       const int ia = lane + 32 * r;
-      if (ia >= ndI) continue;
+      if (ia >= ndI || 32 * r >= lim) continue;
       double acc = 0.0;
       if (ninc[r] <= MI) {
 #pragma unroll
@@ -887,20 +889,19 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
           acc += (w1 & 256u) ? -v : v;
         }
       }
-      acc *= A.scale;
       if (fast_b) {
         E[ia * TS + ib] = acc;
       } else {  // more than 64 column DOFs in the chunk (rare): write directly
         double *pa, *pm;
         if (sel.addr(I, J, ia, ib, pa, pm)) {
-          if (pa) __stcg(pa, __ldcg(pa) + acc);
-          if (pm) __stcg(pm, __ldcg(pm) + acc);
+          if (pa) __stcg(pa, fma(acc, A.scale, __ldcg(pa)));  // (every path: one fused scale-and-add)
+          if (pm) __stcg(pm, fma(acc, A.scale, __ldcg(pm)));
         }
       }
     }
     // more than 64 row DOFs in the chunk (rare): write directly
 #pragma unroll 1
-    for (int ia = lane + 64; ia < ndI; ia += 32) {
+    for (int ia = lane + lim; ia < ndI; ia += 32) {
       double *pa, *pm;
       if (!sel.addr(I, J, ia, ib, pa, pm)) continue;
       double acc = 0.0;
@@ -909,9 +910,8 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
         const double v = P[w1 & 255u];
         acc += (w1 & 256u) ? -v : v;
       }
-      acc *= A.scale;
-      if (pa) __stcg(pa, __ldcg(pa) + acc);
-      if (pm) __stcg(pm, __ldcg(pm) + acc);
+      if (pa) __stcg(pa, fma(acc, A.scale, __ldcg(pa)));  // (every path: one fused scale-and-add)
+      if (pm) __stcg(pm, fma(acc, A.scale, __ldcg(pm)));
     }
   }
   __syncthreads();  // the block E is complete
@@ -920,7 +920,7 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
   // reference ids ascend within a chunk: neighbouring lanes touch neighbouring addresses of one matrix row.  The old
   // values of all the warp's entries are loaded first (one memory latency), then added and stored.  Every entry is
   // owned by this CTA: plain loads and stores, no atomics.
-  const int nbJ = min(ndJ, kCH), naI = min(ndI, kCH);
+  const int nbJ = min(ndJ, lim), naI = min(ndI, lim);
   {
     int ob[2];
     ob[0] = lane < nbJ ? J.x.orig[lane] : 0;
@@ -960,7 +960,7 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
       double* rowp = A.out + (long long)(ra >= 0 ? ra : 0) * A.ld;
 #pragma unroll
       for (int hb = 0; hb < 2; hb++)
-        if ((use >> (2 * q + hb)) & 1u) __stcg(rowp + ob[hb], old[q][hb] + E[ia * TS + lane + 32 * hb]);
+        if ((use >> (2 * q + hb)) & 1u) __stcg(rowp + ob[hb], fma(E[ia * TS + lane + 32 * hb], A.scale, old[q][hb]));
     }
   }
   if (sel.mirror) {  // transposed entries (rows of the column patch are in the output block, rows of this patch are not)
@@ -981,7 +981,7 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
           const bool role1 = oa[ha] <= ob;
           if ((sel.diag && !role1) || (role_sel == 1 && !role1) || (role_sel == 2 && role1)) continue;
         }
-        __stcg(rowp + oa[ha], __ldcg(rowp + oa[ha]) + E[ia * TS + ib]);
+        __stcg(rowp + oa[ha], fma(E[ia * TS + ib], A.scale, __ldcg(rowp + oa[ha])));
       }
     }
   }
@@ -1319,6 +1319,8 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   a.ld = ld;
   a.scale = 1.0 / (4.0 * kPi);
   a.self = self ? 1 : 0;
+  a.fast_lim = 64;
+  if (const char* e = std::getenv("THINCURR_B200_DRAIN_LIMIT")) a.fast_lim = std::atoi(e) >= 64 ? 64 : (std::atoi(e) >= 32 ? 32 : 0);
   a.debug_skip = std::getenv("THINCURR_B200_DEBUG_SKIP") ? std::atoi(std::getenv("THINCURR_B200_DEBUG_SKIP")) : 0;
   a.stats = d_stats;
   int dev = 0, nsm = 148;

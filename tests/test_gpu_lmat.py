@@ -63,3 +63,27 @@ def test_lmat_entries_and_eigs(env, name, js):
         assert np.abs(wg / wo - 1.0).max() < EIG_TOL
         g = G['eig_' + name]
         assert np.abs(wg / np.array(g['vals']) - 1.0).max() < g['tol']
+
+
+@pytest.mark.parametrize('limit', ['32', '0'])
+def test_contraction_direct_write_path(env, limit, monkeypatch):
+    """Chunks with more than 64 local DOFs per side take a direct-write path in the contraction that ordinary
+    meshes never reach; THINCURR_B200_DRAIN_LIMIT lowers the limit so that the path runs (rows, columns, both) and
+    must reproduce the normal build bit for bit, for the single-device and the row-sharded (mirror-writing) tiles."""
+    import torch
+    O, T = build_pair(env, 'torus', 0)
+    T.compute_Lmat()
+    ref = np.array(T.Lmat)
+    rows = T.shard_rows(3, 2)
+    out0 = torch.empty((len(rows), T.nelems), dtype=torch.float64, device='cuda')
+    T.compute_Lmat_shard(3, 2, out0)
+    torch.cuda.synchronize()
+    monkeypatch.setenv('THINCURR_B200_DRAIN_LIMIT', limit)
+    full = torch.empty((T.nelems, T.nelems), dtype=torch.float64, device='cuda')
+    T.compute_Lmat_shard(1, 0, full)
+    out1 = torch.empty_like(out0)
+    T.compute_Lmat_shard(3, 2, out1)
+    torch.cuda.synchronize()
+    allrows = T.shard_rows(1, 0)
+    assert np.array_equal(full.cpu().numpy(), ref[allrows])
+    assert np.array_equal(out1.cpu().numpy(), out0.cpu().numpy())
