@@ -144,6 +144,12 @@ int thincurr_b200_Lmat_shard_sym(void* tw_ptr, int nshards, int shard, double* d
  * the end-to-end path used by bench.py's e2e leg. */
 int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* h_out, int64_t ld,
                                   int64_t* stats);
+/* Minimal HDF5 writer (no libhdf5 needed): root-level contiguous little-endian datasets, float64 (is_f64[i] != 0) or
+ * int32, dims[] = the dimensions of all items concatenated in C order (slowest first); at most 8 items.  This is the
+ * container of the reference's Bmat cache (thin_wall.F90:2208-2225: MODEL_hash, Bel_X|Y|Z, Bdr_X|Y|Z), which
+ * thincurr_Bmat writes and reads through it. */
+int thincurr_b200_h5_write(const char* path, int nitems, const char* const* names, const int* is_f64, const int* ranks,
+                           const int64_t* dims, const void* const* data);
 /* B-field operator rows (element index sharded the same way): d_out[3][np][nrows] */
 int thincurr_b200_Bel_shard(void* tw_ptr, int nshards, int shard, double* d_out, void* stream);
 

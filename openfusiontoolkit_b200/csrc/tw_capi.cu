@@ -409,10 +409,13 @@ void thincurr_Bmat(void* tw_ptr, void* hodlr_ptr, void** Bmat_ptr, void** Bdr_pt
   if (hodlr_ptr) return set_err(error_str, "HODLR compression is not provided by the B200 dense backend");
   Model& m = *(Model*)tw_ptr;
   std::string cache = cstr(cache_file);
-  (void)cache;  // HDF5 Bmat cache: writer not provided (no HDF5 here); the operator is rebuilt
-  std::printf(" Building element->element magnetic reconstruction operator\n");
-  std::string err = gpu_bmat(m);
-  if (!err.empty()) return set_err(error_str, err);
+  const bool use_cache = !cache.empty() && cache != "none";
+  if (!(use_cache && bmat_cache_read(m, cache))) {
+    std::printf(" Building element->element magnetic reconstruction operator\n");
+    std::string err = gpu_bmat(m);
+    if (!err.empty()) return set_err(error_str, err);
+    if (use_cache) bmat_cache_write(m, cache);
+  }
   *Bmat_ptr = m.Bel.p;
   *Bdr_ptr = m.Bdr.p;
 }
@@ -685,6 +688,23 @@ int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* 
     stats[5] = m.dev.empty() ? 0 : (int64_t)m.dev[0]->ps.bytes;  // host->device bytes of the model upload
     stats[6] = (int64_t)bytes;                                   // device->host bytes
   }
+  return 0;
+}
+
+int thincurr_b200_h5_write(const char* path, int nitems, const char* const* names, const int* is_f64, const int* ranks,
+                           const int64_t* dims, const void* const* data) {
+  std::vector<H5Item> items;
+  size_t o = 0;
+  for (int i = 0; i < nitems; i++) {
+    H5Item it;
+    it.name = names[i];
+    it.f64 = is_f64[i] != 0;
+    for (int k = 0; k < ranks[i]; k++) it.dims.push_back((uint64_t)dims[o++]);
+    it.data = data[i];
+    items.push_back(it);
+  }
+  std::string err = write_h5_file(path, items);
+  if (!err.empty()) return fail(err);
   return 0;
 }
 

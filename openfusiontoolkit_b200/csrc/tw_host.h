@@ -148,6 +148,16 @@ struct NativeMesh {
   std::vector<std::vector<int>> nodesets, sidesets;  // 1-based
 };
 std::string read_native_mesh(const std::string& path, NativeMesh& out);
+// minimal HDF5 writer / raw readers (operator caches, thin_wall.F90:2175-2225): root-level contiguous datasets
+struct H5Item {
+  std::string name;
+  bool f64;                    // float64, else int32
+  std::vector<uint64_t> dims;  // C order (slowest first)
+  const void* data;
+};
+std::string write_h5_file(const std::string& path, const std::vector<H5Item>& items);
+std::string read_h5_dataset_f64_into(const std::string& path, const std::string& name, double* dst, uint64_t count);
+std::string read_h5_dataset_i32(const std::string& path, const std::string& name, std::vector<int32_t>& out);
 std::string read_h5_dataset_f64(const std::string& path, const std::string& name, std::vector<double>& out,
                                 std::vector<uint64_t>& shape);
 std::string read_floops(const std::string& path, Sensors& out);

@@ -4,12 +4,18 @@
 // No libhdf5 / FoX is available (or wanted) here: the native mesh format written by
 // OpenFUSIONToolkit/util.py:62-94 (h5py defaults: superblock v0, v1 object headers, symbol
 // table groups, contiguous little-endian datasets) is parsed directly.
+#include <algorithm>
 #include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <sstream>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "tw_host.h"
 
@@ -259,8 +265,21 @@ std::string Model::load_eta_xml(const XmlNode* tc) {
 // ------------------------------------------------------------------ minimal HDF5 reader
 namespace {
 struct H5File {
-  std::vector<uint8_t> b;
+  // read-only mapping of the file (operator caches can be tens of GB: nothing is copied up front)
+  struct Map {
+    const uint8_t* p = nullptr;
+    size_t n = 0;
+    size_t size() const { return n; }
+    const uint8_t* data() const { return p; }
+    const uint8_t& operator[](size_t i) const { return p[i]; }
+  } b;
   std::string err;
+  H5File() = default;
+  H5File(const H5File&) = delete;
+  H5File& operator=(const H5File&) = delete;
+  ~H5File() {
+    if (b.p) munmap((void*)b.p, b.n);
+  }
   template <class T>
   T rd(size_t off) const {
     T v;
@@ -273,19 +292,27 @@ struct H5File {
     size_t off, size;
   };
   bool open(const std::string& path) {
-    FILE* f = std::fopen(path.c_str(), "rb");
-    if (!f) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) {
       err = "file does not exist or is not accessible";
       return false;
     }
-    std::fseek(f, 0, SEEK_END);
-    long n = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    b.resize((size_t)n);
-    size_t got = std::fread(b.data(), 1, (size_t)n, f);
-    std::fclose(f);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 96) {
+      ::close(fd);
+      err = "not an HDF5 file";
+      return false;
+    }
+    void* mp = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (mp == MAP_FAILED) {
+      err = "cannot map file";
+      return false;
+    }
+    b.p = (const uint8_t*)mp;
+    b.n = (size_t)st.st_size;
     static const uint8_t sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
-    if (got != (size_t)n || n < 96 || std::memcmp(b.data(), sig, 8) != 0) {
+    if (std::memcmp(b.data(), sig, 8) != 0) {
       err = "not an HDF5 file";
       return false;
     }
@@ -358,6 +385,43 @@ struct H5File {
     }
     return true;
   }
+  // address, element count, type class (0 int, 1 float) and element size of a contiguous dataset
+  bool locate(uint64_t ohdr, uint64_t& addr, uint64_t& n, int& cls, int& size) {
+    std::vector<uint64_t> shape;
+    cls = -1;
+    size = 0;
+    addr = ~0ull;
+    bool have_layout = false;
+    for (auto& m : messages(ohdr)) {
+      if (m.type == 1) {
+        uint8_t ver = b[m.off], rank = b[m.off + 1];
+        size_t o = m.off + (ver == 1 ? 8 : 4);
+        for (int k = 0; k < rank; k++) shape.push_back(rd<uint64_t>(o + 8 * k));
+      } else if (m.type == 3) {
+        cls = b[m.off] & 0xf;
+        size = (int)rd<uint32_t>(m.off + 4);
+      } else if (m.type == 8) {
+        uint8_t ver = b[m.off];
+        if ((ver == 3 && b[m.off + 1] != 1) || (ver != 3 && b[m.off + 2] != 1)) {
+          err = "only contiguous datasets are supported";
+          return false;
+        }
+        addr = ver == 3 ? rd<uint64_t>(m.off + 2) : rd<uint64_t>(m.off + 8);
+        have_layout = true;
+      }
+    }
+    n = 1;
+    for (auto s_ : shape) n *= s_;
+    if (cls < 0 || !have_layout || (n && addr == ~0ull)) {
+      err = "dataset header incomplete";
+      return false;
+    }
+    if (n && addr + n * size > b.size()) {
+      err = "dataset extends past end of file";
+      return false;
+    }
+    return true;
+  }
   // read a dataset as double or int32 (converted from stored int/float of size 4/8)
   template <class T>
   bool dataset(uint64_t ohdr, std::vector<T>& out, std::vector<uint64_t>& shape) {
@@ -411,6 +475,159 @@ struct H5File {
   }
 };
 }  // namespace
+
+// ------------------------------------------------------------------ minimal HDF5 writer
+// Root-level contiguous datasets (float64 / int32, little endian) in the layout libhdf5 itself produces for
+// such a file (superblock version 0, root group as symbol table: v1 B-tree node + local heap + one symbol-table
+// node, version-1 object headers with dataspace / datatype / fill-value / contiguous-layout messages) -- the
+// byte patterns of the messages are those of the reference's own fixture files (src/tests/physics/tw_test-*.h5).
+// This is what hdf5_create_file + hdf5_write produce for the Bmat cache (thin_wall.F90:2208-2225, oft_io.F90).
+namespace {
+void put(std::vector<uint8_t>& v, const void* p, size_t n) { v.insert(v.end(), (const uint8_t*)p, (const uint8_t*)p + n); }
+template <class T>
+void putv(std::vector<uint8_t>& v, T x) { put(v, &x, sizeof(T)); }
+void pad8(std::vector<uint8_t>& v) { while (v.size() % 8) v.push_back(0); }
+}  // namespace
+
+std::string write_h5_file(const std::string& path, const std::vector<H5Item>& items_in) {
+  constexpr int kLeafK = 4, kNodeK = 16;
+  if (items_in.size() > 2 * kLeafK) return "write_h5_file: at most 8 datasets";
+  std::vector<H5Item> items = items_in;
+  std::sort(items.begin(), items.end(), [](const H5Item& a, const H5Item& b) { return a.name < b.name; });
+  const uint64_t UNDEF = ~0ull;
+  // local heap data: "" at 0, then the names (8-byte aligned), then one free block
+  std::vector<uint8_t> heap(8, 0);
+  std::vector<uint64_t> name_off;
+  for (auto& it : items) {
+    name_off.push_back(heap.size());
+    put(heap, it.name.c_str(), it.name.size() + 1);
+    pad8(heap);
+  }
+  const uint64_t free_off = heap.size();
+  const uint64_t free_size = std::max<uint64_t>(16, 88 > heap.size() ? 88 - heap.size() : 16);
+  putv<uint64_t>(heap, 1);          // H5HL_FREE_NULL: last free block
+  putv<uint64_t>(heap, free_size);
+  heap.resize(free_off + free_size, 0);
+  // fixed layout of the metadata
+  const uint64_t a_root = 96, a_tree = a_root + 16 + 24, tree_size = 8 + 16 + (2 * kNodeK + 1) * 8 + 2 * kNodeK * 8;
+  const uint64_t a_heap = a_tree + tree_size, a_heapdata = a_heap + 32, a_snod = a_heapdata + heap.size();
+  const uint64_t snod_size = 8 + 2 * kLeafK * 40;
+  uint64_t cur = a_snod + snod_size;
+  std::vector<uint64_t> a_ohdr(items.size()), a_data(items.size()), nbytes(items.size());
+  std::vector<std::vector<uint8_t>> ohdr(items.size());
+  for (size_t i = 0; i < items.size(); i++) {  // header sizes first (addresses of the raw data come after all headers)
+    const int rank = (int)items[i].dims.size();
+    const uint64_t hs = (8 + 8 + 16 * rank) + (8 + (items[i].f64 ? 24 : 16)) + (8 + 8) + (8 + 24);
+    a_ohdr[i] = cur;
+    cur += 16 + hs;
+    nbytes[i] = items[i].f64 ? 8 : 4;
+    for (auto d : items[i].dims) nbytes[i] *= d;
+  }
+  for (size_t i = 0; i < items.size(); i++) {
+    a_data[i] = nbytes[i] ? cur : UNDEF;
+    cur += (nbytes[i] + 7) / 8 * 8;
+  }
+  const uint64_t eof = cur;
+  for (size_t i = 0; i < items.size(); i++) {
+    std::vector<uint8_t>& h = ohdr[i];
+    const int rank = (int)items[i].dims.size();
+    std::vector<uint8_t> msgs;
+    // dataspace, version 1, maximum dimensions present (= current)
+    putv<uint16_t>(msgs, 0x0001); putv<uint16_t>(msgs, (uint16_t)(8 + 16 * rank)); putv<uint32_t>(msgs, 0);
+    msgs.push_back(1); msgs.push_back((uint8_t)rank); msgs.push_back(1); msgs.insert(msgs.end(), 5, 0);
+    for (auto d : items[i].dims) putv<uint64_t>(msgs, d);
+    for (auto d : items[i].dims) putv<uint64_t>(msgs, d);
+    // datatype (constant message)
+    if (items[i].f64) {
+      static const uint8_t dt[24] = {0x11, 0x20, 0x3f, 0x00, 8, 0, 0, 0, 0, 0, 0x40, 0, 0x34, 0x0b, 0x00, 0x34, 0xff, 0x03, 0, 0, 0, 0, 0, 0};
+      putv<uint16_t>(msgs, 0x0003); putv<uint16_t>(msgs, 24); putv<uint32_t>(msgs, 1);
+      put(msgs, dt, 24);
+    } else {
+      static const uint8_t dt[16] = {0x10, 0x08, 0x00, 0x00, 4, 0, 0, 0, 0, 0, 0x20, 0, 0, 0, 0, 0};
+      putv<uint16_t>(msgs, 0x0003); putv<uint16_t>(msgs, 16); putv<uint32_t>(msgs, 1);
+      put(msgs, dt, 16);
+    }
+    // fill value, version 2: late allocation, fill if set, default fill value
+    {
+      static const uint8_t fv[8] = {2, 2, 2, 1, 0, 0, 0, 0};
+      putv<uint16_t>(msgs, 0x0005); putv<uint16_t>(msgs, 8); putv<uint32_t>(msgs, 1);
+      put(msgs, fv, 8);
+    }
+    // data layout, version 3, contiguous
+    putv<uint16_t>(msgs, 0x0008); putv<uint16_t>(msgs, 24); putv<uint32_t>(msgs, 0);
+    msgs.push_back(3); msgs.push_back(1);
+    putv<uint64_t>(msgs, a_data[i]); putv<uint64_t>(msgs, nbytes[i]);
+    msgs.insert(msgs.end(), 6, 0);
+    h.push_back(1); h.push_back(0); putv<uint16_t>(h, 4); putv<uint32_t>(h, 1); putv<uint32_t>(h, (uint32_t)msgs.size()); putv<uint32_t>(h, 0);
+    put(h, msgs.data(), msgs.size());
+  }
+  // assemble the metadata block
+  std::vector<uint8_t> md;
+  static const uint8_t sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+  put(md, sig, 8);
+  const uint8_t sb[8] = {0, 0, 0, 0, 0, 8, 8, 0};
+  put(md, sb, 8);
+  putv<uint16_t>(md, kLeafK); putv<uint16_t>(md, kNodeK); putv<uint32_t>(md, 0);
+  putv<uint64_t>(md, 0); putv<uint64_t>(md, UNDEF); putv<uint64_t>(md, eof); putv<uint64_t>(md, UNDEF);
+  putv<uint64_t>(md, 0); putv<uint64_t>(md, a_root); putv<uint32_t>(md, 1); putv<uint32_t>(md, 0);
+  putv<uint64_t>(md, a_tree); putv<uint64_t>(md, a_heap);
+  // root group object header: one symbol-table message
+  md.push_back(1); md.push_back(0); putv<uint16_t>(md, 1); putv<uint32_t>(md, 1); putv<uint32_t>(md, 24); putv<uint32_t>(md, 0);
+  putv<uint16_t>(md, 0x0011); putv<uint16_t>(md, 16); putv<uint32_t>(md, 0);
+  putv<uint64_t>(md, a_tree); putv<uint64_t>(md, a_heap);
+  // B-tree node (group node, leaf level): key 0 = "", child 0 = the symbol-table node, key 1 = the last name
+  put(md, "TREE", 4); md.push_back(0); md.push_back(0); putv<uint16_t>(md, items.empty() ? 0 : 1);
+  putv<uint64_t>(md, UNDEF); putv<uint64_t>(md, UNDEF);
+  putv<uint64_t>(md, 0); putv<uint64_t>(md, a_snod); putv<uint64_t>(md, items.empty() ? 0 : name_off.back());
+  md.resize(a_heap, 0);
+  // local heap
+  put(md, "HEAP", 4); putv<uint32_t>(md, 0);
+  putv<uint64_t>(md, heap.size()); putv<uint64_t>(md, free_off); putv<uint64_t>(md, a_heapdata);
+  put(md, heap.data(), heap.size());
+  // symbol-table node
+  put(md, "SNOD", 4); md.push_back(1); md.push_back(0); putv<uint16_t>(md, (uint16_t)items.size());
+  for (size_t i = 0; i < items.size(); i++) {
+    putv<uint64_t>(md, name_off[i]); putv<uint64_t>(md, a_ohdr[i]); putv<uint32_t>(md, 0); putv<uint32_t>(md, 0);
+    md.insert(md.end(), 16, 0);
+  }
+  md.resize(a_snod + snod_size, 0);
+  for (size_t i = 0; i < items.size(); i++) put(md, ohdr[i].data(), ohdr[i].size());
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) return "cannot create " + path;
+  bool ok = std::fwrite(md.data(), 1, md.size(), f) == md.size();
+  static const uint8_t zeros[8] = {0};
+  for (size_t i = 0; i < items.size() && ok; i++) {
+    if (!nbytes[i]) continue;
+    ok = std::fwrite(items[i].data, 1, nbytes[i], f) == nbytes[i];
+    const size_t padn = (8 - nbytes[i] % 8) % 8;
+    if (ok && padn) ok = std::fwrite(zeros, 1, padn, f) == padn;
+  }
+  ok = (std::fclose(f) == 0) && ok;
+  return ok ? "" : "write error on " + path;
+}
+
+// float64 dataset straight into caller memory (count checked), int32 dataset into a vector
+std::string read_h5_dataset_f64_into(const std::string& path, const std::string& name, double* dst, uint64_t count) {
+  H5File f;
+  if (!f.open(path)) return f.err;
+  uint64_t oh;
+  if (!f.find(name, oh)) return "dataset \"" + name + "\" not found";
+  uint64_t addr = 0, n = 0;
+  int cls = -1, size = 0;
+  if (!f.locate(oh, addr, n, cls, size)) return f.err;
+  if (cls != 1 || size != 8 || n != count) return "dataset \"" + name + "\" has an unexpected type or size";
+  if (n) std::memcpy(dst, f.b.data() + addr, n * 8);
+  return "";
+}
+std::string read_h5_dataset_i32(const std::string& path, const std::string& name, std::vector<int32_t>& out) {
+  H5File f;
+  if (!f.open(path)) return f.err;
+  uint64_t oh;
+  if (!f.find(name, oh)) return "dataset \"" + name + "\" not found";
+  std::vector<uint64_t> shape;
+  if (!f.dataset(oh, out, shape)) return f.err;
+  return "";
+}
 
 std::string read_h5_dataset_f64(const std::string& path, const std::string& name, std::vector<double>& out,
                                 std::vector<uint64_t>& shape) {

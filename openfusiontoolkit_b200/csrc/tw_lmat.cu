@@ -2,23 +2,27 @@
 //
 // Replaces the O(nc^2) OpenMP loop nest of tw_compute_LmatDirect (src/physics/thin_wall.F90:
 // 1008-1126) with an owner-computes tiling.  One persistent CTA per SM pulls output tiles
-// (row patch x column patch) from a cost-sorted queue.  For every pair of 64-cell chunks of the
-// two patches it
-//   A. stages both chunks' SoA geometry records in shared memory (1-D bulk async copies,
-//      mbarrier-tracked) and classifies the 4096 cell pairs: the quadrature order of
-//      thin_wall.F90:1044-1059 is screened in FP32 on locally shifted coordinates with a rigorous
-//      error band and falls back to a bit-exact FP64 evaluation when a threshold is within the band;
-//   B. bins the pairs by rule (counting sort in shared memory, bins padded to warp multiples) so
-//      that every warp executes ONE rule -- no divergence;
-//   C. evaluates T(c1,c2): far pairs (thin_wall.F90:1069-1083) from per-chunk tables of quadrature
-//      points held in shared memory ((x,y,z,|x|^2) in a local frame, d^2 = |xi|^2+|xj|^2-2 xi.xj,
-//      MUFU.RSQ64H seed + third-order correction = 10 FP64-pipe instructions per 1/r), near pairs
-//      (thin_wall.F90:1061-1068) with one half-warp per pair, lanes over the quadrature points of
-//      the analytic potential; work is handed out in warp-sized batches from a shared counter;
-//   D. contracts T onto the vertex/hole DOFs in two stages (cell x column-DOF partial sums in
-//      shared memory, then row-DOF sums) and adds the block into L.
-// Every L entry is owned by exactly one CTA and updated by plain read-modify-writes between
-// barriers: no atomics on the matrix, deterministic summation.
+// (row patch x column patch) from a cost-sorted queue.  One PASS = one pair of 64-cell chunks of the
+// two patches (4096 cell pairs), six block barriers:
+//   0. staging: a chunk is three bulk async copies (cp.async.bulk ... mbarrier::complete_tx) into a
+//      ChunkState slot -- 22 SoA geometry rows, the index record (per-cell min/max DOF, reference DOF ids,
+//      CSR incidences) and this launch's output rows; the next column chunk is prefetched during the pass;
+//   A. classification: the quadrature order of thin_wall.F90:1044-1059 is screened in FP32 on locally
+//      shifted coordinates with a rigorous error band (order 4 from the cells' bounding spheres when they
+//      are far enough apart) and falls back to a bit-exact FP64 evaluation when a threshold is within
+//      the band;
+//   B. binning by rule from per-thread packed histograms + one warp scan (no atomics or votes in the pair
+//      loop); lists are row-major, bins padded to warp multiples, every warp executes ONE rule;
+//   C. evaluation of T(c1,c2) from a dynamic queue of warp-sized batches: far pairs (thin_wall.F90:1069-1083)
+//      from per-chunk tables of quadrature points in shared memory ((x,y,z,|x|^2) in a local frame,
+//      d^2 = |xi|^2+|xj|^2-2 xi.xj, MUFU.RSQ64H seed + third-order correction = 10 FP64-pipe instructions
+//      per 1/r), near pairs (thin_wall.F90:1061-1068) with one half-warp per pair, lanes over the
+//      quadrature points of the analytic potential;
+//   D. contraction onto the vertex/hole DOFs: a warp per column DOF forms the pass's 64 x 64 block of
+//      contributions in shared memory, then a warp per matrix row adds it into L with lanes along the row.
+// Every L entry is owned by exactly one CTA and updated by plain loads and stores between barriers: no
+// atomics on the matrix, deterministic summation.  When the rows of both patches of a tile are in the output
+// block the transposed entries are left to symmetrize_kernel (thin_wall.F90:1146-1151).
 //
 // Role rule (SURVEY hard part 1): for entry (a,b) with a<=b in reference numbering the cell
 // carrying `a` is the analytic side of near pairs.  Role-1 values T(c1 analytic) serve entries
@@ -41,11 +45,8 @@ namespace twk {
 
 using tw::kCH;
 using tw::kGeomRows;
-#ifndef TW_LMAT_NT
-#define TW_LMAT_NT 512
-#endif
-constexpr int NT = TW_LMAT_NT;     // threads per CTA (one persistent CTA per SM; 512 threads x 128 registers)
-constexpr int NTC = 512;           // threads that classify pairs (8 per row cell)
+constexpr int NT = 512;            // threads per CTA (one persistent CTA per SM; 512 threads x 128 registers)
+constexpr int NTC = NT;            // threads that classify pairs (8 per row cell)
 constexpr int NW = NT / 32;
 constexpr int CI = kCH;            // row cells per pass: a pass evaluates one pair of chunks, CI x kCH cell pairs
 constexpr int kGeomL = 22;         // geometry rows the L kernel stages (vertices, area, qbasis, phipot normal)
@@ -99,7 +100,7 @@ static_assert(offsetof(ChunkState, x) % 16 == 0 && offsetof(ChunkState, row) % 1
 struct PassBuf {
   unsigned short list[kListCap];      // pair ids (c1l<<6|c2) sorted by class, bins padded with 0xFFFF
   unsigned char iqmap[CI * kCH];      // iquad | need-role-1 << 5 | need-role-2 << 6
-  int cnt[NCLS], off[NCLS + 1], fill[NCLS];
+  int cnt[NCLS], off[NCLS + 1];
   int qcls[NCLS + 8], qnb[NCLS + 8], qpt[NCLS + 8];  // queue items: class (| 16 = table), batches, table offset
   int gq0[8], gq1[8], gnb[8], ng;     // table groups: item range and batch count
   int qhead, both_count;

@@ -1030,6 +1030,44 @@ void lmat_cache_write(const Model& m, const std::string& path) {
   for (size_t i = 0; i < N; i++) funf_write_record(f, m.Lmat.p + i * N + i, (N - i) * 8);
   std::fclose(f);
 }
+// B-field operator cache: HDF5 file with MODEL_hash i4[4] = {nelems, nc, hash(lc), hash(r)}, Bel_X|Y|Z = Fortran
+// Bel(nelems,np) => C shape [np][nelems], Bdr_X|Y|Z = Fortran Bdr(np,n_icoils) => [n_icoils][np]
+// (thin_wall.F90:2175-2225; oft_io.F90 reverses the dimensions on disk).  Host layout here: Bel[3][np][nelems],
+// Bdr[3][n_icoils][np], i.e. one contiguous slab per dataset.
+bool bmat_cache_read(Model& m, const std::string& path) {
+  FILE* probe = std::fopen(path.c_str(), "rb");
+  if (!probe) return false;
+  std::fclose(probe);
+  std::printf(" Loading B-field operator from file: %s\n", path.c_str());
+  std::vector<int32_t> got;
+  const int32_t want[4] = {m.nelems, m.nc, m.hash_lc(), m.hash_r()};
+  if (!read_h5_dataset_i32(path, "MODEL_hash", got).empty() || got.size() != 4 || std::memcmp(got.data(), want, sizeof want) != 0) return false;
+  const size_t N = (size_t)m.nelems, np = (size_t)m.np, ni = (size_t)m.n_icoils;
+  m.Bel.alloc(3 * np * N, false);
+  m.Bdr.alloc(3 * np * std::max<size_t>(ni, 1), false);
+  if (!m.Bel.p || !m.Bdr.p) return false;
+  const char* comp[3] = {"X", "Y", "Z"};
+  bool ok = true;
+  for (int c = 0; c < 3 && ok; c++) ok = read_h5_dataset_f64_into(path, std::string("Bel_") + comp[c], m.Bel.p + c * np * N, np * N).empty();
+  for (int c = 0; c < 3 && ok; c++) ok = read_h5_dataset_f64_into(path, std::string("Bdr_") + comp[c], m.Bdr.p + c * np * ni, np * ni).empty();
+  if (!ok) {
+    m.Bel.release();
+    m.Bdr.release();
+  }
+  return ok;
+}
+void bmat_cache_write(const Model& m, const std::string& path) {
+  std::printf(" Saving B-field operator to file: %s\n", path.c_str());
+  const uint64_t N = (uint64_t)m.nelems, np = (uint64_t)m.np, ni = (uint64_t)m.n_icoils;
+  const int32_t hash[4] = {m.nelems, m.nc, m.hash_lc(), m.hash_r()};
+  std::vector<H5Item> items;
+  items.push_back({"MODEL_hash", false, {4}, hash});
+  const char* comp[3] = {"X", "Y", "Z"};
+  for (int c = 0; c < 3; c++) items.push_back({std::string("Bel_") + comp[c], true, {np, N}, m.Bel.p + c * np * N});
+  for (int c = 0; c < 3; c++) items.push_back({std::string("Bdr_") + comp[c], true, {ni, np}, m.Bdr.p + c * np * ni});
+  std::string err = write_h5_file(path, items);
+  if (!err.empty()) std::printf("   %s\n", err.c_str());
+}
 bool mutual_cache_read(const Model& m1, const Model& m2, double* M, const std::string& path) {
   FILE* f = std::fopen(path.c_str(), "rb");
   if (!f) return false;

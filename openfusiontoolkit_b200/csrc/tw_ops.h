@@ -36,6 +36,8 @@ std::string gpu_pair_stats(Model& m, int64_t* hist, int64_t* visited);
 // operator caches in the reference's on-disk formats (Fortran unformatted sequential)
 bool lmat_cache_read(Model& m, const std::string& path);
 void lmat_cache_write(const Model& m, const std::string& path);
+bool bmat_cache_read(Model& m, const std::string& path);
+void bmat_cache_write(const Model& m, const std::string& path);
 bool mutual_cache_read(const Model& m1, const Model& m2, double* M, const std::string& path);
 void mutual_cache_write(const Model& m1, const Model& m2, const double* M, const std::string& path);
 bool mcoil_cache_read(Model& m, const std::string& path);

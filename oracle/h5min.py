@@ -107,6 +107,8 @@ class H5:
                     assert body[2] == 1
                     layout = struct.unpack_from('<Q', body, 8)[0]
         n = int(np.prod(shape)) if shape else 1
+        if n == 0:  # zero-size dataset: no storage allocated (address undefined)
+            return np.zeros(shape, dtype='<' + dt)
         a = np.frombuffer(self.b, dtype='<' + dt, count=n, offset=layout)
         return a.reshape(shape) if shape else a
 

@@ -158,3 +158,32 @@ def test_bmat(env, name):
     assert np.abs(Bg_mem - Bo)[far].max() / np.abs(Bo).max() < 1e-9
     Bdg_mem = np.asarray(Bdg).reshape(3, T.n_icoils, T.np)
     assert relerr(Bdg_mem, Bdo) < 1e-13
+
+
+def test_bmat_cache_file(env, tmp_path):
+    """compute_Bmat(cache_file): the HDF5 save file of thin_wall.F90:2208-2225 (MODEL_hash, Bel_X|Y|Z as [np][nelems],
+    Bdr_X|Y|Z as [n_icoils][np]) is written, parses with the oracle-side HDF5 reader, and a second model loads it
+    instead of rebuilding; a model with another mesh ignores it (hash mismatch)."""
+    from oracle import h5min
+    g = G['fr_torus']
+    O, T = make(env, 'torus', g, vcoils=g.get('vcoils'), icoils=g['icoils'])
+    fn = str(tmp_path / 'Bmat.save')
+    Bg, Bdg = T.compute_Bmat(cache_file=fn)
+    Bg = np.array(Bg).reshape(3, T.np, T.nelems)
+    Bdg = np.array(Bdg).reshape(3, T.n_icoils, T.np)
+    h = h5min.H5(fn)
+    t = h.tree()
+    assert sorted(t) == ['Bdr_X', 'Bdr_Y', 'Bdr_Z', 'Bel_X', 'Bel_Y', 'Bel_Z', 'MODEL_hash']
+    mh = h.read(t['MODEL_hash'])
+    assert mh.dtype == np.int32 and mh[0] == T.nelems and mh[1] == T.nc
+    for c, nm in enumerate('XYZ'):
+        assert np.array_equal(h.read(t['Bel_' + nm]), Bg[c])
+        assert np.array_equal(h.read(t['Bdr_' + nm]), Bdg[c])
+    O2, T2 = make(env, 'torus', g, vcoils=g.get('vcoils'), icoils=g['icoils'])
+    B2, Bd2 = T2.compute_Bmat(cache_file=fn)       # loads
+    assert np.array_equal(np.array(B2).reshape(Bg.shape), Bg) and np.array_equal(np.array(Bd2).reshape(Bdg.shape), Bdg)
+    g3 = G['fr_plate']
+    O3, T3 = make(env, 'plate', g3, vcoils=g3.get('vcoils'), icoils=g3['icoils'])
+    B3, _ = T3.compute_Bmat(cache_file=fn)         # other model: hash mismatch => rebuilt (and the file rewritten)
+    assert np.array(B3).size == 3 * T3.np * T3.nelems
+    assert h5min.H5(fn).read(h5min.H5(fn).tree()['MODEL_hash'])[0] == T3.nelems
