@@ -144,6 +144,14 @@ int thincurr_b200_Lmat_shard_sym(void* tw_ptr, int nshards, int shard, double* d
  * the end-to-end path used by bench.py's e2e leg. */
 int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* h_out, int64_t ld,
                                   int64_t* stats);
+/* Dense block of the self-inductance matrix: d_out[i][j] = Lmat(col_ids[j]+1, row_ids[i]+1) (= L(row_ids[i], col_ids[j]),
+ * the matrix is symmetric) for arbitrary subsets of the vertex/hole DOFs (0-based reference ids, no duplicates), into
+ * caller-provided DEVICE memory d_out[nrows][ld >= ncols], asynchronous on `stream`.  Same pair integrals and role rule
+ * as the full build; this is the evaluator a hierarchical (HODLR) compression calls for its dense diagonal and
+ * near-field blocks (tw_compute_Lmatblock, thin_wall_hodlr.F90:136-404).  Work is done per (row patch, column patch)
+ * tile, so thin strips cost as much as the patches they touch. */
+int thincurr_b200_Lmat_block(void* tw_ptr, int nrows, const int* row_ids, int ncols, const int* col_ids, double* d_out,
+                             int64_t ld, void* stream);
 /* Minimal HDF5 writer (no libhdf5 needed): root-level contiguous little-endian datasets, float64 (is_f64[i] != 0) or
  * int32, dims[] = the dimensions of all items concatenated in C order (slowest first); at most 8 items.  This is the
  * container of the reference's Bmat cache (thin_wall.F90:2208-2225: MODEL_hash, Bel_X|Y|Z, Bdr_X|Y|Z), which

@@ -89,6 +89,18 @@ INTERFACE
     TYPE(c_ptr), VALUE :: stats   !< c_null_ptr or INTEGER(c_int64_t) :: stats(8)
     INTEGER(c_int) :: ierr
   END FUNCTION thincurr_b200_Lmat_shard_sym
+  !> Dense block d_out(j,i) = Lmat(col_ids(j)+1,row_ids(i)+1) into DEVICE memory d_out(ld,nrows), ld >= ncols
+  FUNCTION thincurr_b200_Lmat_block(tw_ptr,nrows,row_ids,ncols,col_ids,d_out,ld,stream) &
+    BIND(C,NAME="thincurr_b200_Lmat_block") RESULT(ierr)
+    IMPORT :: c_int, c_int64_t, c_ptr
+    TYPE(c_ptr), VALUE :: tw_ptr
+    INTEGER(c_int), VALUE, INTENT(in) :: nrows,ncols
+    INTEGER(c_int), INTENT(in) :: row_ids(*),col_ids(*)
+    TYPE(c_ptr), VALUE :: d_out   !< device pointer
+    INTEGER(c_int64_t), VALUE, INTENT(in) :: ld
+    TYPE(c_ptr), VALUE :: stream  !< cudaStream_t or c_null_ptr
+    INTEGER(c_int) :: ierr
+  END FUNCTION thincurr_b200_Lmat_block
   !> Rows of one shard into host memory h_out(ld,nrows) (row r = Lmat(:,row_ids(r)+1))
   FUNCTION thincurr_b200_Lmat_shard_host(tw_ptr,nshards,shard,h_out,ld,stats) &
     BIND(C,NAME="thincurr_b200_Lmat_shard_host") RESULT(ierr)

@@ -12,7 +12,7 @@ from ctypes import c_bool, c_double, c_int, c_void_p
 import numpy
 import scipy.sparse
 
-from .._interface import (b200_Bel_shard, b200_Lmat_shard, b200_Lmat_shard_host, b200_Lmat_shard_sym, b200_shard_rows_sym, b200_destroy, b200_get_model,
+from .._interface import (b200_Lmat_block, b200_Bel_shard, b200_Lmat_shard, b200_Lmat_shard_host, b200_Lmat_shard_sym, b200_shard_rows_sym, b200_destroy, b200_get_model,
                           b200_hashes, b200_last_error, b200_msensor, b200_pair_stats, b200_plan, b200_set_coils,
                           b200_set_sensors, b200_setup, b200_shard_rows, c_double_ptr, c_int_ptr, mu0, oftpy_load_xml,
                           thincurr_Bmat, thincurr_cross_coupling, thincurr_get_eta, thincurr_get_sensor_name,
@@ -367,6 +367,14 @@ class ThinCurr():
         _check(b200_Lmat_shard_host(self.tw_obj, nshards, shard, out.ctypes.data_as(c_void_p), out.shape[1],
                                     st.ctypes.data_as(c_void_p) if stats else None))
         return st
+
+    def compute_Lmat_block(self, row_ids, col_ids, out, stream=None):
+        '''! Dense block `out[i, j] = L[row_ids[i], col_ids[j]]` (vertex/hole DOFs, 0-based reference ids) into the CUDA
+        tensor `out[len(row_ids), ld >= len(col_ids)]` (float64).  Asynchronous on `stream`.'''
+        rows = numpy.ascontiguousarray(row_ids, dtype=numpy.int32)
+        cols = numpy.ascontiguousarray(col_ids, dtype=numpy.int32)
+        sptr = c_void_p(stream) if stream else c_void_p()
+        _check(b200_Lmat_block(self.tw_obj, len(rows), rows, len(cols), cols, c_void_p(out.data_ptr()), out.stride(0), sptr))
 
     def compute_Bel_shard(self, nshards, shard, out, stream=None):
         '''! Rows of the B operator into the CUDA tensor `out[3, np, nrows]`.'''

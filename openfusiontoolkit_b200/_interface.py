@@ -88,6 +88,8 @@ b200_Lmat_shard_sym = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard_sym,
     [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p], c_int)
 b200_Lmat_shard_host = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard_host,
     [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p], c_int)
+b200_Lmat_block = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_block,
+    [c_void_p, c_int, ctypes_numpy_array(int32, 1), c_int, ctypes_numpy_array(int32, 1), c_void_p, c_int64, c_void_p], c_int)
 b200_h5_write = ctypes_subroutine(oftpy_lib.thincurr_b200_h5_write,
     [c_char_p, c_int, ctypes.POINTER(c_char_p), ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int64), ctypes.POINTER(c_void_p)], c_int)
 b200_Bel_shard = ctypes_subroutine(oftpy_lib.thincurr_b200_Bel_shard, [c_void_p, c_int, c_int, c_void_p, c_void_p], c_int)

@@ -691,6 +691,57 @@ int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* 
   return 0;
 }
 
+int thincurr_b200_Lmat_block(void* tw_ptr, int nrows, const int* row_ids, int ncols, const int* col_ids, double* d_out, int64_t ld,
+                             void* stream_) {
+  // dense block L(row_ids, col_ids) of the self-inductance matrix (the evaluator behind tw_compute_Lmatblock,
+  // thin_wall_hodlr.F90:136-404: same pair integrals and role rule restricted to a row / column DOF subset)
+  Model& m = *(Model*)tw_ptr;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess) return fail("No CUDA device available (there is no CPU fallback)");
+  std::shared_ptr<DeviceState> ds;
+  std::string err = ensure_device(m, device, ds);
+  if (!err.empty()) return fail(err);
+  const PatchSet& ps = m.plan->ps;
+  if (ld < ncols) return fail("thincurr_b200_Lmat_block: ld < ncols");
+  std::vector<int> internal(ps.ndof, -1), patch_of(ps.ndof, 0);
+  for (int i = 0; i < ps.ndof; i++) internal[ps.dof_orig[i]] = i;
+  for (int p = 0; p < ps.npatch; p++)
+    for (int i = ps.patch_dof_ptr[p]; i < ps.patch_dof_ptr[p + 1]; i++) patch_of[i] = p;
+  std::vector<int> row_out(ps.ndof, -1), col_map(ps.ndof, -1);
+  std::vector<char> prow(ps.npatch, 0), pcol(ps.npatch, 0);
+  for (int r = 0; r < nrows; r++) {
+    if (row_ids[r] < 0 || row_ids[r] >= ps.ndof) return fail("thincurr_b200_Lmat_block: row id out of range (vertex and hole DOFs only)");
+    const int i = internal[row_ids[r]];
+    if (row_out[i] >= 0) return fail("thincurr_b200_Lmat_block: duplicate row id");
+    row_out[i] = r;
+    prow[patch_of[i]] = 1;
+  }
+  for (int c = 0; c < ncols; c++) {
+    if (col_ids[c] < 0 || col_ids[c] >= ps.ndof) return fail("thincurr_b200_Lmat_block: column id out of range (vertex and hole DOFs only)");
+    if (col_map[col_ids[c]] >= 0) return fail("thincurr_b200_Lmat_block: duplicate column id");
+    col_map[col_ids[c]] = c;
+    pcol[patch_of[internal[col_ids[c]]]] = 1;
+  }
+  // every (row patch, column patch) pair as an ordinary tile: all entries, both roles where needed, no mirror
+  std::vector<Tile> tiles;
+  for (int pa = 0; pa < ps.npatch; pa++)
+    if (prow[pa])
+      for (int pb = 0; pb < ps.npatch; pb++)
+        if (pcol[pb]) tiles.push_back(Tile{pa, pb, 4, (float)ps.patch_ncell[pa] * ps.patch_ncell[pb]});
+  std::stable_sort(tiles.begin(), tiles.end(), [](const Tile& a, const Tile& b) { return a.cost > b.cost; });
+  if (cudaMemset2DAsync(d_out, (size_t)ld * 8, 0, (size_t)ncols * 8, (size_t)nrows, stream) != cudaSuccess)
+    return fail("cudaMemset2DAsync failed on the output block");
+  int* d_col_map = nullptr;
+  if (cudaMallocAsync((void**)&d_col_map, (size_t)ps.ndof * sizeof(int), stream) != cudaSuccess) return fail("Device allocation failed");
+  cudaMemcpyAsync(d_col_map, col_map.data(), (size_t)ps.ndof * sizeof(int), cudaMemcpyHostToDevice, stream);
+  cudaStreamSynchronize(stream);  // col_map is a pageable host vector
+  err = gpu_lmat_tiles(ds->ps, ds->ps, tiles, row_out, true, d_out, ld, stream, nullptr, d_col_map, false);
+  cudaFreeAsync(d_col_map, stream);
+  if (!err.empty()) return fail(err);
+  return 0;
+}
+
 int thincurr_b200_h5_write(const char* path, int nitems, const char* const* names, const int* is_f64, const int* ranks,
                            const int64_t* dims, const void* const* data) {
   std::vector<H5Item> items;

@@ -36,11 +36,13 @@ std::string gpu_init_constants();
 void note_launch();
 long long launch_count();
 
+// d_col_map (block builds): reference column DOF id -> output column or -1; symmetrize: copy the transposed entries
+// of the owned diagonal block afterwards (self builds whose tiles defer them, Tile.flags bit 3).
 // Run the tile kernel: out[row_out[internal row]][ld] += (1/4pi) sum ... ; out must be zeroed.
 // h_stats (optional, 8 x u64) forces a stream sync: far pairs, near T evals, 1/r evals, phipot evals.
 std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, const std::vector<Tile>& tiles,
                            const std::vector<int>& row_out, bool self, double* d_out, long long ld, cudaStream_t stream,
-                           unsigned long long* h_stats);
+                           unsigned long long* h_stats, const int* d_col_map = nullptr, bool symmetrize = true);
 
 // FP64 DFMA peak microbenchmark (TFLOP/s)
 double gpu_dfma_peak(int device, double* sm_clock_mhz);

@@ -71,6 +71,7 @@ struct LmatArgs {
   const int *patch_chunk_ptrA, *patch_chunk_ptrB;
   const tw::ChunkAux *auxA, *auxB;    // per-chunk index records
   const int *chunk_row;               // [chunk of A][kMaxChunkDof] output row of each local DOF or -1 (this launch)
+  const int *col_map;                 // block builds: reference column DOF id -> output column or -1 (nullptr: identity)
   const tw::Tile* tiles;
   int ntiles;
   int* tile_counter;
@@ -798,7 +799,8 @@ struct DrainSel {
       if ((diag && !role1) || (role_sel == 1 && !role1) || (role_sel == 2 && role1)) return false;
     }
     const int ra = I.row[ia];
-    if (ra >= 0) pa = A->out + (long long)ra * A->ld + ob;
+    const int oc = A->col_map ? A->col_map[ob] : ob;
+    if (ra >= 0 && oc >= 0) pa = A->out + (long long)ra * A->ld + oc;
     if (A->self && mirror && oa != ob) {
       const int rb = J.row[ib];
       if (rb >= 0) pm = A->out + (long long)rb * A->ld + oa;
@@ -923,9 +925,11 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
   // owned by this CTA: plain loads and stores, no atomics.
   const int nbJ = min(ndJ, lim), naI = min(ndI, lim);
   {
-    int ob[2];
+    int ob[2], oc[2];  // reference id (role rule) and output column of this lane's column DOFs
     ob[0] = lane < nbJ ? J.x.orig[lane] : 0;
     ob[1] = lane + 32 < nbJ ? J.x.orig[lane + 32] : 0;
+    oc[0] = A.col_map ? (lane < nbJ ? A.col_map[ob[0]] : -1) : ob[0];
+    oc[1] = A.col_map ? (lane + 32 < nbJ ? A.col_map[ob[1]] : -1) : ob[1];
     constexpr int RW = kCH / NW;  // rows per warp
     double old[RW][2];
     unsigned use = 0;
@@ -942,14 +946,14 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
 #pragma unroll
       for (int hb = 0; hb < 2; hb++) {
         old[q][hb] = 0.0;
-        bool ok = rowp != nullptr && lane + 32 * hb < nbJ;
+        bool ok = rowp != nullptr && lane + 32 * hb < nbJ && oc[hb] >= 0;
         if (ok && A.self) {
           const bool role1 = oa <= ob[hb];
           if ((sel.diag && !role1) || (role_sel == 1 && !role1) || (role_sel == 2 && role1)) ok = false;
         }
         if (ok) {
           use |= 1u << (2 * q + hb);
-          old[q][hb] = __ldcg(rowp + ob[hb]);
+          old[q][hb] = __ldcg(rowp + oc[hb]);
         }
       }
     }
@@ -961,7 +965,7 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
       double* rowp = A.out + (long long)(ra >= 0 ? ra : 0) * A.ld;
 #pragma unroll
       for (int hb = 0; hb < 2; hb++)
-        if ((use >> (2 * q + hb)) & 1u) __stcg(rowp + ob[hb], fma(E[ia * TS + lane + 32 * hb], A.scale, old[q][hb]));
+        if ((use >> (2 * q + hb)) & 1u) __stcg(rowp + oc[hb], fma(E[ia * TS + lane + 32 * hb], A.scale, old[q][hb]));
     }
   }
   if (sel.mirror) {  // transposed entries (rows of the column patch are in the output block, rows of this patch are not)
@@ -1285,7 +1289,7 @@ void DevicePatchSet::release() {
 
 std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, const std::vector<Tile>& tiles,
                            const std::vector<int>& row_out, bool self, double* d_out, long long ld, cudaStream_t stream,
-                           unsigned long long* h_stats) {
+                           unsigned long long* h_stats, const int* d_col_map, bool symmetrize) {
   std::string e = gpu_init_constants();
   if (!e.empty()) return e;
   if (tiles.empty()) return "";
@@ -1313,6 +1317,7 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   a.patch_chunk_ptrA = A.patch_chunk_ptr; a.patch_chunk_ptrB = B.patch_chunk_ptr;
   a.auxA = A.aux; a.auxB = B.aux;
   a.chunk_row = d_chunk_row;
+  a.col_map = d_col_map;
   a.tiles = d_tiles;
   a.ntiles = (int)tiles.size();
   a.tile_counter = d_counter;
@@ -1331,7 +1336,7 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   twk::lmat_tile_kernel<<<grid, twk::NT, sizeof(twk::Smem), stream>>>(a);
   CK(cudaGetLastError());
   note_launch();
-  if (self) {
+  if (self && symmetrize) {
     // owned internal DOFs form one contiguous range (rows are numbered along it)
     int i0 = -1, i1 = -1;
     for (int i = 0; i < (int)row_out.size(); i++)
