@@ -485,6 +485,12 @@ __device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const 
     const double X = sqrt(hx * hx + hy * hy + hz * hz) + fmax(I.rad, J.rad);
     delta = (float)(X * 1.21e-7);  // two operands, each rounded to FP32 (2^-24 relative), 1% slack
   }
+  // the order-4 prefilter pays only where most pairs pass: chunks at least ~25 cell sizes apart (block-uniform)
+  bool far_pass;
+  {
+    const double hx = I.cx - J.cx, hy = I.cy - J.cy, hz = I.cz - J.cz;
+    far_pass = sqrt(hx * hx + hy * hy + hz * hz) - I.rad - J.rad > 25.0 * (double)(S.u.w.cenI[0].w + S.u.w.cenJ[0].w);
+  }
   // ---------------- classification --------------------------------------------------------------------  // @region A_classify
   // a thread owns one row cell c1 and the kCH/TPR columns c2 = NIT * (t % TPR) + m: the pairs of a thread,
   // and of the TPR threads of a row, are consecutive in a bin, so a batch of 32 pairs of the evaluation
@@ -514,16 +520,33 @@ __device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const 
           n1 = true;
         }
         if (n1 || n2) {
-          // order-4 prefilter: with D the centroid distance and R the sum of the cells' vertex radii,
-          // dl_min >= D-R, dl_max <= D+R (the floor sqrt(2 area) <= 1.62 R < D-R), so dl_min/dl_max > 0.975 > c_thr[0]
-          // as soon as D > 79 R (80 used: FP32 slack)
-          const float4 cj = S.u.w.cenJ[c2];
-          const float ddx = ci.x - cj.x, ddy = ci.y - cj.y, ddz = ci.z - cj.z, rr = ci.w + cj.w + 4.0f * delta;
-          int iq = 4;
-          if (!(fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) > 6400.0f * rr * rr)) {
-            float pj_[9];
+          float pj_[9];
 #pragma unroll
-            for (int k = 0; k < 9; k++) pj_[k] = S.u.w.vfJ[k * kCH + c2];
+          for (int k = 0; k < 9; k++) pj_[k] = S.u.w.vfJ[k * kCH + c2];
+          int iq = -2;
+          if (far_pass) {
+            // order-4 prefilter.  u = unit vector between the centroids, a_k / b_k = projections of the vertices on u,
+            // R = sum of the cells' vertex radii (>= the part of any vertex difference perpendicular to u):
+            //   dl_min >= Lb = min b - max a,   dl_max <= Ub = (max b - min a) + R^2 / (2 Lb)
+            // (the floor sqrt(2 area) <= 1.62 R is below Ub once D > 10 R), so Lb/Ub > 0.9752 > c_thr[0] => iquad = 4.
+            const float4 cj = S.u.w.cenJ[c2];
+            float ux = cj.x - ci.x, uy = cj.y - ci.y, uz = cj.z - ci.z;
+            const float D2 = fmaf(uz, uz, fmaf(uy, uy, ux * ux)), rr = ci.w + cj.w + 4.0f * delta;
+            if (D2 > 100.0f * rr * rr) {
+              const float rD = rsqrtf(D2);
+              ux *= rD;
+              uy *= rD;
+              uz *= rD;
+              const float a0 = fmaf(pi_[2], uz, fmaf(pi_[1], uy, pi_[0] * ux)), a1 = fmaf(pi_[5], uz, fmaf(pi_[4], uy, pi_[3] * ux)),
+                          a2 = fmaf(pi_[8], uz, fmaf(pi_[7], uy, pi_[6] * ux));
+              const float b0 = fmaf(pj_[2], uz, fmaf(pj_[1], uy, pj_[0] * ux)), b1 = fmaf(pj_[5], uz, fmaf(pj_[4], uy, pj_[3] * ux)),
+                          b2 = fmaf(pj_[8], uz, fmaf(pj_[7], uy, pj_[6] * ux));
+              const float lb = fminf(b0, fminf(b1, b2)) - fmaxf(a0, fmaxf(a1, a2)) - 8.0f * delta;
+              const float ub = fmaxf(b0, fmaxf(b1, b2)) - fminf(a0, fminf(a1, a2)) + 8.0f * delta;
+              if (lb > 0.9752f * fmaf(0.5f * rr, __fdividef(rr, lb), ub)) iq = 4;
+            }
+          }
+          if (iq < 0) {
             iq = iquad_screen(pi_, pj_, fmaxf(fli, S.u.w.flJ[c2]), delta);
             if (iq < 0) iq = iquad_exact_cells(I.g, c1, J.g, c2);
           }
