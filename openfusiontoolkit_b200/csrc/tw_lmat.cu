@@ -606,62 +606,70 @@ __device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const 
       for (int i = n; i < padded; i++) pb.list[o + i] = 0xFFFFu;  // padding of the last batch
     }
   }
-  // the work queue (one thread, working from registers: the counts are loaded first, all loops are unrolled).
-  // Items: near classes (largest rules first), far bins too small for a table (evaluated from the vertices),
-  // then the table rules by decreasing size.  Table rules are packed into groups whose point tables fit the
-  // shared-memory pool together; a group is one barrier interval.
-  if (tid == NT - 1) {
-    int n_[NCLS];
-#pragma unroll
-    for (int c = 0; c < NCLS; c++) n_[c] = pb.cnt[c];
-    int nb = 0, nq = 0, ng = 0, pts = 0;
-    unsigned long long fp = 0, ev = 0;
-    pb.gq0[0] = 0;
-#pragma unroll
-    for (int c = NCLS - 1; c >= 0; c--) {
-      const int n = n_[c];
-      const bool near_c = c >= 7;
-      const bool c0 = near_c || c > kTabClsMax || n < kTabMin;  // evaluated analytically / from the vertices
-      if (n > 0 && c0) {
-        const int nbat = near_c ? (n + 1) / 2 : (n + 31) / 32;
-        pb.qcls[nq] = c;
-        pb.qnb[nq] = nbat;
-        nb += nbat;
-        nq++;
-      }
-      if (!near_c) {
-        constexpr int np2[7] = {36, 49, 144, 225, 256, 361, 625};
-        fp += n;
-        ev += (unsigned long long)(n * np2[c < 7 ? c : 0]);
-      }
+  // the work queue, built by the lanes of the last warp (lane c = class c; the grouping of the table rules is computed
+  // redundantly by every lane from shuffled counts).  Items: near classes (largest rules first), far bins too small
+  // for a table (evaluated from the vertices), then the table rules by decreasing size.  Table rules are packed into
+  // groups whose point tables fit the shared-memory pool together; a group is one barrier interval.
+  if (warp == NW - 1) {
+    const int n = lane < NCLS ? pb.cnt[lane] : 0;
+    const bool near_c = lane >= 7;
+    const bool is_tab = lane <= kTabClsMax && n >= kTabMin;
+    const bool is_c0 = lane < NCLS && n > 0 && !is_tab;
+    const int nbat = near_c ? (n + 1) / 2 : (n + 31) / 32;
+    const unsigned m_c0 = __ballot_sync(0xffffffffu, is_c0), m_tab = __ballot_sync(0xffffffffu, is_tab);
+    const int nq0 = __popc(m_c0);
+    if (is_c0) {  // classes in descending order
+      const int q = __popc(m_c0 >> (lane + 1));
+      pb.qcls[q] = lane;
+      pb.qnb[q] = nbat;
     }
+    int nb0 = is_c0 ? nbat : 0;  // batches of the vertex / analytic items: all in group 0
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nb0 += __shfl_xor_sync(0xffffffffu, nb0, o);
+    // table rules, descending; every lane replays the packing
+    int nq = nq0, ng = 0, pts = 0, nb = nb0;
+    int my_q = -1, my_pt = 0;
+    int gq0_ = 0;  // first item of the open group
 #pragma unroll
     for (int c = kTabClsMax; c >= 0; c--) {
-      const int n = n_[c];
-      if (n < kTabMin) continue;
+      const int nbc = __shfl_sync(0xffffffffu, nbat, c);
+      if (!((m_tab >> c) & 1u)) continue;
       constexpr int npc[7] = {6, 7, 12, 15, 16, 19, 25};
-      const int np = npc[c];
-      if (pts + np > kTabPts) {  // close the group
-        pb.gq1[ng] = nq;
-        pb.gnb[ng] = nb;
+      if (pts + npc[c] > kTabPts) {  // close the group
+        if (lane == 0) {
+          pb.gq0[ng] = gq0_;
+          pb.gq1[ng] = nq;
+          pb.gnb[ng] = nb;
+        }
         ng++;
-        pb.gq0[ng] = nq;
+        gq0_ = nq;
         nb = 0;
         pts = 0;
       }
-      const int nbat = (n + 31) / 32;
-      pb.qcls[nq] = c | 16;  // bit 4: evaluate from the tables
-      pb.qnb[nq] = nbat;
-      pb.qpt[nq] = pts;
-      nb += nbat;
-      pts += np;
+      if (lane == c) {
+        my_q = nq;
+        my_pt = pts;
+      }
+      nb += nbc;
+      pts += npc[c];
       nq++;
     }
-    pb.gq1[ng] = nq;
-    pb.gnb[ng] = nb;
-    pb.ng = ng + 1;
-    st_far += fp;
-    st_eval += ev;
+    if (lane == 0) {
+      pb.gq0[ng] = gq0_;
+      pb.gq1[ng] = nq;
+      pb.gnb[ng] = nb;
+      pb.ng = ng + 1;
+    }
+    if (my_q >= 0) {
+      pb.qcls[my_q] = lane | 16;  // bit 4: evaluate from the tables
+      pb.qnb[my_q] = nbat;
+      pb.qpt[my_q] = my_pt;
+    }
+    if (lane < 7) {  // statistics: far pairs and 1/r evaluations of this pass
+      constexpr int np2[7] = {36, 49, 144, 225, 256, 361, 625};
+      st_far += n;
+      st_eval += (unsigned long long)n * np2[lane];
+    }
   }
   // ---------------- scatter the pair ids into the bins ------------------------------------------------------  // @region B_scatter
   unsigned long long used = 0;  // 4 bits per class: pairs of this thread already placed
@@ -868,7 +876,9 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
   for (int ib = warp; ib < ndJ; ib += NW) {
     // stage 1
     double ux0 = 0.0, uy0 = 0.0, uz0 = 0.0, ux1 = 0.0, uy1 = 0.0, uz1 = 0.0;
-    for (int i2 = J.x.iptr[ib]; i2 < J.x.iptr[ib + 1]; i2++) {
+    const int i2e = J.x.iptr[ib + 1];
+#pragma unroll 4
+    for (int i2 = J.x.iptr[ib]; i2 < i2e; i2++) {
       const unsigned w2 = J.x.inc[i2];
       const int c2 = w2 & 63, k2 = (w2 >> 6) & 3;
       double t0 = T[lane * TS + c2], t1 = T[(lane + 32) * TS + c2];
