@@ -5,15 +5,19 @@ One "step" = one complete build of this rank's row block of L for a synthetic to
 mesh (torus with rectangular ports, jittered vertices; openfusiontoolkit_b200.ThinCurr.meshing).
 N=1 builds the whole matrix of a ~20k-vertex vessel (BASELINE.json configs[1]); at N>1 the mesh
 grows so that every GPU keeps the N=1 pair count (weak scaling), rows are sharded over the ranks
-and no data-path collective runs during assembly.
+(symmetric partition: every rank builds the upper trapezoid of its row block, so no pair integral is
+evaluated on two devices), no traffic during assembly, and the transposed blocks are exchanged once
+afterwards (one NCCL all-to-all, inside the timed step).
 
   value  : whole-job pair-integrals/s with the model resident in HBM, rows left in HBM
            (pairs = ordered triangle pairs the reference loop nest visits, thin_wall.F90:1028-1035)
   e2e    : same metric through the host-buffer C-ABI call (thincurr_b200_Lmat_shard_host): host mesh
            -> plan upload -> build -> rows copied to pinned host memory, all inside the timed region
   roofline: FP64 pipe.  achieved = algorithmic flops of the reference loop nest (SURVEY.md 8d flop
-           model x the measured order histogram) / CUDA-event time of the tile kernel; peak = DFMA
-           micro-benchmark measured in this run (MEASURED_PEAKS.json holds no FP64 figure)
+           model x the measured order histogram) / duration of the tile kernel (device globaltimer, first
+           CTA start -> last CTA end, measured live); peak = DFMA micro-benchmark measured in this run
+           (MEASURED_PEAKS.json holds no FP64 figure); traffic = DRAM bytes of the kernel from the
+           committed ncu --set full capture (profiles/r01_ncu_traffic.json)
   cpu_baseline: the oracle's C/OpenMP restatement of the reference loop (reference flags -O2, same
            schedule) on the host cores, on a bounded row sample of the same mesh
 
