@@ -263,7 +263,9 @@ void thincurr_setup(const char* mesh_file, int np, const double* r_loc, int nc, 
 }
 
 // full self-inductance matrix into host memory dst[nelems][nelems] (reference layout), rows sharded
-// over all visible devices, each shard copied straight to its place
+// over all visible devices, each shard copied straight to its place.  With several devices that can read each other's
+// memory the shards are the symmetric ones (upper trapezoid per device, no pair integral evaluated twice) and every
+// device fetches the transposed blocks of the earlier shards over NVLink before its rows go to the host.
 static std::string lmat_full_host(Model& m, double* dst) {
   const size_t N = (size_t)m.nelems;
   int ndev = visible_devices();
@@ -271,22 +273,50 @@ static std::string lmat_full_host(Model& m, double* dst) {
   std::string err = ensure_plan(m);
   if (!err.empty()) return err;
   ndev = std::min(ndev, std::max(1, m.plan->ps.npatch));
+  bool sym = ndev > 1 && m.n_vcoils == 0 && !std::getenv("THINCURR_B200_FULL_ROWS");
+  for (int g = 1; g < ndev && sym; g++)
+    for (int s = 0; s < g && sym; s++) {
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, g, s) != cudaSuccess || !can) sym = false;
+    }
   struct Dev {
     double* d = nullptr;
     cudaStream_t s = nullptr;
+    cudaEvent_t built = nullptr;
     std::vector<int> rows;
+    int i0 = 0, i1 = 0;  // internal DOF range of the rows
+    std::shared_ptr<DeviceState> ds;
   };
   std::vector<Dev> devs(ndev);
+  const PatchSet& ps = m.plan->ps;
   for (int g = 0; g < ndev && err.empty(); g++) {
     cudaSetDevice(g);
     int p0, p1;
-    shard_rows(m, ndev, g, p0, p1, devs[g].rows);
+    shard_rows(m, ndev, g, p0, p1, devs[g].rows, sym);
+    devs[g].i0 = ps.patch_dof_ptr[p0];
+    devs[g].i1 = ps.patch_dof_ptr[p1];
     if (devs[g].rows.empty()) continue;
     if (cudaStreamCreate(&devs[g].s) != cudaSuccess || cudaMalloc((void**)&devs[g].d, devs[g].rows.size() * N * 8) != cudaSuccess) {
       err = std::string("Device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
       break;
     }
-    err = lmat_shard_device(m, ndev, g, devs[g].d, (long long)N, devs[g].s, nullptr);
+    err = lmat_shard_device(m, ndev, g, devs[g].d, (long long)N, devs[g].s, nullptr, sym);
+    if (sym && err.empty()) {
+      err = ensure_device(m, g, devs[g].ds);
+      cudaEventCreateWithFlags(&devs[g].built, cudaEventDisableTiming);
+      cudaEventRecord(devs[g].built, devs[g].s);
+      for (int s = 0; s < g && err.empty(); s++) {  // transposed blocks of the earlier shards
+        if (!devs[s].d) continue;
+        cudaError_t pe = cudaDeviceEnablePeerAccess(s, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
+          err = std::string("cudaDeviceEnablePeerAccess failed: ") + cudaGetErrorString(pe);
+          break;
+        }
+        cudaGetLastError();
+        cudaStreamWaitEvent(devs[g].s, devs[s].built, 0);
+        err = gpu_symmetrize_cross(devs[g].ds->ps, devs[g].i0, devs[g].i1, devs[s].i0, devs[s].i1, devs[g].d, devs[s].d, (long long)N, devs[g].s);
+      }
+    }
     // rows go straight to their place in the reference layout Lmat(:,row)
     for (size_t r = 0; r < devs[g].rows.size() && err.empty();) {
       size_t r1 = r + 1;
@@ -302,8 +332,12 @@ static std::string lmat_full_host(Model& m, double* dst) {
     if (devs[g].s) {
       cudaError_t ce = cudaStreamSynchronize(devs[g].s);
       if (ce != cudaSuccess && err.empty()) err = std::string("Kernel execution failed: ") + cudaGetErrorString(ce);
-      cudaStreamDestroy(devs[g].s);
     }
+  }
+  for (int g = 0; g < ndev; g++) {  // (all devices are done reading each other's blocks)
+    cudaSetDevice(g);
+    if (devs[g].s) cudaStreamDestroy(devs[g].s);
+    if (devs[g].built) cudaEventDestroy(devs[g].built);
     if (devs[g].d) cudaFree(devs[g].d);
   }
   cudaSetDevice(0);

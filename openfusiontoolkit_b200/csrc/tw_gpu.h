@@ -44,6 +44,11 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
                            const std::vector<int>& row_out, bool self, double* d_out, long long ld, cudaStream_t stream,
                            unsigned long long* h_stats, const int* d_col_map = nullptr, bool symmetrize = true);
 
+// dst[i-i0][orig(j)] = src[j-j0][orig(i)] for internal DOFs i in [i0,i1), j in [j0,j1): the transposed block of an earlier
+// shard (src may be peer memory of another device); A = patch set mirror on the device that runs the kernel
+std::string gpu_symmetrize_cross(const DevicePatchSet& A, int i0, int i1, int j0, int j1, double* dst, const double* src, long long ld,
+                                 cudaStream_t stream);
+
 // FP64 DFMA peak microbenchmark (TFLOP/s)
 double gpu_dfma_peak(int device, double* sm_clock_mhz);
 

@@ -1168,6 +1168,29 @@ __global__ void symmetrize_kernel(int i0, int i1, const int* __restrict__ dof_or
   }
 }
 
+// Transposed copy between the row blocks of two shards (possibly on two devices with peer access): for internal DOFs
+// i in [i0,i1) (rows of dst, row index i-i0) and j in [j0,j1) (rows of src, row index j-j0, an earlier shard that
+// computed every [j][orig(i)]): dst[i][orig(j)] = src[j][orig(i)]  (thin_wall.F90:1146-1151 across shards).
+__global__ void symmetrize_cross_kernel(int i0, int i1, int j0, int j1, const int* __restrict__ dof_orig, double* __restrict__ dst,
+                                        const double* __restrict__ src, long long ld) {
+  __shared__ double tile[32][33];
+  __shared__ int oi_s[32], oj_s[32];
+  const int ib = i0 + 32 * blockIdx.x, jb = j0 + 32 * blockIdx.y;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  if (ty == 0) oi_s[tx] = ib + tx < i1 ? dof_orig[ib + tx] : -1;
+  else if (ty == 1) oj_s[tx] = jb + tx < j1 ? dof_orig[jb + tx] : -1;
+  __syncthreads();
+  for (int jj = ty; jj < 32; jj += 8) {  // read src[j][orig(i)], lanes over i
+    const int j = jb + jj;
+    if (j < j1 && oi_s[tx] >= 0) tile[jj][tx] = __ldcg(src + (long long)(j - j0) * ld + oi_s[tx]);
+  }
+  __syncthreads();
+  for (int ii = ty; ii < 32; ii += 8) {  // write dst[i][orig(j)], lanes over j
+    const int i = ib + ii;
+    if (i < i1 && oj_s[tx] >= 0) dst[(long long)(i - i0) * ld + oj_s[tx]] = tile[tx][ii];
+  }
+}
+
 // output row of every local DOF of every chunk for this launch (row_out: internal DOF -> row or -1)
 __global__ void chunk_rows_kernel(int nchunk, const tw::ChunkMeta* __restrict__ chunks, const int* __restrict__ chunk_dof,
                                   const int* __restrict__ row_out, int* __restrict__ chunk_row) {
@@ -1318,6 +1341,15 @@ void DevicePatchSet::release() {
   geom = nullptr;
   dmin = dmax = chunk_dof = inc_ptr = patch_chunk_ptr = dof_orig = nullptr;
   inc = nullptr;
+}
+
+std::string gpu_symmetrize_cross(const DevicePatchSet& A, int i0, int i1, int j0, int j1, double* dst, const double* src, long long ld,
+                                 cudaStream_t stream) {
+  if (i1 <= i0 || j1 <= j0) return "";
+  twk::symmetrize_cross_kernel<<<dim3((i1 - i0 + 31) / 32, (j1 - j0 + 31) / 32), dim3(32, 8), 0, stream>>>(i0, i1, j0, j1, A.dof_orig, dst, src, ld);
+  CK(cudaGetLastError());
+  note_launch();
+  return "";
 }
 
 std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, const std::vector<Tile>& tiles,
