@@ -1,30 +1,40 @@
 #!/usr/bin/env python
 """bench.py -- dense thin-wall inductance (L) build: element-pair integrals per second.
 
-One "step" = one complete build of this rank's row block of L for a synthetic tokamak-vessel
-mesh (torus with rectangular ports, jittered vertices; openfusiontoolkit_b200.ThinCurr.meshing).
-N=1 builds the whole matrix of a ~20k-vertex vessel (BASELINE.json configs[1]); at N>1 the mesh
-grows so that every GPU keeps the N=1 pair count (weak scaling), rows are sharded over the ranks
-(symmetric partition: every rank builds the upper trapezoid of its row block, so no pair integral is
-evaluated on two devices), no traffic during assembly, and the transposed blocks are exchanged once
-afterwards (one NCCL all-to-all, inside the timed step).
+Workload (default, every N): the 98k-vertex synthetic tokamak vessel of BASELINE.json configs[3] (torus with 10
+rectangular ports, jittered vertices; 224x448 grid), STRONG scaling: the same matrix is built by 1, 2, 4 or 8 GPUs.
+`--workload vessel20k` is the configs[1]-sized mesh of round 1, `--workload vessel150k` configs[4].
 
-  value  : whole-job pair-integrals/s with the model resident in HBM, rows left in HBM
-           (pairs = ordered triangle pairs the reference loop nest visits, thin_wall.F90:1028-1035)
-  e2e    : same metric through the host-buffer C-ABI call (thincurr_b200_Lmat_shard_host): host mesh
-           -> plan upload -> build -> rows copied to pinned host memory, all inside the timed region
-  roofline: FP64 pipe.  achieved = algorithmic flops of the reference loop nest (SURVEY.md 8d flop
-           model x the measured order histogram) / duration of the tile kernel (device globaltimer, first
-           CTA start -> last CTA end, measured live); peak = DFMA micro-benchmark measured in this run
-           (MEASURED_PEAKS.json holds no FP64 figure); traffic = DRAM bytes of the kernel from the
-           committed ncu --set full capture (profiles/r01_ncu_traffic.json)
-  cpu_baseline: the oracle's C/OpenMP restatement of the reference loop (reference flags -O2, same
-           schedule) on the host cores, on a bounded row sample of the same mesh
+One "step" = one complete build of L, rows left in HBM:
+  N = 1 : output memset + lmat_tile_kernel (all tiles of the upper triangle) + symmetrize_kernel
+  N > 1 : symmetric row partition -- every rank builds the upper trapezoid of its row block (no pair integral is
+          evaluated on two devices, no traffic during assembly); then ONE exchange inside the library
+          (thincurr_b200_Lmat_exchange: every rank reads the transposed blocks from its peers' HBM over NVLink through
+          cudaIpc mappings, 32x32 transposing tiles), bracketed by two one-element NCCL all-reduces that order the peers'
+          builds before the reads and the reads before the next step's memset.  All of it is inside the timed step.
 
-`--impl reference` times that CPU path alone on this arm's config (the Fortran reference cannot be
-compiled in this image: no Fortran compiler, no HDF5).
+  value   : whole-job pair-integrals/s (pairs = ordered triangle pairs the reference loop nest visits,
+            thin_wall.F90:1028-1035), device-timed (CUDA events on the launching stream), max over ranks
+  e2e     : the same metric through the reference-facing call `ThinCurr.compute_Lmat()` -> `thincurr_Lmat`
+            (thincurr_f.F90:545-581): host mesh -> plan upload -> build on N devices of ONE process -> rows into the
+            library-owned pinned host matrix in the reference layout; host<->device copies inside the timed region.
+            At N > 1 rank 0 makes that call with N visible devices while the other ranks wait at a barrier.
+  roofline: FP64 pipe.  achieved = algorithmic flops of the reference loop nest (SURVEY.md 8d flop model x the measured
+            order histogram) / N / the tile kernel's duration on the slowest rank (device globaltimer, first CTA start ->
+            last CTA end, measured live); peak = DFMA micro-benchmark run in this process (builder-measured:
+            MEASURED_PEAKS.json holds no FP64 figure); kernel_ms_ranks lists every rank's kernel time so that imbalance
+            and exchange separate.
+  cpu_baseline: the oracle's C/OpenMP restatement of the reference loop (reference flags -O2, schedule(dynamic,100),
+            atomics) on the host cores, on a bounded row slab of the same mesh; also the 4-thread figure (BASELINE.md
+            quotes the reference notebook at 4 threads), the build with the reference's `!$omp simd` loops enabled and a
+            -O3 -march=native build.
+
+`--impl reference` times that CPU path alone on this arm's config (the Fortran reference cannot be compiled in this
+image: no Fortran compiler, no HDF5), with every host core (OMP_NUM_THREADS is overridden: torchrun sets it to 1).
 """
 import argparse
+import ctypes
+import importlib.util
 import json
 import os
 import sys
@@ -35,21 +45,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
-
-def vessel_dims(n_gpus, base=(100, 200)):
-    f = float(n_gpus) ** 0.25
-    return int(round(base[0] * f)), int(round(base[1] * f))
+WORKLOADS = {'vessel20k': (100, 200), 'vessel100k': (224, 448), 'vessel150k': (274, 548)}
 
 
-def make_mesh(n_gpus, workload):
-    from openfusiontoolkit_b200.ThinCurr.meshing import build_torus_vessel
-    if workload == 'vessel100k':
-        nt, nphi = 224, 448
-    elif workload == 'vessel150k':
-        nt, nphi = 274, 548
-    else:
-        nt, nphi = vessel_dims(n_gpus)
-    m = build_torus_vessel(nt, nphi, R0=1.0, a=0.5, kappa=1.0, nports=10, jitter=0.05, seed=1234)
+def make_mesh(workload):
+    # the generator is loaded by path: the reference arm must not import the package (which loads the CUDA library)
+    spec = importlib.util.spec_from_file_location('_b200_meshing', os.path.join(ROOT, 'openfusiontoolkit_b200', 'ThinCurr', 'meshing.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    nt, nphi = WORKLOADS[workload]
+    m = mod.build_torus_vessel(nt, nphi, R0=1.0, a=0.5, kappa=1.0, nports=10, jitter=0.05, seed=1234)
     m['dims'] = (nt, nphi)
     return m
 
@@ -84,8 +89,8 @@ class ClockSampler(threading.Thread):
         if self.nv is None:
             return
         nv = self.nv
-        names = {nv.nvmlClocksEventReasonSwPowerCap if hasattr(nv, 'nvmlClocksEventReasonSwPowerCap') else 0x4: 'sw_power_cap',
-                 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake_slowdown'}
+        names = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+                 0x80: 'hw_power_brake_slowdown'}
         while not self.stop_flag:
             try:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
@@ -107,63 +112,80 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': float(np.median(self.sm)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
 
 
-def cpu_sample(mesh, seconds_target=15.0, steps=1):
-    """Oracle C/OpenMP loop (reference schedule) over a bounded block of row cells; returns
-    (pairs/s, threads, description)."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_sample(mesh, nthreads, variant=None, seconds=8.0, O=None):
+    """Oracle C/OpenMP loop (reference schedule) over a bounded slab of row cells in the middle of the mesh, sized from a
+    short probe so that it takes about `seconds`; returns (pairs/s, description, model)."""
     from oracle import tw_oracle as tw
-    O = tw.OracleModel(mesh['r'], mesh['lc'], None, nodesets=mesh['nodesets'], closures=mesh['closures'])
-    L = tw.lib()
-    nthreads = int(L.tco_num_threads())
-    nrows = min(O.nc, 100 * nthreads)          # one schedule(dynamic,100) chunk per thread
-    i0 = (O.nc - nrows) // 2
+    if O is None:
+        O = tw.OracleModel(mesh['r'], mesh['lc'], None, nodesets=mesh['nodesets'], closures=mesh['closures'])
     out = np.zeros((O.nelems, O.nelems))  # calloc-backed: only the rows the sample touches are ever committed
-    best = 0.0
-    for _ in range(steps):
+    mid = O.nc // 2
+    probe = min(O.nc, 100 * nthreads)  # one schedule(dynamic,100) chunk per thread
+    t0 = time.perf_counter()
+    vis = tw.lmat_sample(O, mid - probe // 2, mid - probe // 2 + probe, out, variant=variant, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    nrows = int(min(O.nc, max(probe, (seconds / max(dt, 1e-3)) * probe)) // (100 * nthreads)) * 100 * nthreads
+    nrows = max(nrows, probe)
+    if nrows > probe:
+        i0 = max(0, mid - nrows // 2)
         t0 = time.perf_counter()
-        O.compute_Lmat(i0, i0 + nrows, finalize=False, out=out)
+        vis = tw.lmat_sample(O, i0, i0 + nrows, out, variant=variant, nthreads=nthreads)
         dt = time.perf_counter() - t0
-        best = max(best, O.visited / dt)
-        last = (O.visited, dt)
-    desc = 'rows [%d,%d) of %d row cells x all %d column cells (%d visited pairs in %.1f s), gcc -O2 -fopenmp schedule(dynamic,100)' % (
-        i0, i0 + nrows, O.nc, O.nc, last[0], last[1])
-    return best, nthreads, desc, last
+    else:
+        i0 = mid - probe // 2
+    flags = {None: 'gcc -O2 -fopenmp', 'simd': 'gcc -O2 -fopenmp + omp simd loops (thin_wall.F90:1047,1070)',
+             'tuned': 'gcc -O3 -march=native -fopenmp + omp simd loops'}[variant]
+    desc = 'rows [%d,%d) of %d row cells x all %d column cells (%d visited pairs in %.1f s), %s, schedule(dynamic,100), %d threads' % (
+        i0, i0 + nrows, O.nc, O.nc, vis, dt, flags, nthreads)
+    return vis / dt, desc, O
+
+
+def workload_name(mesh):
+    return 'synthetic tokamak vessel with 10 ports, %dx%d grid (%d vertices / %d triangles), self-inductance L' % (
+        mesh['dims'][0], mesh['dims'][1], mesh['r'].shape[0], mesh['lc'].shape[0])
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    mesh = make_mesh(args.gpus, args.workload)
+    cores = host_cores()
+    os.environ['OMP_NUM_THREADS'] = str(cores)  # torchrun exports OMP_NUM_THREADS=1
+    mesh = make_mesh(args.workload)
+    O = None
     vals = []
+    best_variant = None
     for s in range(args.warmup + args.steps):
-        v, nthreads, desc, last = cpu_sample(mesh, steps=1)
+        # the reference's loop with and without its `omp simd` annotations honoured: the faster one is the reference arm
+        res = {}
+        for variant in (None, 'simd'):
+            v, desc, O = cpu_sample(mesh, cores, variant=variant, seconds=4.0, O=O)
+            res[variant] = (v, desc)
+        best_variant = max(res, key=lambda k: res[k][0])
         if s >= args.warmup:
-            vals.append((v, last[1]))
+            vals.append(res[best_variant])
     value = float(np.mean([v for v, _ in vals]))
+    nc = int(mesh['lc'].shape[0])
     line = {'impl': 'reference', 'metric': 'L-matrix pair-integrals/s', 'value': value, 'unit': 'pairs/s', 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * float(np.mean([t for _, t in vals])),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload_name(mesh, args), 'np': int(mesh['r'].shape[0]), 'nc': int(mesh['lc'].shape[0])},
-            'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': nthreads, 'kind': 'port', 'sample': desc},
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': None,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload_name(mesh), 'np': int(mesh['r'].shape[0]), 'nc': nc, 'nc2_pairs': nc * nc},
+            'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': vals[-1][1]},
             'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
 
 
-def ncu_traffic(mesh):
-    """dram__bytes_read.sum + dram__bytes_write.sum of lmat_tile_kernel per launch from the committed ncu --set full
-    capture of this workload (profiles/r01_ncu_traffic.json), or None when the capture is for another mesh."""
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')) as f:
-            d = json.load(f)
-        if int(d['np']) == int(mesh['r'].shape[0]) and int(d['nc']) == int(mesh['lc'].shape[0]):
-            return float(d['dram_bytes_read']) + float(d['dram_bytes_write'])
-    except Exception:
-        pass
-    return None
+class _DevBuf:
+    """Device memory of the library as a __cuda_array_interface__ object (for torch.as_tensor)."""
 
-
-def workload_name(mesh, args):
-    return 'synthetic tokamak vessel with 10 ports, %dx%d grid (%d vertices / %d triangles), self-inductance L' % (
-        mesh['dims'][0], mesh['dims'][1], mesh['r'].shape[0], mesh['lc'].shape[0])
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 3, 'strides': None}
 
 
 def main():
@@ -172,9 +194,11 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='auto', help='auto (weak-scaled ~20k-vertex vessel) | vessel100k | vessel150k')
+    ap.add_argument('--workload', default='vessel100k', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-gather', action='store_true')
+    ap.add_argument('--export', default=None, help='N>1: also stream every shard into this Lmat.save cache file (timed separately)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -194,34 +218,44 @@ def main():
     from openfusiontoolkit_b200 import _interface as I
     from openfusiontoolkit_b200.ThinCurr import ThinCurr
 
-    mesh = make_mesh(args.gpus, args.workload)
+    mesh = make_mesh(args.workload)
     T = ThinCurr(OFT_env(nthreads=-1))
     T.setup_model(r=mesh['r'], lc=mesh['lc'], nodesets=mesh['nodesets'], closures=mesh['closures'])
     N = T.nelems
-    # N > 1: symmetric partition -- every rank builds the upper trapezoid of its row block (no pair integral is
-    # evaluated on two devices) and the transposed blocks are exchanged once after the assembly (NCCL send/recv)
     sym = world > 1
     ids_all = [T.shard_rows_sym(world, s) for s in range(world)] if sym else None
     rows = ids_all[rank] if sym else T.shard_rows(world, rank)
     nrows = len(rows)
-    out = torch.empty((nrows, N), dtype=torch.float64, device='cuda')
+    out_ptr = T.device_alloc(max(nrows, 1) * N * 8)
+    out = torch.as_tensor(_DevBuf(out_ptr, (nrows, N)), device='cuda')
     stream = torch.cuda.current_stream().cuda_stream
+    token = torch.zeros(1, device='cuda')
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # peers' row blocks mapped into this process (cudaIpc over NVLink)
+    peer_ptrs = [None] * world
+    if sym:
+        handles = [None] * world
+        dist.all_gather_object(handles, T.ipc_export(out_ptr))
+        for s in range(world):
+            if s != rank:
+                peer_ptrs[s] = T.ipc_open(handles[s])
+        peer_ptrs[rank] = out_ptr
+
     # reference-loop statistics of the whole mesh (outside the timed region)
     hist, visited = T.pair_stats()
     flops_total = flop_model(hist)
-    # this rank's share of the algorithmic work: rows are balanced by cell count
-    share = 1.0 / world
 
     def step(stats=False):
         if sym:
             st_ = T.compute_Lmat_shard_sym(world, rank, out, stream=stream, stats=stats)
-            T.exchange_symmetric(out, world, rank, row_ids=ids_all)
+            dist.all_reduce(token)  # every peer's build is complete (stream-ordered)
+            T.exchange_symmetric_peer(out_ptr, N, world, rank, peer_ptrs, stream=stream)
+            dist.all_reduce(token)  # every peer is done reading before the next memset
             return st_
         return T.compute_Lmat_shard(world, rank, out, stream=stream, stats=stats)
 
@@ -243,25 +277,44 @@ def main():
     clocks = sampler.result()
     launches = I.b200_launch_count() - launches0
     ms_dev = ev[0].elapsed_time(ev[args.steps])
-    tt = torch.tensor([ms_dev, wall * 1e3], dtype=torch.float64, device='cuda')
+    tt = torch.tensor([ms_dev, wall * 1e3, float(launches)], dtype=torch.float64, device='cuda')
     if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_dev, ms_wall = [float(v) for v in tt.tolist()]
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        ms_dev, ms_wall, launches = float(tmax[0]), float(tmax[1]), int(tt[2])
+    else:
+        ms_dev, ms_wall = float(tt[0]), float(tt[1])
     ms_step = ms_dev / args.steps
     value = visited / (ms_step * 1e-3)
 
-    # kernel-only time of one step (events right around the tile kernel would need hooks inside the
-    # library; the step is memset + one tile kernel, so time a step without the memset share)
+    # the tile kernel's own duration on every rank (device globaltimer, first CTA start -> last CTA end, written by the
+    # kernel when stats are requested), and the exchange alone (events around the library call)
     st = step(stats=True)
-    # lmat_tile_kernel's own duration from the device's globaltimer (first CTA start -> last CTA end, written by the
-    # kernel when stats are requested); the step additionally holds the output memset, the row-map kernel and the
-    # symmetrisation pass
     kern_ms = (int(st[4]) - int(st[6])) * 1e-6
-    if not (0.0 < kern_ms <= 1.05 * ms_step):
-        kern_ms = ms_step
+    exch_ms = 0.0
+    if sym:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        T.exchange_symmetric_peer(out_ptr, N, world, rank, peer_ptrs, stream=stream)
+        e1.record()
+        barrier()
+        exch_ms = e0.elapsed_time(e1)
+    per_rank = torch.tensor([kern_ms, exch_ms, float(nrows)] + [float(st[k]) for k in range(4)], dtype=torch.float64, device='cuda')
+    allr = [torch.empty_like(per_rank) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, per_rank)
+    else:
+        allr = [per_rank]
+    allr = torch.stack(allr).cpu().numpy()
+    kern_ranks = [float(v) for v in allr[:, 0]]
+    kern_max = max(kern_ranks)
+    if not (0.0 < kern_max <= 1.05 * ms_step):
+        kern_max = ms_step
 
-    # N > 1: sanity check of the exchange outside the timed region -- block sums of L[rows r][DOFs s] and
-    # L[rows s][DOFs r] (its transpose, held by the other rank) must agree
+    # N > 1: the exchange must leave L[rows r][DOFs s] == L[rows s][DOFs r]^T: compare the block sums held by the two
+    # ranks (cheap; tests/test_gpu_multi.py compares every entry with the single-device build)
     exchange_check = None
     if sym:
         bs = torch.stack([out[:, torch.as_tensor(i.astype(np.int64), device='cuda')].sum() for i in ids_all])
@@ -270,27 +323,66 @@ def main():
         M = torch.stack(allbs).cpu().numpy()
         exchange_check = float(np.abs(M - M.T).max() / np.abs(M).max())
 
-    # e2e through the host-buffer entry point
-    e2e = None
-    if not args.no_e2e:
-        host = torch.empty((len(T.shard_rows(world, rank)), N), dtype=torch.float64, pin_memory=True)
-        hnp = host.numpy()
-        est = None
-        for _ in range(2):
-            est = T.compute_Lmat_shard_host(world, rank, hnp, stats=True)
+    # one gather over NVLink: the full matrix on rank 0's device (only when it fits next to the local block)
+    gather = None
+    if sym and not args.no_gather and (N * N * 8 + nrows * N * 8) < 150e9:
+        if rank == 0:
+            full_ptr = T.device_alloc(N * N * 8)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            T.gather_full(world, True, peer_ptrs, N, full_ptr, N, stream=stream)  # warm-up (maps, page tables)
+            torch.cuda.synchronize()
+            g0.record()
+            T.gather_full(world, True, peer_ptrs, N, full_ptr, N, stream=stream)
+            g1.record()
+            torch.cuda.synchronize()
+            gms = g0.elapsed_time(g1)
+            full = torch.as_tensor(_DevBuf(full_ptr, (N, N)), device='cuda')
+            k = min(N, 4096)
+            symm = float((full[:k, :k] - full[:k, :k].t()).abs().max() / full[:k, :k].abs().max())
+            mine = float((full[torch.as_tensor(rows.astype(np.int64), device='cuda')] - out).abs().max())
+            gather = {'ms': gms, 'GBps': N * N * 8 / gms / 1e6, 'bytes': N * N * 8, 'asym_rel_4096': symm, 'own_rows_maxdiff': mine,
+                      'api': 'thincurr_b200_Lmat_gather (peer reads over NVLink into the reference row order)'}
+            del full
+            T.device_free(full_ptr)
+        barrier()
+
+    # streamed export of every shard into one Lmat.save cache file (reference format, ranks write concurrently)
+    export = None
+    if args.export:
+        if rank == 0:
+            T.save_Lmat_begin(args.export)
         barrier()
         t0 = time.perf_counter()
-        nrep = max(1, min(args.steps, 3))
-        for _ in range(nrep):
-            est = T.compute_Lmat_shard_host(world, rank, hnp, stats=True)
+        T.save_Lmat_rows(args.export, world, rank, sym, out_ptr, N)
         barrier()
-        dt = (time.perf_counter() - t0) / nrep
-        tt = torch.tensor([dt], dtype=torch.float64, device='cuda')
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {'value': visited / dt, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(est[5]) * world, 'd2h_bytes_per_step': int(est[6]) * world,
-               'ms_per_step': dt * 1e3, 'api': 'thincurr_b200_Lmat_shard_host (host mesh -> pinned host rows)'}
+        dt = time.perf_counter() - t0
+        export = {'path': args.export, 's': dt, 'bytes': os.path.getsize(args.export) if rank == 0 else None}
+
+    # e2e through the reference-facing entry point: ThinCurr.compute_Lmat() -> thincurr_Lmat, N devices from one process
+    for s in range(world):
+        if sym and s != rank and peer_ptrs[s]:
+            T.ipc_close(peer_ptrs[s])
+    del out
+    barrier()
+    T.device_free(out_ptr)
+    barrier()
+    e2e = None
+    if not args.no_e2e:
+        if rank == 0:
+            os.environ['THINCURR_B200_NDEV'] = str(world)
+            T.compute_Lmat()  # allocates + pins the library-owned host matrix, device scratch, peer mappings
+            T.compute_Lmat()
+            nrep = 2
+            t0 = time.perf_counter()
+            for _ in range(nrep):
+                T.compute_Lmat()
+            dt = (time.perf_counter() - t0) / nrep
+            pi = T.plan_info()
+            e2e = {'value': visited / dt, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(pi.get('model_bytes', 0)) * world,
+                   'd2h_bytes_per_step': int(N) * int(N) * 8, 'ms_per_step': dt * 1e3,
+                   'api': 'ThinCurr.compute_Lmat() -> thincurr_Lmat: host mesh -> %d device(s) of one process -> library-owned pinned host matrix (reference layout)' % world,
+                   'sym_check': float(np.abs(T.Lmat[:2048, :2048] - T.Lmat[:2048, :2048].T).max())}
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -298,28 +390,39 @@ def main():
         return
 
     peak_clock = np.zeros(1)
-    import ctypes
     peak_tf = float(I.b200_dfma_peak(local_rank, peak_clock.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
-    achieved_tf = flops_total * share / (kern_ms * 1e-3) / 1e12
+    achieved_tf = flops_total / world / (kern_max * 1e-3) / 1e12
+    dev_evals = allr[:, 3:7].sum(axis=0)
     roofline = {'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf if peak_tf > 0 else None,
-                'traffic': ncu_traffic(mesh), 'peak_source': 'DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
-                'algorithmic_flops_per_step': flops_total * share, 'flops_per_pair': flops_total / visited,
-                'hbm_write_GBps': nrows * N * 8 / (kern_ms * 1e-3) / 1e9, 'kernel': 'lmat_tile_kernel',
-                'kernel_ms': kern_ms, 'cta_finish_spread': {'first_ms': (int(st[7]) - int(st[6])) * 1e-6, 'last_ms': (int(st[4]) - int(st[6])) * 1e-6},
-                'device_evals': {'far_pairs': int(st[0]), 'near_T': int(st[1]), 'inv_r': int(st[2]), 'phipot': int(st[3])}}
+                'traffic': None, 'peak_source': 'builder-measured: DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)',
+                'algorithmic_flops_per_step': flops_total, 'flops_per_pair': flops_total / visited,
+                'hbm_write_GBps': nrows * N * 8 / (kern_max * 1e-3) / 1e9, 'kernel': 'lmat_tile_kernel',
+                'kernel_ms': kern_max, 'kernel_ms_ranks': kern_ranks, 'exchange_ms_ranks': [float(v) for v in allr[:, 1]],
+                'rows_ranks': [int(v) for v in allr[:, 2]],
+                'device_evals': {'far_pairs': int(dev_evals[0]), 'near_T': int(dev_evals[1]), 'inv_r': int(dev_evals[2]), 'phipot': int(dev_evals[3])},
+                'inv_r_vs_reference': float(dev_evals[2]) / max(1.0, float(sum(hist[q] * n * n for q, n in ((4, 6), (5, 7), (6, 12), (7, 15), (8, 16), (9, 19), (10, 25)))))}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, nthreads, desc, _ = cpu_sample(mesh)
-        cpu = {'value': v, 'unit': 'pairs/s', 'cores': nthreads, 'kind': 'port', 'sample': desc}
+        cores = host_cores()
+        v, desc, O = cpu_sample(mesh, cores, seconds=8.0)
+        cpu = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': desc}
+        v4, d4, _ = cpu_sample(mesh, min(4, cores), seconds=4.0, O=O)
+        vs, ds, _ = cpu_sample(mesh, cores, variant='simd', seconds=4.0, O=O)
+        vt, dtn, _ = cpu_sample(mesh, cores, variant='tuned', seconds=4.0, O=O)
+        cpu['four_threads'] = {'value': v4, 'sample': d4}
+        cpu['omp_simd'] = {'value': vs, 'sample': ds}
+        cpu['tuned'] = {'value': vt, 'sample': dtn}
     line = {'metric': 'L-matrix pair-integrals/s', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload_name(mesh, args), 'np': int(mesh['r'].shape[0]), 'nc': int(mesh['lc'].shape[0]),
+            'config': {'workload': workload_name(mesh), 'np': int(mesh['r'].shape[0]), 'nc': int(mesh['lc'].shape[0]),
                        'nelems': int(N), 'visited_pairs': int(visited), 'nc2_pairs': int(mesh['lc'].shape[0]) ** 2,
-                       'order_hist': {str(q): int(hist[q]) for q in range(4, 19)}, 'sharding': ('row blocks, 1 shard, no collective' if not sym else
+                       'order_hist': {str(q): int(hist[q]) for q in range(4, 19)},
+                       'sharding': ('row blocks, 1 shard, no collective' if not sym else
                                     'row blocks balanced over the upper trapezoid, %d shards, no traffic during assembly; transposed blocks '
-                                    'exchanged once afterwards (NCCL send/recv, inside the timed step)' % world),
-                       'exchange_check_rel': exchange_check,
+                                    'read from peer HBM over NVLink afterwards (thincurr_b200_Lmat_exchange through cudaIpc mappings, '
+                                    'ordered by two 1-element NCCL all-reduces), inside the timed step' % world),
+                       'exchange_check_rel': exchange_check, 'gather': gather, 'export': export,
                        'l2': 'flushed every step by the %.1f GB output memset' % (nrows * N * 8 / 1e9), 'plan': T.plan_info()},
             'wall_ms_per_step': ms_wall / args.steps, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'roofline': roofline, 'cpu_baseline': cpu}

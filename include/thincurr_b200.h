@@ -73,6 +73,49 @@ void thincurr_get_eta(void* tw_ptr, double* eta_surf, char* error_str);
 void thincurr_set_eta(void* tw_ptr, const double* eta_surf, const double* eta_vol, const double* thickness,
                       char* error_str);
 
+/* The remaining names the reference's Python layer binds at import (P:21-119), so that the unmodified
+ * OpenFUSIONToolkit.ThinCurr package loads against this library.  Answered natively: thincurr_scale_va (F:453-466),
+ * thincurr_get_eta_vol (F:721-731), thincurr_get_thickness (F:887-902), thincurr_apply_Lmat (F:470-497: dense mat-vec on
+ * the device, vals overwritten), thincurr_eigenvalues (F:975-1013: iterative path = Lanczos on the device-resident L,
+ * direct=true is refused).  The others belong to the reference's downstream solvers / plotting and report
+ * "not provided" through error_str (those without an error_str print the message and call the abort callback that
+ * oftpy_init received, the reference's oft_abort convention). */
+void thincurr_setup_io(void* tw_ptr, const char* basepath, bool save_debug, bool legacy_hdf5, char* error_str);
+void thincurr_recon_curr(void* tw_ptr, const double* vals, double* curr, int format);
+void thincurr_recon_field(void* tw_ptr, const double* pot, const double* coils, double* field, void* hodlr_ptr);
+void thincurr_save_field(void* tw_ptr, const double* vals, const char* fieldname);
+void thincurr_save_scalar(void* tw_ptr, const double* vals, const char* fieldname);
+void thincurr_scale_va(void* tw_ptr, double* vals, bool div_flag);
+void thincurr_apply_Lmat(void* tw_ptr, double* vals, void* hodlr_ptr);
+void thincurr_cross_eval(void* tw_ptr1, void* tw_ptr2, int nrhs, const double* vec1, double* vec2, char* error_str);
+void thincurr_get_eta_vol(void* tw_ptr, double* eta_vol, char* error_str);
+void thincurr_get_thickness(void* tw_ptr, double* thickness, char* error_str);
+void thincurr_curr_regmat(void* tw_ptr, double* Rmat, char* error_str);
+void thincurr_eigenvalues(void* tw_ptr, bool direct, int neigs, double* eig_vals, double* eig_vec, void* hodlr_ptr,
+                          char* error_str);
+void thincurr_freq_response(void* tw_ptr, bool direct, int fr_limit, double freq, double* fr_driver, void* hodlr_ptr,
+                            char* error_str);
+void thincurr_time_domain(void* tw_ptr, bool direct, double dt, int nsteps, double cg_atol, double cg_rtol, bool timestep_cn,
+                          int nstatus, int nplot, const double* vec_ic, void* sensor_ptr, int ncurr, const double* curr_ptr,
+                          int nvolt, const double* volt_ptr, bool volts_full, void* sensor_vals_ptr, void* hodlr_ptr,
+                          char* error_str);
+void thincurr_time_domain_plot(void* tw_ptr, bool compute_B, bool rebuild_sensors, int nsteps, int nplot, void* sensor_ptr,
+                               const double* sensor_vals, int nsensors, void* hodlr_ptr, char* error_str);
+void thincurr_reduce_model(void* tw_ptr, const char* filename, int neigs, const double* eig_vec, bool compute_B,
+                           void* sensor_ptr, void* hodlr_ptr, char* error_str);
+
+/* Names the reference's BASE package binds at import (src/python/OpenFUSIONToolkit/_interface.py:114-132): mesh
+ * objects of the other physics modules.  Exported so that the unmodified package loads; they report "not provided". */
+void oft_setup_smesh(int ndim, int np, const double* r_loc, int npc, int nc, const int* lc_loc, const int* reg_loc,
+                     int* nregs, void** mesh_ptr);
+void oft_smesh_get(void* mesh_ptr, int* ndim, int* np, double** r_loc, int* npc, int* nc, int** lc_loc, int** reg_loc,
+                   int* nregs, char* error_str);
+void oft_setup_vmesh(int np, const double* r_loc, int npc, int nc, const int* lc_loc, const int* reg_loc, int* nregs,
+                     void** mesh_ptr);
+void oft_vmesh_get(void* mesh_ptr, int* np, double** r_loc, int* npc, int* nc, int** lc_loc, int** reg_loc, int* nregs,
+                   char* error_str);
+void dump_cov(void);
+
 /* ---------------------------------------------------------------------------------------
  * Block 2: B200-native flat interface (what a Fortran host binds through ISO_C_BINDING;
  * see include/thincurr_b200_f.F90 and INTEGRATION.md).  All return 0 on success, else an
@@ -122,6 +165,10 @@ int thincurr_b200_shard_rows(void* tw_ptr, int nshards, int shard, int* row_ids)
 /* info[8]: patch size, patches, chunks, sum of patch cells (halo included), self tiles, chunk pairs,
  * cell pairs of those tiles (diagonal tiles counted in full), vertex patches */
 int thincurr_b200_plan_info(void* tw_ptr, int64_t* info);
+/* introspection: patch_chunk_ptr[npatch+1]; chunk_info[nchunk][6] = centre xyz, bounding radius, longest edge, cells */
+int thincurr_b200_plan_chunks(void* tw_ptr, int* patch_chunk_ptr, double* chunk_info);
+/* host->device bytes of one upload of the model (plan mirror) to a device; 0 before the first build */
+int64_t thincurr_b200_model_bytes(void* tw_ptr);
 
 /* Self-inductance rows of one shard into caller-provided DEVICE memory d_out[nrows][ld]
  * (row r = full reference row row_ids[r], i.e. Lmat(:,row_ids[r]+1); ld >= nelems), on the
@@ -171,20 +218,59 @@ long long thincurr_b200_launch_count(void);
 /* FP64 DFMA peak microbenchmark on the current device (TFLOP/s, FMA = 2 flops). */
 double thincurr_b200_dfma_peak(int device, double* sm_clock_mhz);
 
-/* Kernel-level probes for the parity tests: the device functions of the operator kernels on
- * caller-given inputs.  probe_pairs: T(i,j) with cell i the analytic side when near, and the
- * selected quadrature order (thin_wall.F90:1044-1083); Pi/Pj = [n][3][3] vertices, Ai/Aj areas;
- * mode 0 = FP64 classification + far field from the vertices, mode 1 = the tile kernel's path (FP32
- * order screen with exact fallback [iquad bit 6 set when taken], far field from point tables).
- * probe_phipot: tw_compute_phipot (thin_wall.F90:1934-1985) for tri[n][3][3], pt[n][3]. */
-int thincurr_b200_probe_pairs(int n, int mode, const double* Pi, const double* Ai, const double* Pj, const double* Aj,
-                              double* T, int* iquad);
-int thincurr_b200_probe_phipot(int n, const double* tri, const double* pt, double* out);
-int thincurr_b200_probe_rsqrt(int n, const double* x, double* y);
-
 /* Introspection for tests. */
 int thincurr_b200_get_model(void* tw_ptr, int* pmap, int* lc, int* kfh, int* lfh, double* qbasis, double* ca);
 int thincurr_b200_hashes(void* tw_ptr, int32_t* hash_lc, int32_t* hash_r);
+
+/* Release the device-side state of a model (plan mirrors, row-block scratch of the host-buffer entry points). */
+int thincurr_b200_release_device(void* tw_ptr);
+
+/* ---------------------------------------------------------------------------------------
+ * Block 3: multi-device data plane of the sharded operators (csrc/tw_shard.cu, csrc/tw_solve.cu).
+ * The assembly needs no inter-device traffic; these entry points are what follows it.
+ * ------------------------------------------------------------------------------------ */
+/* Device memory that other ranks of the same node can map (cudaMalloc + cudaIpc*), and peer access between the
+ * devices of one process. handle64 = 64 bytes (cudaIpcMemHandle_t). */
+int thincurr_b200_device_alloc(int64_t bytes, void** d_ptr);
+int thincurr_b200_device_free(void* d_ptr);
+int thincurr_b200_ipc_export(void* d_ptr, unsigned char* handle64);
+int thincurr_b200_ipc_open(const unsigned char* handle64, void** d_ptr);
+int thincurr_b200_ipc_close(void* d_ptr);
+int thincurr_b200_enable_peer(int peer_device);
+
+/* Exchange after a symmetric build (thin_wall.F90:1146-1151 across shards): shard `shard` fills the columns of the
+ * DOFs of every earlier shard s < shard of its rows d_out[nrows][ld] with the transposes of the blocks those shards
+ * computed, READING peer_rows[s] (device pointer to shard s's row block with the same ld: a peer device of this process
+ * or a cudaIpc-mapped pointer of another rank) over NVLink.  Asynchronous on `stream`; the caller orders it after the
+ * peers' builds (event / stream-ordered collective) and keeps the peers' blocks unchanged until it has run. */
+int thincurr_b200_Lmat_exchange(void* tw_ptr, int nshards, int shard, double* d_out, int64_t ld,
+                                const double* const* peer_rows, void* stream);
+/* "One gather over NVLink when the full matrix is requested on one device": rows of all shards (pointers readable from
+ * the current device, ld_src) into d_full[nelems][ld_full] in the reference row order.  sym != 0: the shards are the
+ * symmetric partition's (already exchanged). */
+int thincurr_b200_Lmat_gather(void* tw_ptr, int nshards, int sym, const double* const* shard_rows, int64_t ld_src,
+                              double* d_full, int64_t ld_full, void* stream);
+/* Export of a shard's rows (device) into a host matrix h_full[nelems][ld_full] in the reference layout, streamed
+ * through pinned buffers (matrices that fit no single device: 150k-vertex vessel, 180 GB). */
+int thincurr_b200_rows_to_host(void* tw_ptr, int nshards, int shard, int sym, const double* d_rows, int64_t ld,
+                               double* h_full, int64_t ld_full);
+/* Export into the reference's `Lmat.save` cache (thin_wall.F90:1161-1171): _begin writes the header record and sizes the
+ * file, _rows writes the upper-packed records of a shard's rows at their file offsets (ranks write concurrently). */
+int thincurr_b200_Lmat_save_begin(void* tw_ptr, const char* path);
+int thincurr_b200_Lmat_save_rows(void* tw_ptr, const char* path, int nshards, int shard, int sym, const double* d_rows,
+                                 int64_t ld);
+
+/* Dense apply on a resident row block: d_y[nrows] = d_rows[nrows][ld] . d_x[n] (thincurr_apply_Lmat, F:470-497, per
+ * shard; the caller all-gathers y).  HBM-bound row kernel, asynchronous on `stream`. */
+int thincurr_b200_rows_apply(const double* d_rows, int64_t ld, int nrows, int n, const double* d_x, double* d_y,
+                             void* stream);
+/* Leading `neigs` eigenvalues of L x = lambda R x (lr_eigenmodes_arpack, thin_wall_solvers.F90:119-224) by Lanczos in
+ * the R inner product; y = L x is supplied by the caller (HOST vectors of nelems doubles; returns 0 on success) so the
+ * matrix can stay sharded over devices / ranks.  eig_vec[neigs][nelems]; tol = relative residual (<=0: 1e-10);
+ * max_dim = basis limit (<=0: 400); n_applies (optional) returns the number of mat-vecs used. */
+typedef int (*thincurr_b200_apply_fn)(void* user, const double* x, double* y);
+int thincurr_b200_lr_eigs(void* tw_ptr, int neigs, double tol, int max_dim, thincurr_b200_apply_fn apply, void* user,
+                          double* eig_vals, double* eig_vec, int* n_applies);
 
 #ifdef __cplusplus
 }

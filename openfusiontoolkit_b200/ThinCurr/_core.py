@@ -3,8 +3,9 @@ behaviour as the reference's src/python/OpenFUSIONToolkit/ThinCurr/_core.py for 
 build path (setup_model :99-166, compute_Lmat :269-288, compute_Bmat :307-331, compute_Mcoil
 :333-348, compute_Msensor :350-387, compute_Rmat :491-513, cross_coupling :515-531).  All
 matrices are zero-copy numpy views of library-owned buffers in the reference's layouts.
-Methods of the reference that belong to downstream solvers (eigenmodes, time stepping,
-frequency response, plotting) are out of scope and raise NotImplementedError.
+`get_eigs` (iterative path, _core.py:563-580) and `apply_Lmat` (:472-489 region) run on the device-resident matrix.
+Methods of the reference that belong to the remaining downstream solvers (time stepping, frequency response, plotting,
+reduced models) are out of scope and raise NotImplementedError.
 """
 import ctypes
 from ctypes import c_bool, c_double, c_int, c_void_p
@@ -12,7 +13,10 @@ from ctypes import c_bool, c_double, c_int, c_void_p
 import numpy
 import scipy.sparse
 
-from .._interface import (b200_Lmat_block, b200_Bel_shard, b200_Lmat_shard, b200_Lmat_shard_host, b200_Lmat_shard_sym, b200_shard_rows_sym, b200_destroy, b200_get_model,
+from .._interface import (B200_APPLY_FN, b200_device_alloc, b200_device_free, b200_ipc_close, b200_ipc_export, b200_ipc_open,
+                          b200_Lmat_exchange, b200_Lmat_gather, b200_Lmat_save_begin, b200_Lmat_save_rows, b200_lr_eigs,
+                          b200_release_device, b200_rows_apply, b200_rows_to_host, thincurr_apply_Lmat, thincurr_eigenvalues,
+                          b200_Lmat_block, b200_Bel_shard, b200_Lmat_shard, b200_Lmat_shard_host, b200_Lmat_shard_sym, b200_shard_rows_sym, b200_destroy, b200_get_model,
                           b200_hashes, b200_last_error, b200_msensor, b200_pair_stats, b200_plan, b200_set_coils,
                           b200_set_sensors, b200_setup, b200_shard_rows, c_double_ptr, c_int_ptr, mu0, oftpy_load_xml,
                           thincurr_Bmat, thincurr_cross_coupling, thincurr_get_eta, thincurr_get_sensor_name,
@@ -386,8 +390,11 @@ class ThinCurr():
         from .._interface import b200_plan_info
         info = numpy.zeros(8, dtype=numpy.int64)
         _check(b200_plan_info(self.tw_obj, info))
-        return dict(zip(('patch_size', 'npatch', 'nchunk', 'patch_cells', 'ntiles', 'chunk_pairs', 'cell_pairs', 'nvert_patch'),
-                        [int(v) for v in info]))
+        from .._interface import b200_model_bytes
+        d = dict(zip(('patch_size', 'npatch', 'nchunk', 'patch_cells', 'ntiles', 'chunk_pairs', 'cell_pairs', 'nvert_patch'),
+                     [int(v) for v in info]))
+        d['model_bytes'] = int(b200_model_bytes(self.tw_obj))
+        return d
 
     def pair_stats(self):
         '''! iquad histogram [19] and number of ordered pairs visited by the reference loop nest.'''
@@ -414,9 +421,119 @@ class ThinCurr():
         b200_hashes(self.tw_obj, ctypes.byref(a), ctypes.byref(b))
         return a.value, b.value
 
+    # ---- dense apply / leading eigenmodes on the device-resident matrix ---------------------------
+    def apply_Lmat(self, vals):
+        '''! y = L x with the dense matrix of `compute_Lmat` (reference: thincurr_apply_Lmat, thincurr_f.F90:470-497);
+        returns a new array.'''
+        out = numpy.ascontiguousarray(vals, dtype=numpy.float64).copy()
+        if out.shape[0] != self.nelems:
+            raise IndexError('Incorrect shape of "vals", should be [nelems]')
+        thincurr_apply_Lmat(self.tw_obj, out, self.Lmat_hodlr)
+        return out
+
+    def get_eigs(self, neigs, direct=False):
+        '''! Leading L/R eigenmodes (reference: _core.py:563-580).  Iterative path only (Lanczos on the device-resident
+        matrix); `direct=True` is refused by the library.
+
+        @result Eigenvalues `(neigs)`, eigenvectors `(neigs,:)`'''
+        eig_vals = numpy.zeros((neigs,), dtype=numpy.float64)
+        eig_vecs = numpy.zeros((neigs, self.nelems), dtype=numpy.float64)
+        error_string = self._oft_env.get_c_errorbuff()
+        thincurr_eigenvalues(self.tw_obj, c_bool(direct), c_int(neigs), eig_vals, eig_vecs, c_void_p(), error_string)
+        if error_string.value != b'':
+            raise Exception(error_string.value.decode())
+        return eig_vals, eig_vecs
+
+    def get_eigs_sharded(self, neigs, apply, tol=1e-10, max_dim=400):
+        '''! (extension) Leading L/R eigenmodes with the mat-vec supplied by the caller: `apply(x) -> y` on host vectors
+        of `nelems` doubles, e.g. `rows_apply` on every rank's resident row block + an all-gather of y.  Needs
+        `compute_Rmat`.  Returns eigenvalues, eigenvectors `(neigs,:)` and the number of mat-vecs.'''
+        n = self.nelems
+
+        def _cb(_user, xp, yp):
+            try:
+                x = numpy.ctypeslib.as_array(xp, shape=(n,))
+                y = numpy.ctypeslib.as_array(yp, shape=(n,))
+                y[:] = apply(x)
+                return 0
+            except Exception:  # pragma: no cover
+                import traceback
+                traceback.print_exc()
+                return 1
+        cb = B200_APPLY_FN(_cb)
+        eig_vals = numpy.zeros((neigs,), dtype=numpy.float64)
+        eig_vecs = numpy.zeros((neigs, n), dtype=numpy.float64)
+        napp = c_int()
+        _check(b200_lr_eigs(self.tw_obj, neigs, tol, max_dim, cb, None, eig_vals, eig_vecs, ctypes.byref(napp)))
+        return eig_vals, eig_vecs, napp.value
+
+    @staticmethod
+    def rows_apply(rows_ptr, ld, nrows, n, x_ptr, y_ptr, stream=None):
+        '''! (extension) y[nrows] = rows[nrows][ld] . x[n] on the current device (device pointers as ints).'''
+        _check(b200_rows_apply(c_void_p(rows_ptr), ld, nrows, n, c_void_p(x_ptr), c_void_p(y_ptr), c_void_p(stream) if stream else c_void_p()))
+
+    # ---- multi-device data plane in the library (include/thincurr_b200.h block 3) ---------------------
+    @staticmethod
+    def device_alloc(nbytes):
+        '''! (extension) cudaMalloc'ed block on the current device that other ranks can map (returns the pointer as int).'''
+        p = c_void_p()
+        _check(b200_device_alloc(int(nbytes), ctypes.byref(p)))
+        return p.value
+
+    @staticmethod
+    def device_free(ptr):
+        _check(b200_device_free(c_void_p(ptr)))
+
+    @staticmethod
+    def ipc_export(ptr):
+        h = ctypes.create_string_buffer(64)
+        _check(b200_ipc_export(c_void_p(ptr), h))
+        return h.raw
+
+    @staticmethod
+    def ipc_open(handle):
+        p = c_void_p()
+        _check(b200_ipc_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(p)))
+        return p.value
+
+    @staticmethod
+    def ipc_close(ptr):
+        _check(b200_ipc_close(c_void_p(ptr)))
+
+    def exchange_symmetric_peer(self, out_ptr, ld, nshards, shard, peer_ptrs, stream=None):
+        '''! (extension) Complete the rows built by `compute_Lmat_shard_sym` by READING the transposed blocks from the
+        earlier shards' row blocks (`peer_ptrs[s]`: device pointer readable from this device -- a peer device of this
+        process or a cudaIpc mapping -- for every s < shard) over NVLink, inside the library
+        (thincurr_b200_Lmat_exchange).  Asynchronous on `stream`; the caller orders it after the peers' builds.'''
+        arr = (c_void_p * nshards)(*[c_void_p(p) if p else c_void_p() for p in peer_ptrs])
+        _check(b200_Lmat_exchange(self.tw_obj, nshards, shard, c_void_p(out_ptr), ld, arr, c_void_p(stream) if stream else c_void_p()))
+
+    def gather_full(self, nshards, sym, shard_ptrs, ld_src, full_ptr, ld_full, stream=None):
+        '''! (extension) One gather over NVLink: the rows of all shards (device pointers readable from this device) into
+        the full matrix `full[nelems][ld_full]` on the current device, reference row order.'''
+        arr = (c_void_p * nshards)(*[c_void_p(p) if p else c_void_p() for p in shard_ptrs])
+        _check(b200_Lmat_gather(self.tw_obj, nshards, 1 if sym else 0, arr, ld_src, c_void_p(full_ptr), ld_full,
+                                c_void_p(stream) if stream else c_void_p()))
+
+    def rows_to_host(self, nshards, shard, sym, rows_ptr, ld, full_host):
+        '''! (extension) Stream this shard's rows (device) into the host matrix `full_host[nelems, ld_full]` (numpy).'''
+        _check(b200_rows_to_host(self.tw_obj, nshards, shard, 1 if sym else 0, c_void_p(rows_ptr), ld,
+                                 full_host.ctypes.data_as(c_void_p), full_host.shape[1]))
+
+    def save_Lmat_begin(self, path):
+        '''! (extension) Header + size of an `Lmat.save` cache file that shards then fill concurrently.'''
+        _check(b200_Lmat_save_begin(self.tw_obj, self._oft_env.path2c(path)))
+
+    def save_Lmat_rows(self, path, nshards, shard, sym, rows_ptr, ld):
+        _check(b200_Lmat_save_rows(self.tw_obj, self._oft_env.path2c(path), nshards, shard, 1 if sym else 0, c_void_p(rows_ptr), ld))
+
+    def release_device(self):
+        '''! (extension) Free the device-side state of the model (plan mirrors, row scratch).'''
+        _check(b200_release_device(self.tw_obj))
+
     # ---- out of scope (downstream consumers of the operators) ----------------------
     def _oos(self, *a, **k):
         raise NotImplementedError('Not part of the B200 operator-build backend; use the reference library for this step')
 
-    get_eigs = compute_freq_response = run_td = plot_td = build_reduced_model = cross_eval = _oos
-    setup_io = save_current = save_scalar = reconstruct_current = reconstruct_Bfield = apply_Lmat = get_regmat = _oos
+    compute_freq_response = run_td = plot_td = build_reduced_model = cross_eval = _oos
+    setup_io = save_current = save_scalar = reconstruct_current = reconstruct_Bfield = get_regmat = _oos

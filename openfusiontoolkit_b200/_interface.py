@@ -101,11 +101,54 @@ b200_get_model = ctypes_subroutine(oftpy_lib.thincurr_b200_get_model,
 b200_hashes = ctypes_subroutine(oftpy_lib.thincurr_b200_hashes, [c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)], c_int)
 _f64 = numpy.ctypeslib.ndpointer(dtype=numpy.float64, flags='C_CONTIGUOUS')
 _i32 = numpy.ctypeslib.ndpointer(dtype=numpy.int32, flags='C_CONTIGUOUS')
-b200_probe_pairs = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_pairs, [c_int, c_int, _f64, _f64, _f64, _f64, _f64, _i32], c_int)
-b200_probe_phipot = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_phipot, [c_int, _f64, _f64, _f64], c_int)
-b200_probe_rsqrt = ctypes_subroutine(oftpy_lib.thincurr_b200_probe_rsqrt, [c_int, _f64, _f64], c_int)
 b200_launch_count = ctypes_subroutine(oftpy_lib.thincurr_b200_launch_count, [], ctypes.c_longlong)
 b200_plan_info = ctypes_subroutine(oftpy_lib.thincurr_b200_plan_info, [c_void_p, numpy.ctypeslib.ndpointer(dtype=numpy.int64, flags='C_CONTIGUOUS')], c_int)
 b200_model_from_tw = ctypes_subroutine(oftpy_lib.thincurr_b200_model_from_tw,
     [c_int, _f64, c_int, _i32, c_void_p, _i32, c_int, c_int, _i32, c_void_p, c_void_p, c_void_p, c_void_ptr_ptr], c_int)
 b200_Lmat_host = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_host, [c_void_p, _f64], c_int)
+b200_model_bytes = ctypes_subroutine(oftpy_lib.thincurr_b200_model_bytes, [c_void_p], c_int64)
+b200_release_device = ctypes_subroutine(oftpy_lib.thincurr_b200_release_device, [c_void_p], c_int)
+
+# ---- the remaining reference names (ThinCurr/_interface.py:21-119): native where cheap, "not provided" otherwise
+thincurr_setup_io = ctypes_subroutine(oftpy_lib.thincurr_setup_io, [c_void_p, c_char_p, c_bool, c_bool, c_char_p])
+thincurr_recon_curr = ctypes_subroutine(oftpy_lib.thincurr_recon_curr, [c_void_p, ctypes_numpy_array(float64, 1), ctypes_numpy_array(float64, 2), c_int])
+thincurr_recon_field = ctypes_subroutine(oftpy_lib.thincurr_recon_field,
+    [c_void_p, ctypes_numpy_array(float64, 1), ctypes_numpy_array(float64, 1), ctypes_numpy_array(float64, 2), c_void_p])
+thincurr_save_field = ctypes_subroutine(oftpy_lib.thincurr_save_field, [c_void_p, ctypes_numpy_array(float64, 1), c_char_p])
+thincurr_save_scalar = ctypes_subroutine(oftpy_lib.thincurr_save_scalar, [c_void_p, ctypes_numpy_array(float64, 1), c_char_p])
+thincurr_scale_va = ctypes_subroutine(oftpy_lib.thincurr_scale_va, [c_void_p, ctypes_numpy_array(float64, 1), c_bool])
+thincurr_apply_Lmat = ctypes_subroutine(oftpy_lib.thincurr_apply_Lmat, [c_void_p, ctypes_numpy_array(float64, 1), c_void_p])
+thincurr_cross_eval = ctypes_subroutine(oftpy_lib.thincurr_cross_eval,
+    [c_void_p, c_void_p, c_int, ctypes_numpy_array(float64, 2), ctypes_numpy_array(float64, 2), c_char_p])
+thincurr_get_eta_vol = ctypes_subroutine(oftpy_lib.thincurr_get_eta_vol, [c_void_p, ctypes_numpy_array(float64, 1), c_char_p])
+thincurr_get_thickness = ctypes_subroutine(oftpy_lib.thincurr_get_thickness, [c_void_p, ctypes_numpy_array(float64, 1), c_char_p])
+thincurr_curr_regmat = ctypes_subroutine(oftpy_lib.thincurr_curr_regmat, [c_void_p, ctypes_numpy_array(float64, 2), c_char_p])
+thincurr_eigenvalues = ctypes_subroutine(oftpy_lib.thincurr_eigenvalues,
+    [c_void_p, c_bool, c_int, ctypes_numpy_array(float64, 1), ctypes_numpy_array(float64, 2), c_void_p, c_char_p])
+thincurr_freq_response = ctypes_subroutine(oftpy_lib.thincurr_freq_response,
+    [c_void_p, c_bool, c_int, c_double, ctypes_numpy_array(float64, 2), c_void_p, c_char_p])
+thincurr_time_domain = ctypes_subroutine(oftpy_lib.thincurr_time_domain,
+    [c_void_p, c_bool, c_double, c_int, c_double, c_double, c_bool, c_int, c_int, ctypes_numpy_array(float64, 1), c_void_p, c_int,
+     ctypes_numpy_array(float64, 2), c_int, ctypes_numpy_array(float64, 2), c_bool, c_void_p, c_void_p, c_char_p])
+thincurr_time_domain_plot = ctypes_subroutine(oftpy_lib.thincurr_time_domain_plot,
+    [c_void_p, c_bool, c_bool, c_int, c_int, c_void_p, ctypes_numpy_array(float64, 2), c_int, c_void_p, c_char_p])
+thincurr_reduce_model = ctypes_subroutine(oftpy_lib.thincurr_reduce_model,
+    [c_void_p, c_char_p, c_int, ctypes_numpy_array(float64, 2), c_bool, c_void_p, c_void_p, c_char_p])
+
+# ---- multi-device data plane (include/thincurr_b200.h, block 3)
+_pp = ctypes.POINTER(c_void_p)
+b200_device_alloc = ctypes_subroutine(oftpy_lib.thincurr_b200_device_alloc, [c_int64, c_void_ptr_ptr], c_int)
+b200_device_free = ctypes_subroutine(oftpy_lib.thincurr_b200_device_free, [c_void_p], c_int)
+b200_ipc_export = ctypes_subroutine(oftpy_lib.thincurr_b200_ipc_export, [c_void_p, c_char_p], c_int)
+b200_ipc_open = ctypes_subroutine(oftpy_lib.thincurr_b200_ipc_open, [c_char_p, c_void_ptr_ptr], c_int)
+b200_ipc_close = ctypes_subroutine(oftpy_lib.thincurr_b200_ipc_close, [c_void_p], c_int)
+b200_enable_peer = ctypes_subroutine(oftpy_lib.thincurr_b200_enable_peer, [c_int], c_int)
+b200_Lmat_exchange = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_exchange, [c_void_p, c_int, c_int, c_void_p, c_int64, _pp, c_void_p], c_int)
+b200_Lmat_gather = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_gather, [c_void_p, c_int, c_int, _pp, c_int64, c_void_p, c_int64, c_void_p], c_int)
+b200_rows_to_host = ctypes_subroutine(oftpy_lib.thincurr_b200_rows_to_host, [c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64], c_int)
+b200_Lmat_save_begin = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_save_begin, [c_void_p, c_char_p], c_int)
+b200_Lmat_save_rows = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_save_rows, [c_void_p, c_char_p, c_int, c_int, c_int, c_void_p, c_int64], c_int)
+b200_rows_apply = ctypes_subroutine(oftpy_lib.thincurr_b200_rows_apply, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p], c_int)
+B200_APPLY_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_double_ptr, c_double_ptr)
+b200_lr_eigs = ctypes_subroutine(oftpy_lib.thincurr_b200_lr_eigs,
+    [c_void_p, c_int, c_double, c_int, B200_APPLY_FN, c_void_p, ctypes_numpy_array(float64, 1), ctypes_numpy_array(float64, 2), c_int_ptr], c_int)

@@ -45,7 +45,23 @@ def build(force=False, verbose=False, defs=(), out=None):
     return out or LIB
 
 
+TEST_LIB = os.path.join(HERE, 'libthincurr_b200_test.so')
+
+
+def build_test(force=False):
+    """Test build: the same sources with -DTW_TEST_HOOKS (kernel probes of csrc/tw_probe.cu, the switches that force the
+    rare contraction paths).  Loaded only by tests/ through openfusiontoolkit_b200._testlib; never by the product path."""
+    if not force and os.path.exists(TEST_LIB) and os.path.getmtime(TEST_LIB) >= os.path.getmtime(build()):
+        stale = any(os.path.getmtime(os.path.join(CSRC, f)) > os.path.getmtime(TEST_LIB) for f in os.listdir(CSRC))
+        if not stale:
+            return TEST_LIB
+    return build(defs=('TW_TEST_HOOKS',), out=TEST_LIB)
+
+
 if __name__ == '__main__':
     defs = [a[2:] for a in sys.argv[1:] if a.startswith('-D')]
     outs = [a[2:] for a in sys.argv[1:] if a.startswith('-o')]
+    if '--test' in sys.argv:
+        print('built', build_test(force='--force' in sys.argv))
+        sys.exit(0)
     print('built', build(force='--force' in sys.argv, verbose='-v' in sys.argv, defs=defs, out=outs[0] if outs else None))

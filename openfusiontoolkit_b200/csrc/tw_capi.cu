@@ -9,8 +9,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -58,6 +62,8 @@ struct XmlDoc {
 // ---------------------------------------------------------------------------------------------
 namespace tw {
 
+int capi_fail(const std::string& msg) { return fail(msg); }
+
 void HostBuf::alloc(size_t count, bool zero) {
   if (p && n == count) {  // reuse (rebuilds of the same operator keep the Python view valid)
     if (zero) std::memset(p, 0, count * sizeof(double));
@@ -67,8 +73,11 @@ void HostBuf::alloc(size_t count, bool zero) {
   n = count;
   if (count == 0) return;
   size_t bytes = count * sizeof(double);
-  // pinned memory for matrices up to 16 GiB; beyond that pinning costs more than it saves
-  if (bytes <= (size_t)16 << 30) {
+  // page-locked memory (direct copy-engine target) up to THINCURR_B200_PIN_MAX_GB (default 192 GiB); beyond that, or if
+  // the host refuses to lock that much, a pageable buffer served by the staging threads of HostCopier
+  size_t pin_max = (size_t)192 << 30;
+  if (const char* e = std::getenv("THINCURR_B200_PIN_MAX_GB")) pin_max = (size_t)std::max(0, std::atoi(e)) << 30;
+  if (bytes <= pin_max) {
     if (cudaMallocHost((void**)&p, bytes) == cudaSuccess) {
       pinned = true;
       if (zero) std::memset(p, 0, bytes);
@@ -146,11 +155,39 @@ void shard_rows(const Model& m, int nshards, int shard, int& p0, int& p1, std::v
     for (int j = 0; j < m.n_vcoils; j++) row_ids.push_back(m.np_active + m.nholes + j);
 }
 
+// Bands of a shard: contiguous patch ranges with (nearly) equal row counts.  A band's rows are complete (all columns of
+// this and later shards) as soon as its own tiles and the transposed copies from the earlier bands are done, so the
+// rows of band k can leave the device while band k+1 is being built.
+std::vector<int> band_cuts(const PatchSet& ps, int p0, int p1, int nbands) {
+  std::vector<int> cuts{p0};
+  const int i0 = ps.patch_dof_ptr[p0], i1 = ps.patch_dof_ptr[p1];
+  for (int b = 1; b < nbands; b++) {
+    const long long target = i0 + (long long)(i1 - i0) * b / nbands;
+    int p = cuts.back();
+    while (p < p1 && ps.patch_dof_ptr[p] < target) p++;
+    if (p > cuts.back() && p < p1) cuts.push_back(p);
+  }
+  cuts.push_back(p1);
+  return cuts;
+}
+
+// Number of bands of a single-device build whose rows go to the host: one band costs one extra kernel tail (~ the longest
+// tile), so small builds stay in one piece
+int auto_bands(const PatchSet& ps, int p0, int p1) {
+  if (const char* e = std::getenv("THINCURR_B200_BANDS")) return std::max(1, std::atoi(e));
+  const long long np = p1 - p0;
+  const long long ntiles = np * (np + 1) / 2;
+  return (int)std::max(1LL, std::min(16LL, ntiles / 1200));
+}
+
 // Build the self-inductance rows of one shard on the current device into d_out[nrows][ld]
 // (zeroed here).  Asynchronous on `stream` unless stats are requested.
 // sym: symmetric partition, only the blocks against this and later shards are computed (upper trapezoid)
+// nbands > 1: the shard is built band by band (same tiles, same bits); after band k `band_done(k, r0, r1)` is called with
+// the band's row range [r0, r1) of d_out, whose rows are final once the work enqueued so far on `stream` has run.
 std::string lmat_shard_device(Model& m, int nshards, int shard, double* d_out, long long ld, cudaStream_t stream,
-                              unsigned long long* stats, bool sym) {
+                              unsigned long long* stats, bool sym, int nbands,
+                              const std::function<std::string(int, int, int)>& band_done) {
   int device = 0;
   if (cudaGetDevice(&device) != cudaSuccess) return "No CUDA device available (there is no CPU fallback)";
   std::shared_ptr<DeviceState> ds;
@@ -161,17 +198,51 @@ std::string lmat_shard_device(Model& m, int nshards, int shard, double* d_out, l
   int p0, p1;
   std::vector<int> row_ids;
   shard_rows(m, nshards, shard, p0, p1, row_ids, sym);
-  std::vector<int> row_out(ps.ndof, -1);
-  for (int i = ps.patch_dof_ptr[p0], r = 0; i < ps.patch_dof_ptr[p1]; i++, r++) row_out[i] = r;
-  std::vector<Tile> tiles;
-  build_self_tiles(ps, p0, p1, tiles, sym);
-  if (cudaMemsetAsync(d_out, 0, (size_t)row_ids.size() * ld * sizeof(double), stream) != cudaSuccess)
-    return "cudaMemsetAsync failed on the output block";
-  err = gpu_lmat_tiles(ds->ps, ds->ps, tiles, row_out, true, d_out, ld, stream, stats);
-  if (!err.empty()) return err;
+  const int I0 = ps.patch_dof_ptr[p0];
+  const std::vector<int> cuts = band_cuts(ps, p0, p1, std::max(1, nbands));
+  unsigned long long acc[8] = {0, 0, 0, 0, 0, 0, 0, ~0ull};
+  for (size_t b = 0; b + 1 < cuts.size(); b++) {
+    const int b0 = cuts[b], b1 = cuts[b + 1];
+    const int i0 = ps.patch_dof_ptr[b0], i1 = ps.patch_dof_ptr[b1];
+    double* d_band = d_out + (size_t)(i0 - I0) * ld;
+    std::vector<int> row_out(ps.ndof, -1);
+    for (int i = i0, r = 0; i < i1; i++, r++) row_out[i] = r;
+    std::vector<Tile> tiles;
+    build_self_tiles(ps, b0, b1, tiles, sym, b > 0 ? p0 : -1);
+    if (cudaMemsetAsync(d_band, 0, (size_t)(i1 - i0) * ld * sizeof(double), stream) != cudaSuccess)
+      return "cudaMemsetAsync failed on the output block";
+    unsigned long long st[8] = {0};
+    err = gpu_lmat_tiles(ds->ps, ds->ps, tiles, row_out, true, d_band, ld, stream, stats ? st : nullptr);
+    if (!err.empty()) return err;
+    if (stats) {
+      for (int k = 0; k < 4; k++) acc[k] += st[k];
+      acc[5] += st[4] - st[6];            // kernel time (ns) summed over the bands
+      if (b == 0) acc[6] = st[6];         // start of the first band's kernel
+      acc[4] = st[4];                     // end of the last band's kernel
+      acc[7] = std::min(acc[7], st[7] - st[6]);
+    }
+    if (b > 0) {  // transposed blocks of the earlier bands of this shard (thin_wall.F90:1146-1151)
+      err = gpu_symmetrize_cross(ds->ps, i0, i1, I0, i0, d_band, d_out, ld, stream);
+      if (!err.empty()) return err;
+    }
+    if (band_done) {
+      err = band_done((int)b, i0 - I0, i1 - I0);
+      if (!err.empty()) return err;
+    }
+  }
   if (m.n_vcoils > 0) {
+    const size_t nr0 = (size_t)(ps.patch_dof_ptr[p1] - I0);
+    if (row_ids.size() > nr0 &&
+        cudaMemsetAsync(d_out + nr0 * ld, 0, (row_ids.size() - nr0) * (size_t)ld * sizeof(double), stream) != cudaSuccess)
+      return "cudaMemsetAsync failed on the output block";
     err = gpu_fill_vcoil_block(m, row_ids, d_out, ld, stream);
     if (!err.empty()) return err;
+  }
+  if (stats) {  // [6] -> [4]: summed duration of the band kernels; [7]: earliest first-CTA finish of a band
+    acc[4] = acc[6] + acc[5];
+    acc[7] = acc[6] + acc[7];
+    std::memcpy(stats, acc, sizeof acc);
+    stats[5] = 0;
   }
   return "";
 }
@@ -183,8 +254,11 @@ std::string lmat_shard_device(Model& m, int nshards, int shard, double* d_out, l
 // =============================================================================================
 extern "C" {
 
+static void (*g_abort_callback)(void) = nullptr;
+
 void oftpy_init(int nthreads, bool quiet, const char* input_file, int* slens, void* abort_callback) {
-  (void)nthreads; (void)input_file; (void)abort_callback;
+  (void)nthreads; (void)input_file;
+  g_abort_callback = (void (*)(void))abort_callback;  // installed by the Python layer (_interface.py:90-96)
   if (slens) {
     slens[0] = 4;   // OFT_MPI_PLEN (src/CMakeLists.txt:34-37)
     slens[1] = 80;  // OFT_SLEN
@@ -262,85 +336,305 @@ void thincurr_setup(const char* mesh_file, int np, const double* r_loc, int nc, 
   fill_sizes(*m, sizes);
 }
 
+// Device -> host copies.  Page-locked destinations take the copy engine directly (cudaMemcpyAsync, asynchronous).
+// Pageable ones (a Fortran or numpy array of the caller, or a matrix too large to pin) would turn every
+// cudaMemcpyAsync into a blocking staged copy on the calling thread and serialise the devices, so they are served by a
+// helper thread per device that drains a job queue through a pinned double buffer.
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+class HostCopier {
+ public:
+  explicit HostCopier(int device) : device_(device) {}
+  ~HostCopier() { finish(); }
+  // copy `bytes` from device memory `src` to pageable host memory `dst` once `after` (event, may be null) has completed
+  void push(void* dst, const void* src, size_t bytes, cudaEvent_t after) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      jobs_.push_back(Job{dst, src, bytes, after});
+      if (!started_) {
+        started_ = true;
+        th_ = std::thread([this] { run(); });
+      }
+    }
+    cv_.notify_one();
+  }
+  std::string finish() {
+    if (started_) {
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        done_ = true;
+      }
+      cv_.notify_one();
+      if (th_.joinable()) th_.join();
+      started_ = false;
+    }
+    return err_;
+  }
+
+ private:
+  struct Job {
+    void* dst;
+    const void* src;
+    size_t bytes;
+    cudaEvent_t after;
+  };
+  static constexpr size_t kSlot = (size_t)32 << 20;
+  void run() {
+    void* slot[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    bool ok = cudaSetDevice(device_) == cudaSuccess && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++)
+      ok = cudaMallocHost(&slot[i], kSlot) == cudaSuccess && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) err_ = "Pinned staging buffers for the device->host copy could not be set up";
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return done_ || !jobs_.empty(); });
+        if (jobs_.empty()) break;
+        j = jobs_.front();
+        jobs_.pop_front();
+      }
+      if (!err_.empty()) continue;
+      if (j.after && cudaStreamWaitEvent(st, j.after, 0) != cudaSuccess) err_ = "cudaStreamWaitEvent failed";
+      size_t off = 0, po[2] = {0, 0}, pn[2] = {0, 0};
+      int k = 0;
+      auto flush = [&](int i) {
+        if (!pn[i]) return;
+        if (cudaEventSynchronize(ev[i]) != cudaSuccess) err_ = "Device->host copy failed";
+        else std::memcpy((char*)j.dst + po[i], slot[i], pn[i]);
+        pn[i] = 0;
+      };
+      while (off < j.bytes && err_.empty()) {
+        const size_t n = std::min(kSlot, j.bytes - off);
+        flush(k);
+        if (cudaMemcpyAsync(slot[k], (const char*)j.src + off, n, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaEventRecord(ev[k], st) != cudaSuccess)
+          err_ = std::string("Device->host copy failed: ") + cudaGetErrorString(cudaGetLastError());
+        po[k] = off;
+        pn[k] = n;
+        off += n;
+        k ^= 1;
+      }
+      flush(k);
+      flush(k ^ 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      if (slot[i]) cudaFreeHost(slot[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    if (st) cudaStreamDestroy(st);
+  }
+  int device_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<Job> jobs_;
+  std::thread th_;
+  bool started_ = false, done_ = false;
+  std::string err_;
+};
+
+struct DeviceGuard {  // restores the caller's current device
+  int dev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+      cudaGetLastError();
+      dev = -1;
+    }
+  }
+  ~DeviceGuard() {
+    if (dev >= 0) cudaSetDevice(dev);
+  }
+};
+
+// devices a reference-facing operator call may use: all visible ones (THINCURR_B200_NDEV caps the count), or only the
+// caller's current device when the process is one rank of a one-process-per-GPU job (torchrun / mpirun set LOCAL_RANK) or
+// THINCURR_B200_ONE_DEVICE is set
+static std::vector<int> build_devices() {
+  const int n = visible_devices();
+  std::vector<int> out;
+  const bool one = std::getenv("THINCURR_B200_ONE_DEVICE") || (std::getenv("LOCAL_RANK") && !std::getenv("THINCURR_B200_NDEV"));
+  int cur = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess) {
+    cudaGetLastError();
+    cur = 0;
+  }
+  if (one || n <= 1) {
+    if (n >= 1) out.push_back(cur);
+    return out;
+  }
+  for (int g = 0; g < n; g++) out.push_back(g);
+  return out;
+}
+
+// row-block scratch of the host-buffer entry points, kept between calls (a cudaMalloc/cudaFree pair of tens of GB per
+// call costs more than the copies it serves); released by thincurr_b200_release_device / thincurr_b200_destroy
+static std::string scratch_rows(DeviceState& ds, size_t bytes, double** out) {
+  if (ds.scratch && ds.scratch_bytes >= bytes) {
+    *out = ds.scratch;
+    return "";
+  }
+  if (ds.scratch) cudaFree(ds.scratch);
+  ds.scratch = nullptr;
+  ds.scratch_bytes = 0;
+  if (cudaMalloc((void**)&ds.scratch, std::max<size_t>(bytes, 8)) != cudaSuccess) {
+    cudaGetLastError();
+    return "Device allocation of the row block failed";
+  }
+  ds.scratch_bytes = bytes;
+  *out = ds.scratch;
+  return "";
+}
+
 // full self-inductance matrix into host memory dst[nelems][nelems] (reference layout), rows sharded
-// over all visible devices, each shard copied straight to its place.  With several devices that can read each other's
-// memory the shards are the symmetric ones (upper trapezoid per device, no pair integral evaluated twice) and every
-// device fetches the transposed blocks of the earlier shards over NVLink before its rows go to the host.
+// over the usable devices, each shard copied straight to its place.  One device: the matrix is built in row bands and
+// the rows of a finished band go to the host (copy engine) while the next band is evaluated.  Several devices that can
+// read each other's memory: symmetric shards (upper trapezoid per device, no pair integral evaluated twice); all builds
+// are launched first, then every device fetches the transposed blocks of the earlier shards over NVLink
+// (symmetrize_cross_kernel on peer memory) and sends its rows to the host.
 static std::string lmat_full_host(Model& m, double* dst) {
   const size_t N = (size_t)m.nelems;
-  int ndev = visible_devices();
-  if (ndev < 1) return "No CUDA device available (the B200 backend has no CPU fallback)";
+  DeviceGuard guard;
+  std::vector<int> devs_ids = build_devices();
+  if (devs_ids.empty()) return "No CUDA device available (the B200 backend has no CPU fallback)";
   std::string err = ensure_plan(m);
   if (!err.empty()) return err;
-  ndev = std::min(ndev, std::max(1, m.plan->ps.npatch));
+  const PatchSet& ps = m.plan->ps;
+  int ndev = std::min((int)devs_ids.size(), std::max(1, ps.npatch));
+  devs_ids.resize(ndev);
   bool sym = ndev > 1 && m.n_vcoils == 0 && !std::getenv("THINCURR_B200_FULL_ROWS");
   for (int g = 1; g < ndev && sym; g++)
     for (int s = 0; s < g && sym; s++) {
       int can = 0;
-      if (cudaDeviceCanAccessPeer(&can, g, s) != cudaSuccess || !can) sym = false;
+      if (cudaDeviceCanAccessPeer(&can, devs_ids[g], devs_ids[s]) != cudaSuccess || !can) sym = false;
     }
+  cudaGetLastError();
   struct Dev {
     double* d = nullptr;
-    cudaStream_t s = nullptr;
+    cudaStream_t s = nullptr, cs = nullptr;  // build stream, copy stream
     cudaEvent_t built = nullptr;
+    std::vector<cudaEvent_t> band_ev;
     std::vector<int> rows;
     int i0 = 0, i1 = 0;  // internal DOF range of the rows
     std::shared_ptr<DeviceState> ds;
   };
   std::vector<Dev> devs(ndev);
-  const PatchSet& ps = m.plan->ps;
-  for (int g = 0; g < ndev && err.empty(); g++) {
-    cudaSetDevice(g);
-    int p0, p1;
-    shard_rows(m, ndev, g, p0, p1, devs[g].rows, sym);
-    devs[g].i0 = ps.patch_dof_ptr[p0];
-    devs[g].i1 = ps.patch_dof_ptr[p1];
-    if (devs[g].rows.empty()) continue;
-    if (cudaStreamCreate(&devs[g].s) != cudaSuccess || cudaMalloc((void**)&devs[g].d, devs[g].rows.size() * N * 8) != cudaSuccess) {
-      err = std::string("Device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
-      break;
+  const bool pinned = is_pinned(dst);
+  std::vector<std::unique_ptr<HostCopier>> copier(ndev);
+  // rows [r0,r1) of device g to their place in the reference layout Lmat(:,row), runs of consecutive reference ids as
+  // one copy; the copies wait for `after` (an event of the build stream)
+  auto rows_to_host = [&](int g, int r0, int r1, cudaEvent_t after) -> std::string {
+    Dev& D = devs[g];
+    if (pinned && cudaStreamWaitEvent(D.cs, after, 0) != cudaSuccess) return "cudaStreamWaitEvent failed";
+    if (!pinned && !copier[g]) copier[g].reset(new HostCopier(devs_ids[g]));
+    for (int r = r0; r < r1;) {
+      int e = r + 1;
+      while (e < r1 && D.rows[e] == D.rows[e - 1] + 1) e++;
+      double* to = dst + (size_t)D.rows[r] * N;
+      const double* from = D.d + (size_t)r * N;
+      const size_t bytes = (size_t)(e - r) * N * 8;
+      if (!pinned) copier[g]->push(to, from, bytes, after);
+      else if (cudaMemcpyAsync(to, from, bytes, cudaMemcpyDeviceToHost, D.cs) != cudaSuccess)
+        return std::string("Device->host copy failed: ") + cudaGetErrorString(cudaGetLastError());
+      r = e;
     }
-    err = lmat_shard_device(m, ndev, g, devs[g].d, (long long)N, devs[g].s, nullptr, sym);
-    if (sym && err.empty()) {
-      err = ensure_device(m, g, devs[g].ds);
-      cudaEventCreateWithFlags(&devs[g].built, cudaEventDisableTiming);
-      cudaEventRecord(devs[g].built, devs[g].s);
-      for (int s = 0; s < g && err.empty(); s++) {  // transposed blocks of the earlier shards
+    return "";
+  };
+  auto ck = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && err.empty()) err = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaSuccess;
+  };
+  // ---- phase 1: every device starts building its shard
+  for (int g = 0; g < ndev && err.empty(); g++) {
+    Dev& D = devs[g];
+    if (!ck(cudaSetDevice(devs_ids[g]), "cudaSetDevice")) break;
+    int p0, p1;
+    shard_rows(m, ndev, g, p0, p1, D.rows, sym);
+    D.i0 = ps.patch_dof_ptr[p0];
+    D.i1 = ps.patch_dof_ptr[p1];
+    if (D.rows.empty()) continue;
+    if (!ck(cudaStreamCreateWithFlags(&D.s, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !ck(cudaStreamCreateWithFlags(&D.cs, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !ck(cudaEventCreateWithFlags(&D.built, cudaEventDisableTiming), "cudaEventCreate"))
+      break;
+    err = ensure_device(m, devs_ids[g], D.ds);
+    if (!err.empty()) break;
+    err = D.ds->ps.upload_from(ps);  // the call's inputs: host model -> device, every call
+    if (!err.empty()) break;
+    err = scratch_rows(*D.ds, D.rows.size() * N * 8, &D.d);  // row block kept between calls
+    if (!err.empty()) break;
+    const int nb = ndev == 1 ? auto_bands(ps, p0, p1) : 1;
+    auto band_done = [&, g](int, int r0, int r1) -> std::string {
+      // (single device) the band's rows are final: hand them to the copy engine behind an event
+      cudaEvent_t ev = nullptr;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return "cudaEventCreate failed";
+      devs[g].band_ev.push_back(ev);
+      if (cudaEventRecord(ev, devs[g].s) != cudaSuccess) return "cudaEventRecord failed";
+      return rows_to_host(g, r0, r1, ev);
+    };
+    if (ndev == 1 && m.n_vcoils == 0) {
+      err = lmat_shard_device(m, ndev, g, D.d, (long long)N, D.s, nullptr, sym, nb, band_done);
+    } else {
+      err = lmat_shard_device(m, ndev, g, D.d, (long long)N, D.s, nullptr, sym);
+      if (err.empty()) ck(cudaEventRecord(D.built, D.s), "cudaEventRecord");
+    }
+  }
+  // ---- phase 2: transposed blocks of the earlier shards from peer memory, then the rows go to the host
+  if (!(ndev == 1 && m.n_vcoils == 0)) {
+    for (int g = 0; g < ndev && err.empty(); g++) {
+      Dev& D = devs[g];
+      if (!D.d) continue;
+      if (!ck(cudaSetDevice(devs_ids[g]), "cudaSetDevice")) break;
+      for (int s = 0; s < g && sym && err.empty(); s++) {
         if (!devs[s].d) continue;
-        cudaError_t pe = cudaDeviceEnablePeerAccess(s, 0);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(devs_ids[s], 0);
         if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
-          err = std::string("cudaDeviceEnablePeerAccess failed: ") + cudaGetErrorString(pe);
+          ck(pe, "cudaDeviceEnablePeerAccess");
           break;
         }
         cudaGetLastError();
-        cudaStreamWaitEvent(devs[g].s, devs[s].built, 0);
-        err = gpu_symmetrize_cross(devs[g].ds->ps, devs[g].i0, devs[g].i1, devs[s].i0, devs[s].i1, devs[g].d, devs[s].d, (long long)N, devs[g].s);
+        if (!ck(cudaStreamWaitEvent(D.s, devs[s].built, 0), "cudaStreamWaitEvent")) break;
+        err = gpu_symmetrize_cross(D.ds->ps, D.i0, D.i1, devs[s].i0, devs[s].i1, D.d, devs[s].d, (long long)N, D.s);
       }
     }
-    // rows go straight to their place in the reference layout Lmat(:,row)
-    for (size_t r = 0; r < devs[g].rows.size() && err.empty();) {
-      size_t r1 = r + 1;
-      while (r1 < devs[g].rows.size() && devs[g].rows[r1] == devs[g].rows[r1 - 1] + 1) r1++;
-      if (cudaMemcpyAsync(dst + (size_t)devs[g].rows[r] * N, devs[g].d + r * N, (r1 - r) * N * 8, cudaMemcpyDeviceToHost,
-                          devs[g].s) != cudaSuccess)
-        err = std::string("Device->host copy failed: ") + cudaGetErrorString(cudaGetLastError());
-      r = r1;
+    for (int g = 0; g < ndev && err.empty(); g++) {
+      Dev& D = devs[g];
+      if (!D.d) continue;
+      if (!ck(cudaSetDevice(devs_ids[g]), "cudaSetDevice")) break;
+      cudaEvent_t ev = nullptr;
+      if (!ck(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate")) break;
+      D.band_ev.push_back(ev);
+      if (!ck(cudaEventRecord(ev, D.s), "cudaEventRecord")) break;
+      err = rows_to_host(g, 0, (int)D.rows.size(), ev);
     }
   }
   for (int g = 0; g < ndev; g++) {
-    cudaSetDevice(g);
-    if (devs[g].s) {
-      cudaError_t ce = cudaStreamSynchronize(devs[g].s);
-      if (ce != cudaSuccess && err.empty()) err = std::string("Kernel execution failed: ") + cudaGetErrorString(ce);
+    if (!devs[g].s) continue;
+    cudaSetDevice(devs_ids[g]);
+    cudaError_t ce = cudaStreamSynchronize(devs[g].s);
+    if (ce == cudaSuccess && devs[g].cs) ce = cudaStreamSynchronize(devs[g].cs);
+    if (ce != cudaSuccess && err.empty()) err = std::string("Kernel execution failed: ") + cudaGetErrorString(ce);
+    if (copier[g]) {
+      std::string ce2 = copier[g]->finish();
+      if (err.empty()) err = ce2;
     }
   }
   for (int g = 0; g < ndev; g++) {  // (all devices are done reading each other's blocks)
-    cudaSetDevice(g);
+    cudaSetDevice(devs_ids[g]);
     if (devs[g].s) cudaStreamDestroy(devs[g].s);
+    if (devs[g].cs) cudaStreamDestroy(devs[g].cs);
     if (devs[g].built) cudaEventDestroy(devs[g].built);
-    if (devs[g].d) cudaFree(devs[g].d);
+    for (cudaEvent_t e : devs[g].band_ev) cudaEventDestroy(e);
   }
-  cudaSetDevice(0);
+  cudaGetLastError();
   return err;
 }
 
@@ -489,6 +783,92 @@ void thincurr_set_eta(void* tw_ptr, const double* eta_surf, const double* eta_vo
   }
 }
 
+// ---- remaining names the reference's Python layer binds at import (ThinCurr/_interface.py:21-119) ---------------------
+// Cheap model queries are answered natively; the dense apply and the iterative eigen solve run on the device
+// (tw_solve.cu); everything that belongs to the reference's downstream solvers / plotting returns an error through
+// error_str (or, for the wrappers without one, prints it and calls the abort callback oftpy_init received, the
+// reference's oft_abort convention).
+static const char* kNotProvided = "is not provided by the B200 operator-build backend (use the reference liboftpy for this step)";
+static void no_errstr_abort(const char* name) {
+  std::fprintf(stderr, "ERROR: %s %s\n", name, kNotProvided);
+  if (g_abort_callback) g_abort_callback();
+}
+// names the reference's base package binds at import (OpenFUSIONToolkit/_interface.py:114-132); mesh objects of the
+// other physics modules are not part of this backend
+void oft_setup_smesh(int, int, const double*, int, int, const int*, const int*, int*, void** mesh_ptr) {
+  if (mesh_ptr) *mesh_ptr = nullptr;
+  no_errstr_abort("oft_setup_smesh");
+}
+void oft_smesh_get(void*, int*, int*, double**, int*, int*, int**, int**, int*, char* error_str) {
+  set_err(error_str, std::string("oft_smesh_get ") + kNotProvided);
+}
+void oft_setup_vmesh(int, const double*, int, int, const int*, const int*, int*, void** mesh_ptr) {
+  if (mesh_ptr) *mesh_ptr = nullptr;
+  no_errstr_abort("oft_setup_vmesh");
+}
+void oft_vmesh_get(void*, int*, double**, int*, int*, int**, int**, int*, char* error_str) {
+  set_err(error_str, std::string("oft_vmesh_get ") + kNotProvided);
+}
+void dump_cov(void) {}
+void thincurr_scale_va(void* tw_ptr, double* vals, bool div_flag) {  // thincurr_f.F90:453-466
+  Model& m = *(Model*)tw_ptr;
+  for (int i = 0; i < m.np; i++) vals[i] = div_flag ? vals[i] / m.va[i] : vals[i] * m.va[i];
+}
+void thincurr_get_eta_vol(void* tw_ptr, double* eta_vol, char* error_str) {  // thincurr_f.F90:721-731
+  set_err(error_str, "");
+  Model& m = *(Model*)tw_ptr;
+  for (int i = 0; i < m.nreg; i++) eta_vol[i] = m.eta_vol[i] * kMu0;
+}
+void thincurr_get_thickness(void* tw_ptr, double* thickness, char* error_str) {  // thincurr_f.F90:887-902
+  set_err(error_str, "");
+  Model& m = *(Model*)tw_ptr;
+  for (int i = 0; i < m.nreg; i++) thickness[i] = m.thickness[i];
+}
+void thincurr_setup_io(void*, const char*, bool, bool, char* error_str) { set_err(error_str, std::string("thincurr_setup_io ") + kNotProvided); }
+void thincurr_recon_curr(void*, const double*, double*, int) { no_errstr_abort("thincurr_recon_curr"); }
+void thincurr_recon_field(void*, const double*, const double*, double*, void*) { no_errstr_abort("thincurr_recon_field"); }
+void thincurr_save_field(void*, const double*, const char*) { no_errstr_abort("thincurr_save_field"); }
+void thincurr_save_scalar(void*, const double*, const char*) { no_errstr_abort("thincurr_save_scalar"); }
+void thincurr_curr_regmat(void*, double*, char* error_str) { set_err(error_str, std::string("thincurr_curr_regmat ") + kNotProvided); }
+void thincurr_freq_response(void*, bool, int, double, double*, void*, char* error_str) {
+  set_err(error_str, std::string("thincurr_freq_response ") + kNotProvided);
+}
+void thincurr_time_domain(void*, bool, double, int, double, double, bool, int, int, const double*, void*, int, const double*, int, const double*,
+                          bool, void*, void*, char* error_str) {
+  set_err(error_str, std::string("thincurr_time_domain ") + kNotProvided);
+}
+void thincurr_time_domain_plot(void*, bool, bool, int, int, void*, const double*, int, void*, char* error_str) {
+  set_err(error_str, std::string("thincurr_time_domain_plot ") + kNotProvided);
+}
+void thincurr_reduce_model(void*, const char*, int, const double*, bool, void*, void*, char* error_str) {
+  set_err(error_str, std::string("thincurr_reduce_model ") + kNotProvided);
+}
+void thincurr_cross_eval(void*, void*, int, const double*, double*, char* error_str) {
+  set_err(error_str, std::string("thincurr_cross_eval ") + kNotProvided);
+}
+void thincurr_apply_Lmat(void* tw_ptr, double* vals, void* hodlr_ptr) {
+  Model& m = *(Model*)tw_ptr;
+  if (hodlr_ptr || !m.Lmat.p) return no_errstr_abort("thincurr_apply_Lmat without a dense inductance matrix");
+  std::string err = gpu_apply_host_matrix(m.Lmat.p, (size_t)m.nelems, (size_t)m.nelems, vals);
+  if (!err.empty()) {
+    std::fprintf(stderr, "ERROR: thincurr_apply_Lmat: %s\n", err.c_str());
+    if (g_abort_callback) g_abort_callback();
+  }
+}
+void thincurr_eigenvalues(void* tw_ptr, bool direct, int neigs, double* eig_vals, double* eig_vec, void* hodlr_ptr, char* error_str) {
+  // thincurr_f.F90:975-1013.  Iterative path only (lr_eigenmodes_arpack, thin_wall_solvers.F90:119-224): Lanczos on the
+  // device-resident L with R factorised on the host; the dense LAPACK path (direct=true) stays with the reference.
+  Model& m = *(Model*)tw_ptr;
+  if (m.nelems <= 0) return set_err(error_str, "Invalid ThinCurr model, may not be setup yet");
+  if (hodlr_ptr) return set_err(error_str, "HODLR compression is not provided by the B200 dense backend");
+  if (!m.Lmat.p) return set_err(error_str, "Inductance matrix required, but not computed");
+  if (m.R_kr.empty()) return set_err(error_str, "Resistance matrix required, but not computed");
+  if (direct) return set_err(error_str, std::string("thincurr_eigenvalues(direct=True) ") + kNotProvided);
+  set_err(error_str, "");
+  std::string err = gpu_lr_eigenmodes_host(m, neigs, eig_vals, eig_vec);
+  if (!err.empty()) set_err(error_str, err);
+}
+
 // =============================================================================================
 // Block 2: flat / sharded interface
 // =============================================================================================
@@ -615,6 +995,27 @@ int thincurr_b200_plan(void* tw_ptr, int nshards, int shard, int* nrows) {
   return 0;
 }
 
+int thincurr_b200_plan_chunks(void* tw_ptr, int* patch_chunk_ptr, double* chunk_info) {
+  // introspection: chunk_info[nchunk][6] = centre (3), radius, longest edge, cells; patch_chunk_ptr[npatch+1]
+  Model& m = *(Model*)tw_ptr;
+  std::string err = ensure_plan(m);
+  if (!err.empty()) return fail(err);
+  const PatchSet& ps = m.plan->ps;
+  if (patch_chunk_ptr) std::memcpy(patch_chunk_ptr, ps.patch_chunk_ptr.data(), ps.patch_chunk_ptr.size() * sizeof(int));
+  if (chunk_info)
+    for (int c = 0; c < ps.nchunk; c++) {
+      const ChunkMeta& cm = ps.chunks[c];
+      double* o = chunk_info + 6 * (size_t)c;
+      o[0] = cm.cx; o[1] = cm.cy; o[2] = cm.cz; o[3] = cm.rad; o[4] = cm.emax; o[5] = cm.ncell;
+    }
+  return 0;
+}
+
+int64_t thincurr_b200_model_bytes(void* tw_ptr) {
+  Model& m = *(Model*)tw_ptr;
+  return m.dev.empty() ? 0 : (int64_t)m.dev[0]->ps.bytes;
+}
+
 int thincurr_b200_plan_info(void* tw_ptr, int64_t* info) {
   Model& m = *(Model*)tw_ptr;
   std::string err = ensure_plan(m);
@@ -684,7 +1085,8 @@ int thincurr_b200_Lmat_shard_sym(void* tw_ptr, int nshards, int shard, double* d
 }
 
 int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* h_out, int64_t ld, int64_t* stats) {
-  // end-to-end: (re)upload the model, build the rows, bring them back to host memory
+  // end-to-end: upload the model, build the rows band by band, bring every finished band back to host memory
+  // (copy engine, overlapped with the evaluation of the next band)
   Model& m = *(Model*)tw_ptr;
   const bool trace = std::getenv("THINCURR_B200_TRACE") != nullptr;
   auto now = [] { return std::chrono::steady_clock::now(); };
@@ -692,36 +1094,79 @@ int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* 
     return std::chrono::duration<double, std::milli>(b - a).count();
   };
   auto t0 = now();
-  drop_device_state(m);
-  m.plan.reset();
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess) return fail("No CUDA device available (there is no CPU fallback)");
   std::string err = ensure_plan(m);
+  if (!err.empty()) return fail(err);
+  std::shared_ptr<DeviceState> ds;
+  err = ensure_device(m, device, ds);
+  if (!err.empty()) return fail(err);
+  err = ds->ps.upload_from(m.plan->ps);  // the step's inputs: host model -> device, every call
   if (!err.empty()) return fail(err);
   auto t1 = now();
   int p0, p1;
   std::vector<int> rows;
   shard_rows(m, nshards, shard, p0, p1, rows);
   double* d = nullptr;
-  size_t bytes = rows.size() * (size_t)ld * 8;
-  if (cudaMalloc((void**)&d, std::max<size_t>(bytes, 8)) != cudaSuccess) return fail("Device allocation failed");
+  const size_t bytes = rows.size() * (size_t)ld * 8;
+  err = scratch_rows(*ds, bytes, &d);
+  if (!err.empty()) return fail(err);
   auto t2 = now();
-  unsigned long long st[8] = {0};
-  err = lmat_shard_device(m, nshards, shard, d, ld, 0, stats ? st : nullptr);
-  if (err.empty() && cudaDeviceSynchronize() != cudaSuccess) err = std::string("Kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+  cudaStream_t sb = nullptr, sc = nullptr;
+  if (cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking) != cudaSuccess)
+    return fail("cudaStreamCreate failed");
+  const bool pinned = is_pinned(h_out);
+  HostCopier copier(device);
+  std::vector<cudaEvent_t> evs;
+  auto band_done = [&](int, int r0, int r1) -> std::string {
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return "cudaEventCreate failed";
+    evs.push_back(ev);
+    if (cudaEventRecord(ev, sb) != cudaSuccess) return "cudaEventRecord failed";
+    const size_t off = (size_t)r0 * ld, nb = (size_t)(r1 - r0) * ld * 8;
+    if (!pinned) {
+      copier.push(h_out + off, d + off, nb, ev);
+      return "";
+    }
+    if (cudaStreamWaitEvent(sc, ev, 0) != cudaSuccess || cudaMemcpyAsync(h_out + off, d + off, nb, cudaMemcpyDeviceToHost, sc) != cudaSuccess)
+      return std::string("Device->host copy failed: ") + cudaGetErrorString(cudaGetLastError());
+    return "";
+  };
+  // (device-side evaluation counters would force a stream synchronisation per band: not collected on this path)
+  const int nb = m.n_vcoils == 0 ? auto_bands(m.plan->ps, p0, p1) : 1;
+  if (m.n_vcoils == 0) {
+    err = lmat_shard_device(m, nshards, shard, d, ld, sb, nullptr, false, nb, band_done);
+  } else {  // V-coil rows and columns are filled after the tiles: one copy of the finished block
+    err = lmat_shard_device(m, nshards, shard, d, ld, sb, nullptr, false);
+    if (err.empty()) err = band_done(0, 0, (int)rows.size());
+  }
   auto t3 = now();
-  if (err.empty() && cudaMemcpy(h_out, d, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
-    err = std::string("Device->host copy failed: ") + cudaGetErrorString(cudaGetLastError());
+  if (cudaStreamSynchronize(sb) != cudaSuccess && err.empty()) err = std::string("Kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+  if (cudaStreamSynchronize(sc) != cudaSuccess && err.empty()) err = std::string("Device->host copy failed: ") + cudaGetErrorString(cudaGetLastError());
+  {
+    std::string ce = copier.finish();
+    if (err.empty()) err = ce;
+  }
   auto t4 = now();
-  cudaFree(d);
-  auto t5 = now();
+  for (cudaEvent_t e : evs) cudaEventDestroy(e);
+  cudaStreamDestroy(sb);
+  cudaStreamDestroy(sc);
   if (trace)
-    std::fprintf(stderr, "[Lmat_shard_host] plan %.1f ms, alloc %.1f, upload+build %.1f, d2h %.1f (%.2f GB), free %.1f\n", ms(t0, t1), ms(t1, t2),
-                 ms(t2, t3), ms(t3, t4), bytes * 1e-9, ms(t4, t5));
+    std::fprintf(stderr, "[Lmat_shard_host] plan+upload %.1f ms, scratch %.1f, enqueue %.1f (%d bands), drain %.1f (%.2f GB, %s)\n", ms(t0, t1),
+                 ms(t1, t2), ms(t2, t3), nb, ms(t3, t4), bytes * 1e-9, pinned ? "pinned" : "pageable");
   if (!err.empty()) return fail(err);
   if (stats) {
-    for (int k = 0; k < 8; k++) stats[k] = (int64_t)st[k];
-    stats[5] = m.dev.empty() ? 0 : (int64_t)m.dev[0]->ps.bytes;  // host->device bytes of the model upload
-    stats[6] = (int64_t)bytes;                                   // device->host bytes
+    for (int k = 0; k < 8; k++) stats[k] = 0;
+    stats[4] = nb;
+    stats[5] = (int64_t)ds->ps.bytes;  // host->device bytes of the model upload
+    stats[6] = (int64_t)bytes;         // device->host bytes
   }
+  return 0;
+}
+
+int thincurr_b200_release_device(void* tw_ptr) {
+  if (!tw_ptr) return 0;
+  drop_device_state(*(Model*)tw_ptr);
   return 0;
 }
 

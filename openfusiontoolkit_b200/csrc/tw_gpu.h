@@ -29,6 +29,11 @@ struct DevicePatchSet {
 struct DeviceState {
   int device = 0;
   DevicePatchSet ps;
+  double* scratch = nullptr;  // row block of the host-buffer entry points, kept between calls
+  size_t scratch_bytes = 0;
+  ~DeviceState() {
+    if (scratch) cudaFree(scratch);
+  }
 };
 
 std::string gpu_init_constants();

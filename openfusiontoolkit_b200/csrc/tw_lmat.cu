@@ -1391,8 +1391,11 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   a.scale = 1.0 / (4.0 * kPi);
   a.self = self ? 1 : 0;
   a.fast_lim = 64;
+  a.debug_skip = 0;
+#ifdef TW_TEST_HOOKS  // test / tuning build only (libthincurr_b200_test.so): force the rare drain paths, skip phases
   if (const char* e = std::getenv("THINCURR_B200_DRAIN_LIMIT")) a.fast_lim = std::atoi(e) >= 64 ? 64 : (std::atoi(e) >= 32 ? 32 : 0);
   a.debug_skip = std::getenv("THINCURR_B200_DEBUG_SKIP") ? std::atoi(std::getenv("THINCURR_B200_DEBUG_SKIP")) : 0;
+#endif
   a.stats = d_stats;
   int dev = 0, nsm = 148;
   CK(cudaGetDevice(&dev));

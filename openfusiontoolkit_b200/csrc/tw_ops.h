@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -11,12 +12,17 @@
 namespace tw {
 
 int visible_devices();
+// records the message returned by thincurr_b200_last_error(); returns 1
+int capi_fail(const std::string& msg);
 std::string ensure_plan(Model& m);
 std::string ensure_device(Model& m, int device, std::shared_ptr<DeviceState>& out);
 void drop_device_state(Model& m);
 void shard_rows(const Model& m, int nshards, int shard, int& p0, int& p1, std::vector<int>& row_ids, bool sym = false);
+std::vector<int> band_cuts(const PatchSet& ps, int p0, int p1, int nbands);
+int auto_bands(const PatchSet& ps, int p0, int p1);
 std::string lmat_shard_device(Model& m, int nshards, int shard, double* d_out, long long ld, cudaStream_t stream,
-                              unsigned long long* stats, bool sym = false);
+                              unsigned long long* stats, bool sym = false, int nbands = 1,
+                              const std::function<std::string(int, int, int)>& band_done = nullptr);
 
 // V-coil rows/columns of L from Ael2coil / Acoil2coil (thin_wall.F90:1128-1145), scaled by 1/4pi
 std::string gpu_fill_vcoil_block(const Model& m, const std::vector<int>& row_ids, double* d_out, long long ld,
@@ -30,6 +36,13 @@ std::string gpu_bmat(Model& m);
 std::string bel_shard_device(Model& m, int nshards, int shard, double* d_out, cudaStream_t stream);
 // mutual inductance between two models (tw_compute_LmatDirect with col_model, :887-1186)
 std::string gpu_cross_coupling(Model& m1, Model& m2, double* Mmat_host);
+// dense apply / leading L/R eigenmodes (tw_solve.cu)
+std::string gpu_rows_apply(const double* d_rows, long long ld, int nrows, int n, const double* d_x, double* d_y, cudaStream_t stream);
+std::string gpu_apply_host_matrix(const double* A, size_t nrows, size_t n, double* vals);
+std::string gpu_lr_eigenmodes_host(Model& m, int neigs, double* eig_vals, double* eig_vec);
+std::string lr_eigs_lanczos(int n, const int* kr, const int* lc, const double* rv, int neigs, double tol, int max_dim,
+                            const std::function<std::string(const double*, double*)>& apply_L, double* eig_vals, double* eig_vec,
+                            int* iters_out);
 // iquad histogram + visited-pair count of the reference loop nest
 std::string gpu_pair_stats(Model& m, int64_t* hist, int64_t* visited);
 

@@ -181,6 +181,16 @@ std::string build_patches(const Model& m, int P, PatchSet& ps) {
             r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
           }
         cm.rad = std::sqrt(r2) * (1.0 + 1e-12);
+        double e2 = 0.0;
+        for (int s = 0; s < cm.ncell; s++)
+          for (int k = 0; k < 3; k++) {
+            const int k1 = (k + 1) % 3;
+            double dx = ps.geom[g0 + (size_t)(k * 3) * kCH + s] - ps.geom[g0 + (size_t)(k1 * 3) * kCH + s],
+                   dy = ps.geom[g0 + (size_t)(k * 3 + 1) * kCH + s] - ps.geom[g0 + (size_t)(k1 * 3 + 1) * kCH + s],
+                   dz = ps.geom[g0 + (size_t)(k * 3 + 2) * kCH + s] - ps.geom[g0 + (size_t)(k1 * 3 + 2) * kCH + s];
+            e2 = std::max(e2, dx * dx + dy * dy + dz * dz);
+          }
+        cm.emax = std::sqrt(e2) * (1.0 + 1e-12);
       }
       auto& L = by_chunk[ch];
       // local DOFs in ascending reference id: neighbouring lanes of the kernel's write-out touch neighbouring columns
@@ -324,7 +334,7 @@ void shard_range_sym(const PatchSet& ps, int nshards, int shard, int& p0, int& p
   p1 = cut(shard + 1);
 }
 
-void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles, bool upper_only) {
+void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles, bool upper_only, int skip_lo) {
   tiles.clear();
   auto balls = patch_balls(ps);
   double h = mean_cell_size(ps);
@@ -339,6 +349,7 @@ void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& til
       bool owned = pb >= p0 && pb < p1;
       if (owned && pb < pa) continue;  // produced by the mirror write of tile (pb,pa)
       if (upper_only && !owned && pb < pa) continue;  // transposed block of an earlier shard (exchanged afterwards)
+      if (skip_lo >= 0 && pb >= skip_lo && pb < p0) continue;  // rows of an earlier band of the same device (copied afterwards)
       Tile t;
       t.flags = 0;
       if (!owned && pb < pa) {

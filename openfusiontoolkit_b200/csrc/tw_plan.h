@@ -41,6 +41,7 @@ struct ChunkMeta {
   int inc_off;  // offset of this chunk's incidence list
   double cx, cy, cz;  // centre of the bounding box of the chunk's vertices
   double rad;         // radius of the bounding sphere around that centre
+  double emax;        // longest triangle edge of the chunk's cells (bounds dl_max - dl_min of a cell pair by emax_I + emax_J)
 };
 
 // Patch decomposition of ONE model (row or column side).
@@ -87,7 +88,9 @@ void shard_range(const PatchSet& ps, int nshards, int shard, int& p0, int& p1);
 void shard_range_sym(const PatchSet& ps, int nshards, int shard, int& p0, int& p1);
 // Tiles of a self-inductance build for row patches [p0,p1)
 // upper_only: skip the tiles against earlier (unowned) patches
-void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles, bool upper_only = false);
+// skip_lo >= 0: also skip the tiles against patches [skip_lo, p0) -- the rows of earlier bands of the same build, whose
+// transposed blocks are copied into place afterwards (banded builds, tw_capi.cu)
+void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles, bool upper_only = false, int skip_lo = -1);
 // Tiles of a mutual build (all row patches x all column patches)
 void build_mutual_tiles(const PatchSet& rows, const PatchSet& cols, std::vector<Tile>& tiles);
 

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/thincurr_b200.h"
+#include "tw_probe.h"
 #include "tw_device.cuh"
 #include "tw_gpu.h"
 #include "tw_ops.h"

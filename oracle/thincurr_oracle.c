@@ -137,6 +137,9 @@ double tco_pair_T(const double pts_i[3][3], double area_i, const double pts_j[3]
                   double area_j, int *iquad_out) {
   double dl_min = 1.e99;
   double dl_max = sqrt(fmax(area_i, area_j) * 2.0);
+#ifdef TCO_SIMD /* CPU-baseline build only: the reference's `!$omp simd ... reduction` (thin_wall.F90:1047) */
+#pragma omp simd reduction(max : dl_max) reduction(min : dl_min)
+#endif
   for (int ii = 0; ii < 3; ii++)
     for (int jj = 0; jj < 3; jj++) {
       double dx = pts_i[ii][0] - pts_j[jj][0], dy = pts_i[ii][1] - pts_j[jj][1],
@@ -158,6 +161,10 @@ double tco_pair_T(const double pts_i[3][3], double area_i, const double pts_j[3]
     }
     tmp = tmp * area_j;
   } else {
+#ifdef TCO_SIMD /* CPU-baseline build only: `!$omp simd collapse(1) private(pt_i,pt_j) reduction(+:tmp)` (thin_wall.F90:1070);
+                   the parity oracle keeps the sequential summation order */
+#pragma omp simd reduction(+ : tmp)
+#endif
     for (int ii = 0; ii < nq; ii++) {
       double pt_i[3];
       quad_point(iquad, ii, pts_i, pt_i);

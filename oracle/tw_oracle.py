@@ -26,14 +26,33 @@ MU0 = np.pi * 4.e-7
 TRI_ED = ((2, 1), (0, 2), (1, 0))  # trimesh_type.F90:34 tri_ed (0-based)
 
 
-def build(force=False):
+# CPU-baseline variants of the same source (bench.py only; the parity oracle is always the default build):
+#   simd  : reference flags + the reference's `!$omp simd` loops (thin_wall.F90:1047,1070) enabled (-DTCO_SIMD)
+#   tuned : -O3 -march=native on top of that ("what a tuned CPU build of the same loop nest reaches")
+_VARIANTS = {None: ['-O2'], 'simd': ['-O2', '-DTCO_SIMD'], 'tuned': ['-O3', '-march=native', '-DTCO_SIMD']}
+
+
+def build(force=False, variant=None):
     """Compile the C restatement with the reference's release flags (-O2 + OpenMP)."""
     src = os.path.join(_HERE, 'thincurr_oracle.c')
     hdr = os.path.join(_HERE, 'quad_tables.h')
-    if (not force) and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        return _SO
-    subprocess.check_call(['gcc', '-O2', '-fopenmp', '-fPIC', '-shared', '-std=c11', '-o', _SO, src, '-lm'])
-    return _SO
+    so = _SO if variant is None else _SO.replace('.so', '_%s.so' % variant)
+    if (not force) and os.path.exists(so) and os.path.getmtime(so) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return so
+    subprocess.check_call(['gcc'] + _VARIANTS[variant] + ['-fopenmp', '-fPIC', '-shared', '-std=c11', '-o', so, src, '-lm'])
+    return so
+
+
+def lmat_sample(model, i_begin, i_end, out, variant=None, nthreads=None):
+    """bench.py: the tw_compute_LmatDirect loop over row cells [i_begin, i_end) with a CPU-baseline build variant and an
+    explicit OpenMP thread count; returns the number of visited pairs."""
+    L = ctypes.CDLL(build(variant=variant))
+    L.tco_lmat_direct.restype = ctypes.c_longlong
+    L.tco_lmat_direct.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    if nthreads:
+        L.tco_set_num_threads(int(nthreads))
+    return L.tco_lmat_direct(ctypes.byref(model.c), None, out.ctypes.data_as(ctypes.c_void_p), None, None, int(i_begin), int(i_end), 0, None)
 
 
 class _CModel(ctypes.Structure):

@@ -1,7 +1,8 @@
 """Kernel-level GPU parity: the device pair integral T(i,j), the order selection and the analytic
 potential, evaluated by the same device functions the operator kernels use, against the oracle's
 tco_pair_T / tco_phipot (thin_wall.F90:1044-1083, :1934-1985) on seeded random pairs of the
-reference's own test meshes.  Tolerances: order selection bit-exact (integer); T within 2e-14
+reference's own test meshes.  The probes live in the TEST build of the library
+(libthincurr_b200_test.so, -DTW_TEST_HOOKS: same sources, same device functions), not in the product library.  Tolerances: order selection bit-exact (integer); T within 2e-14
 relative (far field differs from the CPU only by summation order / FMA; the near field is evaluated
 with the reference's operation order and IEEE sqrt/div, differing by the libm log/atan2 only)."""
 import ctypes
@@ -36,7 +37,7 @@ def _oracle_T(Pi, Ai, Pj, Aj):
 @pytest.mark.parametrize('name,js', [('plate', 0), ('cyl', 2), ('torus', 0), ('ex_torus', 0)])
 @pytest.mark.parametrize('mode', [0, 1])
 def test_pair_integrals(name, js, mode):
-    from openfusiontoolkit_b200 import _interface as I
+    from openfusiontoolkit_b200 import _testlib as I
     Pi, Ai, Pj, Aj = _pairs(name, js, 200000, 7)
     To, qo = _oracle_T(Pi, Ai, Pj, Aj)
     Tg, qg = np.zeros_like(To), np.zeros_like(qo)
@@ -50,7 +51,7 @@ def test_pair_integrals(name, js, mode):
 
 def test_pair_integrals_scaled_geometry():
     """Order selection / evaluation must not depend on the length scale or the position in space."""
-    from openfusiontoolkit_b200 import _interface as I
+    from openfusiontoolkit_b200 import _testlib as I
     Pi, Ai, Pj, Aj = _pairs('torus', 0, 50000, 11)
     for scale, shift in ((1e-3, 0.0), (37.0, 0.0), (1.0, 1000.0)):
         Pi2, Pj2 = Pi * scale + shift, Pj * scale + shift
@@ -71,7 +72,7 @@ def test_pair_integrals_scaled_geometry():
 
 
 def test_phipot():
-    from openfusiontoolkit_b200 import _interface as I
+    from openfusiontoolkit_b200 import _testlib as I
     rng = np.random.default_rng(3)
     n = 100000
     tri = rng.normal(size=(n, 9))
@@ -92,7 +93,7 @@ def test_phipot():
 
 
 def test_rsqrt():
-    from openfusiontoolkit_b200 import _interface as I
+    from openfusiontoolkit_b200 import _testlib as I
     x = np.exp(np.random.default_rng(0).uniform(-60, 60, 300000))
     y = np.zeros_like(x)
     assert I.b200_probe_rsqrt(len(x), x, y) == 0

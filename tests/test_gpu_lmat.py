@@ -5,6 +5,7 @@ leading L/R eigenvalues.  Entry errors are measured relative to the entry itself
 larger than 1e-8 * max|L| (smaller ones are sums that cancel to rounding) and relative to max|L|
 for the rest.
 """
+import os
 import numpy as np
 import pytest
 from helpers import MU0, goldens, load_mesh, split_nodesets, ref_circle, ref_floop, dummy_mesh
@@ -66,25 +67,49 @@ def test_lmat_entries_and_eigs(env, name, js):
         assert np.abs(wg / np.array(g['vals']) - 1.0).max() < g['tol']
 
 
+_DRAIN_SCRIPT = r"""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], 'tests'))
+from helpers import load_mesh
+from openfusiontoolkit_b200 import OFT_env
+from openfusiontoolkit_b200.ThinCurr import ThinCurr
+m = load_mesh('torus')
+T = ThinCurr(OFT_env(nthreads=-1))
+T.setup_model(r=m['r'], lc=m['lc'], reg=m['reg'], nodesets=m['nodesets'], closures=m['sidesets'][0])
+T.compute_Lmat()
+ref = np.array(T.Lmat)
+rows = T.shard_rows(3, 2)
+out0 = torch.empty((len(rows), T.nelems), dtype=torch.float64, device='cuda')
+T.compute_Lmat_shard(3, 2, out0)
+torch.cuda.synchronize()
+os.environ['THINCURR_B200_DRAIN_LIMIT'] = sys.argv[2]
+full = torch.empty((T.nelems, T.nelems), dtype=torch.float64, device='cuda')
+T.compute_Lmat_shard(1, 0, full)
+out1 = torch.empty_like(out0)
+T.compute_Lmat_shard(3, 2, out1)
+torch.cuda.synchronize()
+allrows = T.shard_rows(1, 0)
+assert np.array_equal(full.cpu().numpy(), ref[allrows])
+assert np.array_equal(out1.cpu().numpy(), out0.cpu().numpy())
+print('DRAIN_OK')
+"""
+
+
 @pytest.mark.parametrize('limit', ['32', '0'])
-def test_contraction_direct_write_path(env, limit, monkeypatch):
+def test_contraction_direct_write_path(limit, tmp_path):
     """Chunks with more than 64 local DOFs per side take a direct-write path in the contraction that ordinary
-    meshes never reach; THINCURR_B200_DRAIN_LIMIT lowers the limit so that the path runs (rows, columns, both) and
-    must reproduce the normal build bit for bit, for the single-device and the row-sharded (mirror-writing) tiles."""
-    import torch
-    O, T = build_pair(env, 'torus', 0)
-    T.compute_Lmat()
-    ref = np.array(T.Lmat)
-    rows = T.shard_rows(3, 2)
-    out0 = torch.empty((len(rows), T.nelems), dtype=torch.float64, device='cuda')
-    T.compute_Lmat_shard(3, 2, out0)
-    torch.cuda.synchronize()
-    monkeypatch.setenv('THINCURR_B200_DRAIN_LIMIT', limit)
-    full = torch.empty((T.nelems, T.nelems), dtype=torch.float64, device='cuda')
-    T.compute_Lmat_shard(1, 0, full)
-    out1 = torch.empty_like(out0)
-    T.compute_Lmat_shard(3, 2, out1)
-    torch.cuda.synchronize()
-    allrows = T.shard_rows(1, 0)
-    assert np.array_equal(full.cpu().numpy(), ref[allrows])
-    assert np.array_equal(out1.cpu().numpy(), out0.cpu().numpy())
+    meshes never reach; the TEST build of the library (libthincurr_b200_test.so, -DTW_TEST_HOOKS) reads
+    THINCURR_B200_DRAIN_LIMIT to lower the limit so that the path runs (rows, columns, both) and must reproduce the
+    normal build bit for bit, for the single-device and the row-sharded (mirror-writing) tiles.  Runs in a
+    subprocess because the product library has no such switch."""
+    import subprocess
+    import sys
+    from openfusiontoolkit_b200.build import build_test
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / 'drain.py'
+    script.write_text(_DRAIN_SCRIPT)
+    env = dict(os.environ, THINCURR_B200_LIB=build_test())
+    res = subprocess.run([sys.executable, str(script), root, limit], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and 'DRAIN_OK' in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]

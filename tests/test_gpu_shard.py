@@ -102,7 +102,7 @@ def test_vessel_mesh_rows_and_stats(env):
     device's pair statistics against the oracle's loop-nest counts on a row-cell sample."""
     from bench import make_mesh
     from openfusiontoolkit_b200.ThinCurr import ThinCurr
-    m = make_mesh(1, 'auto')
+    m = make_mesh('vessel20k')
     T = ThinCurr(env)
     T.setup_model(r=m['r'], lc=m['lc'], nodesets=m['nodesets'], closures=m['closures'])
     T.compute_Lmat()

@@ -103,10 +103,13 @@ def test_symmetric_exchange(world):
         assert sizes[0] < sizes[-1], 'earlier shards own fewer rows (their rows are longer in the upper trapezoid)'
 
 
-def test_weak_scaling_mesh_sizes():
+def test_bench_workloads_are_the_baseline_configs():
+    """bench.py's meshes: configs[3] (~100k vertices, the default at every N: strong scaling), configs[1] (~20k),
+    configs[4] (~150k, ~180 GB matrix)."""
     sys.path.insert(0, ROOT)
-    from bench import vessel_dims
-    base = np.prod(vessel_dims(1))
-    for n in (2, 4, 8):
-        cells = np.prod(vessel_dims(n))
-        assert abs(cells ** 2 / n / base ** 2 - 1.0) < 0.03, 'pairs per rank stay constant'
+    import bench
+    assert bench.WORKLOADS['vessel100k'] == (224, 448)
+    m = bench.make_mesh('vessel20k')
+    assert 19000 < m['r'].shape[0] < 21000
+    nt, nphi = bench.WORKLOADS['vessel150k']
+    assert 170e9 < (nt * nphi) ** 2 * 8 < 190e9

@@ -59,3 +59,18 @@ if __name__ == '__main__':
     kat = np.array([[float(x) for x in r] for r in rows])
     np.save(os.path.join(out, 'quad_2d_kat.npy'), kat)
     json.dump(GOLDENS, open(os.path.join(out, 'goldens.json'), 'w'), indent=1)
+
+
+def reference_interface_symbols():
+    """Names the reference's Python layer binds from liboftpy.so for ThinCurr (ThinCurr/_interface.py:17-119):
+    a replacement library must export every one of them or `import OpenFUSIONToolkit.ThinCurr` raises AttributeError."""
+    import re
+    src = open('/root/reference/src/python/OpenFUSIONToolkit/ThinCurr/_interface.py').read()
+    return sorted(set(re.findall(r'oftpy_lib\.(\w+)', src)))
+
+
+if __name__ == '__main__' and '--symbols' in sys.argv:
+    names = reference_interface_symbols()
+    json.dump({'source': 'src/python/OpenFUSIONToolkit/ThinCurr/_interface.py:17-119', 'names': names},
+              open(os.path.join(ROOT, 'tests', 'golden', 'ref_interface_symbols.json'), 'w'), indent=1)
+    print('wrote %d names' % len(names))
