@@ -502,6 +502,9 @@ static std::string scratch_rows(DeviceState& ds, size_t bytes, double** out) {
 // (symmetrize_cross_kernel on peer memory) and sends its rows to the host.
 static std::string lmat_full_host(Model& m, double* dst) {
   const size_t N = (size_t)m.nelems;
+  const bool trace = std::getenv("THINCURR_B200_TRACE") != nullptr;
+  const auto tr0 = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
   DeviceGuard guard;
   std::vector<int> devs_ids = build_devices();
   if (devs_ids.empty()) return "No CUDA device available (the B200 backend has no CPU fallback)";
@@ -528,6 +531,7 @@ static std::string lmat_full_host(Model& m, double* dst) {
   };
   std::vector<Dev> devs(ndev);
   const bool pinned = is_pinned(dst);
+  size_t ncopies = 0;
   std::vector<std::unique_ptr<HostCopier>> copier(ndev);
   // rows [r0,r1) of device g to their place in the reference layout Lmat(:,row), runs of consecutive reference ids as
   // one copy; the copies wait for `after` (an event of the build stream)
@@ -544,6 +548,7 @@ static std::string lmat_full_host(Model& m, double* dst) {
       if (!pinned) copier[g]->push(to, from, bytes, after);
       else if (cudaMemcpyAsync(to, from, bytes, cudaMemcpyDeviceToHost, D.cs) != cudaSuccess)
         return std::string("Device->host copy failed: ") + cudaGetErrorString(cudaGetLastError());
+      ncopies++;
       r = e;
     }
     return "";
@@ -552,6 +557,7 @@ static std::string lmat_full_host(Model& m, double* dst) {
     if (e != cudaSuccess && err.empty()) err = std::string(what) + ": " + cudaGetErrorString(e);
     return e == cudaSuccess;
   };
+  const double tr_plan = since(tr0);
   // ---- phase 1: every device starts building its shard
   for (int g = 0; g < ndev && err.empty(); g++) {
     Dev& D = devs[g];
@@ -627,6 +633,9 @@ static std::string lmat_full_host(Model& m, double* dst) {
       if (err.empty()) err = ce2;
     }
   }
+  if (trace)
+    std::fprintf(stderr, "[lmat_full_host] %d device(s), %s destination, plan %.1f ms, total %.1f ms, %zu row-run copies, sym %d\n", ndev,
+                 pinned ? "pinned" : "pageable", tr_plan, since(tr0), ncopies, (int)sym);
   for (int g = 0; g < ndev; g++) {  // (all devices are done reading each other's blocks)
     cudaSetDevice(devs_ids[g]);
     if (devs[g].s) cudaStreamDestroy(devs[g].s);

@@ -3,25 +3,30 @@
 // Replaces the O(nc^2) OpenMP loop nest of tw_compute_LmatDirect (src/physics/thin_wall.F90:
 // 1008-1126) with an owner-computes tiling.  One persistent CTA per SM pulls output tiles
 // (row patch x column patch) from a cost-sorted queue.  One PASS = one pair of 64-cell chunks of the
-// two patches (4096 cell pairs), six block barriers:
+// two patches (4096 cell pairs):
 //   0. staging: a chunk is three bulk async copies (cp.async.bulk ... mbarrier::complete_tx) into a
 //      ChunkState slot -- 22 SoA geometry rows, the index record (per-cell min/max DOF, reference DOF ids,
-//      CSR incidences) and this launch's output rows; the next column chunk is prefetched during the pass;
-//   A. classification: the quadrature order of thin_wall.F90:1044-1059 is screened in FP32 on locally
-//      shifted coordinates with a rigorous error band (order 4 from the cells' bounding spheres when they
-//      are far enough apart) and falls back to a bit-exact FP64 evaluation when a threshold is within
-//      the band;
-//   B. binning by rule from per-thread packed histograms + one warp scan (no atomics or votes in the pair
-//      loop); lists are row-major, bins padded to warp multiples, every warp executes ONE rule;
-//   C. evaluation of T(c1,c2) from a dynamic queue of warp-sized batches: far pairs (thin_wall.F90:1069-1083)
-//      from per-chunk tables of quadrature points in shared memory ((x,y,z,|x|^2) in a local frame,
-//      d^2 = |xi|^2+|xj|^2-2 xi.xj, MUFU.RSQ64H seed + third-order correction = 10 FP64-pipe instructions
-//      per 1/r), near pairs (thin_wall.F90:1061-1068) with one half-warp per pair, lanes over the
-//      quadrature points of the analytic potential;
-//   D. contraction onto the vertex/hole DOFs: a warp per column DOF forms the pass's 64 x 64 block of
-//      contributions in shared memory, then a warp per matrix row adds it into L with lanes along the row.
+//      CSR incidences) and this launch's output rows; the next column chunk is prefetched during the pass.
+//      All local coordinates of a sweep are relative to the centre of the ROW chunk, so its FP32 copies and
+//      its quadrature-point tables (rules of 6, 7 and 12 points) are built once per row chunk;
+//   1. the column chunk's FP32 copies and point tables (one barrier);
+//   2. ROW SWEEP, no barrier inside: a warp takes one row cell at a time from a counter, classifies its 64
+//      pairs -- the quadrature order of thin_wall.F90:1044-1059 screened in FP32 with a rigorous error band
+//      (order 4 from the cells' bounding spheres when they are far enough apart; bit-exact FP64 evaluation
+//      when a threshold is within the band; nothing at all when the chunks' bounding spheres already
+//      guarantee order 4 for every pair) -- compacts the pairs of the three tabled rules with warp votes
+//      into its own pending lists and evaluates every full batch of 32 at once from the shared-memory
+//      point tables ((x,y,z,|x|^2), d^2 = |xi|^2+|xj|^2-2 xi.xj, MUFU.RSQ64H seed + third-order
+//      correction = 10 FP64-pipe instructions per 1/r).  Warps drift apart, so the FP32/integer work of
+//      the classifying warps overlaps the FP64 work of the evaluating ones;
+//   3. what is left -- the warps' partial batches, pairs of the larger far rules (evaluated from the
+//      vertices) and near pairs (thin_wall.F90:1061-1068: one half-warp per pair, lanes over the points
+//      of the analytic potential) -- is evaluated from block-wide lists through a dynamic queue;
+//   4. contraction onto the vertex/hole DOFs, fused with the update of L: a warp per row DOF sums its
+//      cells' rows of T against the column side and adds the result into its row of L with lanes along
+//      the row (old values loaded up front).
 // Every L entry is owned by exactly one CTA and updated by plain loads and stores between barriers: no
-// atomics on the matrix, deterministic summation.  When the rows of both patches of a tile are in the output
+// atomics on the matrix, deterministic values.  When the rows of both patches of a tile are in the output
 // block the transposed entries are left to symmetrize_kernel (thin_wall.F90:1146-1151).
 //
 // Role rule (SURVEY hard part 1): for entry (a,b) with a<=b in reference numbering the cell
@@ -53,11 +58,12 @@ constexpr int kGeomL = 22;         // geometry rows the L kernel stages (vertice
 static_assert(CI == tw::kRowHalf, "row block of the plan records");
 constexpr int TS = kCH + 1;        // row stride of the T tile (bank-conflict-free column access)
 constexpr int NCLS = 12;           // far classes 0..6 (iquad 4..10), near classes 7..11 (28,33,46,55,72 points)
-constexpr int kListCap = CI * kCH + NCLS * 32;
-constexpr int kTabMaxN = 25;       // largest rule served from shared-memory point tables
-constexpr int kTabClsMax = 6;      // ... as a far class index
-constexpr int kTabPts = 34;        // points the table pool holds (several rules at once)
-constexpr int kTabMin = 64;        // fewer pairs of a rule than this: evaluate from the vertices instead
+constexpr int kTabMaxN = 25;       // largest rule far_tab is instantiated for (probes)
+constexpr int kTabClsMax = 2;      // far classes served from the shared-memory point tables by the tile kernel (rules 4, 5, 6)
+constexpr int kTabPts = 25;        // 6 + 7 + 12 points
+constexpr int kPend = 96;          // pending pairs per (warp, tabled class): < 32 left over + <= 64 of a new row
+constexpr int kLeft = 512;         // leftover pairs per tabled class and pass (< 32 per warp)
+constexpr int kOList = CI * kCH + (NCLS - 3) * 32;  // pairs of the other classes, bins padded to batches
 
 __device__ __constant__ int c_cls_np[NCLS] = {6, 7, 12, 15, 16, 19, 25, 28, 33, 46, 55, 72};
 __device__ __forceinline__ int cls_of(int iq) {
@@ -79,8 +85,8 @@ struct LmatArgs {
   long long ld;
   double scale;                       // 1/(4 pi)
   int self;                           // 1: self inductance (role rule, mirror), 0: mutual
-  int fast_lim;                       // local DOFs per chunk side handled through the shared-memory block (64; 32 or 0 in tests of the direct path)
-  int debug_skip;                     // profiling aid: bit0 skip near-field evaluation, bit1 skip far-field evaluation,
+  int fast_lim;                       // column DOFs per chunk handled from registers in the contraction (64; 32 or 0 in tests of the generic path)
+  int debug_skip;                     // test build only: bit0 skip near-field evaluation, bit1 skip far-field evaluation,
                                       // bit2 skip the contraction
   unsigned long long* stats;          // [0] far pairs, [1] near T evaluations, [2] 1/r evaluations, [3] phipot evals
 };
@@ -91,20 +97,22 @@ struct alignas(16) ChunkState {
   double g[kGeomL * kCH];             // rows 0-8 vertices, 9 area, 10-18 qbasis, 19-21 unit normal (phipot's)
   tw::ChunkAux x;
   int row[tw::kMaxChunkDof];          // output rows (or -1)
-  double cx, cy, cz, rad;
+  double cx, cy, cz, rad, emax;
   int ncell, ndof;
   unsigned long long bar;             // mbarrier of the bulk copies
 };
 static_assert(offsetof(ChunkState, x) % 16 == 0 && offsetof(ChunkState, row) % 16 == 0, "bulk copy alignment");
 
-// classification result of one pass (CI x kCH cell pairs): pair lists binned by rule + the work queue
-struct PassBuf {
-  unsigned short list[kListCap];      // pair ids (c1l<<6|c2) sorted by class, bins padded with 0xFFFF
-  unsigned char iqmap[CI * kCH];      // iquad | need-role-1 << 5 | need-role-2 << 6
-  int cnt[NCLS], off[NCLS + 1];
-  int qcls[NCLS + 8], qnb[NCLS + 8], qpt[NCLS + 8];  // queue items: class (| 16 = table), batches, table offset
-  int gq0[8], gq1[8], gnb[8], ng;     // table groups: item range and batch count
-  int qhead, both_count;
+// per-pass work lists
+struct alignas(16) PassBuf {
+  unsigned short olist[kOList];       // pairs (c1<<6|c2) of the classes > kTabClsMax sorted by class, bins padded with 0xFFFF
+  unsigned short left[kTabClsMax + 1][kLeft];       // partial batches of the tabled classes handed over by the warps
+  unsigned short pend[NW][kTabClsMax + 1][kPend];   // per warp: pairs of the tabled classes waiting for a full batch
+  unsigned char iqmap[CI * kCH];      // per pair: 0, or for a pair of another class iquad | need-role-1 << 5 | need-role-2 << 6
+  int nleft[kTabClsMax + 1];
+  int cnt[NCLS], pos[NCLS], off[NCLS + 1];
+  int qcls[NCLS], qnb[NCLS], nq, qtotal;
+  int rowhead, lhead, qhead, both_count;
 };
 
 struct Smem {
@@ -112,42 +120,22 @@ struct Smem {
   ChunkState J[2];                    // column chunks: the one in use and the next one (prefetched)
   PassBuf pb;
   alignas(16) double T[CI * TS];
-  union {                             // phases that never overlap share this region
-    struct {
-      double2 tabI[kTabPts * 2 * CI];   // per rule [(p*2+h)*CI + c1]: h=0 (-2x,-2y), h=1 (-2z,|x|^2)
-      double2 tabJ[kTabPts * 2 * kCH];  //          [(p*2+h)*kCH + c2]: h=0 (x,y),    h=1 (z,|x|^2)
-    } tab;
-    struct {
-      float vfI[9 * CI], vfJ[9 * kCH];  // vertices in the local frame, FP32 (order screening)
-      float flI[CI], flJ[kCH];          // 2 * area
-      float4 cenI[CI], cenJ[kCH];       // centroid (local frame) and the radius covering the vertices
-      char pad0[8192 - (9 * CI + 9 * kCH + CI + kCH) * 4 - (CI + kCH) * 16];
-      double E[CI * TS];                // contraction: contribution of the pass to L[row DOF][column DOF] (first 64 x 64)
-      char pad1[kTabPts * 2 * CI * 16 - 8192 - CI * TS * 8];  // (the per-warp scratch starts at tabJ)
-      double P[NW][3 * CI];             // per warp: products of the contraction
-    } w;
+  alignas(16) double2 tabI[kTabPts * 2 * CI];   // [(p*2+h)*CI + c1]: h=0 (-2x,-2y), h=1 (-2z,|x|^2); rules 4,5,6 at points 0,6,13
+  union {
+    double2 tabJ[kTabPts * 2 * kCH];  //          [(p*2+h)*kCH + c2]: h=0 (x,y),    h=1 (z,|x|^2)
+    double P[NW][3 * kCH];            // contraction scratch of the warps (the column tables are dead by then)
   } u;
+  float vfI[9 * CI], vfJ[9 * kCH];    // vertices relative to the row chunk's centre, FP32 (order screening)
+  float flI[CI], flJ[kCH];            // 2 * area
+  float4 cenI[CI], cenJ[kCH];         // centroid (same frame) and the radius covering the vertices
   int tile_id;
-#ifdef TW_LMAT_PROF
-  long long prof[16], prof_last[2];
-#endif
 };
 static_assert(sizeof(Smem) <= 232448, "shared memory of one CTA");
 template <int N> struct ShowSize;
 #ifdef TW_SHOW_SMEM
 ShowSize<sizeof(Smem)> show_smem_size;
 #endif
-#ifdef TW_LMAT_PROF
-// section timing of CTA 0 (tuning builds only): who = 0 service thread 0, 1 evaluation thread 0
-#define TW_MARK(S, who, t, i)                                   \
-  if ((t) == 0 && blockIdx.x == 0) {                            \
-    const long long now_ = clock64();                           \
-    (S).prof[i] += now_ - (S).prof_last[who];                   \
-    (S).prof_last[who] = now_;                                  \
-  }
-#else
 #define TW_MARK(S, who, t, i)
-#endif
 
 // ---- far field from the vertices (rules without a table / tiny bins) --------------------------
 // T = area_i area_j sum_p sum_q w_p w_q / |x_p(i) - x_q(j)|, same rule on both triangles
@@ -426,91 +414,113 @@ __device__ __forceinline__ void stage_issue(ChunkState& C, int side, const LmatA
   C.cy = cm.cy;
   C.cz = cm.cz;
   C.rad = cm.rad;
+  C.emax = cm.emax;
 }
 
-// ---- prep: classification of the CI x kCH cell pairs of a pass, binned by rule -------------------------
-// Stage 0 (before the pass barrier): FP32 local-frame copies of the vertices and the bin counters.
-__device__ __forceinline__ void prep_stage(Smem& S, const ChunkState& I, const ChunkState& J, int tid) {  // @region A0_fp32_stage
-  PassBuf& pb = S.pb;
-  // local frame: midpoint of the two chunk centres
-  const double ox = 0.5 * (I.cx + J.cx), oy = 0.5 * (I.cy + J.cy), oz = 0.5 * (I.cz + J.cz);
+// ---- preparation of a chunk for the sweep: FP32 copies (order screening) and point tables of the tabled rules, all
+// relative to the centre (ox,oy,oz) of the ROW chunk.  row side: once per row chunk; column side: once per pass.
+__device__ __forceinline__ void prep_chunk(const ChunkState& C, float* __restrict__ vf, float* __restrict__ fl, float4* __restrict__ cen,  // @region prep_chunk
+                                           double2* __restrict__ tab, bool neg, double ox, double oy, double oz, int tid) {
   for (int i = tid; i < 9 * kCH; i += NT) {
-    const int k = i / kCH, dd = k % 3;
-    const double o = dd == 0 ? ox : (dd == 1 ? oy : oz);
-    S.u.w.vfJ[i] = (float)(J.g[i] - o);
-    S.u.w.vfI[i] = (float)(I.g[i] - o);
+    const int dd = (i / kCH) % 3;
+    vf[i] = (float)(C.g[i] - (dd == 0 ? ox : (dd == 1 ? oy : oz)));
   }
-  for (int i = tid; i < kCH; i += NT) {
-    S.u.w.flJ[i] = (float)(2.0 * J.g[9 * kCH + i]);
-    S.u.w.flI[i] = (float)(2.0 * I.g[9 * kCH + i]);
-  }
-  if (tid < 2 * kCH) {  // bounding sphere of every cell (order-4 prefilter of the classification)
-    const int c = tid & (kCH - 1);
-    const double* g = tid < kCH ? I.g : J.g;
+  if (tid >= NT - kCH) {  // bounding sphere of every cell (order-4 prefilter of the classification) and 2 * area
+    const int c = tid - (NT - kCH);
     double P[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) P[k] = g[k * kCH + c];
+    for (int k = 0; k < 9; k++) P[k] = C.g[k * kCH + c];
     const double mx = (P[0] + P[3] + P[6]) * (1.0 / 3.0), my = (P[1] + P[4] + P[7]) * (1.0 / 3.0), mz = (P[2] + P[5] + P[8]) * (1.0 / 3.0);
     // radius over the vertices; the dl_max floor sqrt(2 area) <= 1.62 x this radius needs no separate term: the test
-    // below implies D - R > 79 R
+    // of the prefilter implies D - R > 79 R
     double r2 = 0.0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       const double dx = P[3 * k] - mx, dy = P[3 * k + 1] - my, dz = P[3 * k + 2] - mz;
       r2 = fmax(r2, dx * dx + dy * dy + dz * dz);
     }
-    const float4 v = make_float4((float)(mx - ox), (float)(my - oy), (float)(mz - oz), (float)(sqrt(r2) * 1.00001));
-    if (tid < kCH) S.u.w.cenI[c] = v;
-    else S.u.w.cenJ[c] = v;
+    cen[c] = make_float4((float)(mx - ox), (float)(my - oy), (float)(mz - oz), (float)(sqrt(r2) * 1.00001));
+    fl[c] = (float)(2.0 * C.g[9 * kCH + c]);
   }
-  if (tid < NCLS) pb.cnt[tid] = 0;
-  if (tid == 0) {
-    pb.both_count = 0;
-    pb.qhead = 0;
+  build_table(tab, kCH, C.g, 0, C.ncell, 4, 6, ox, oy, oz, neg, tid, NT);
+  build_table(tab + 6 * 2 * kCH, kCH, C.g, 0, C.ncell, 5, 7, ox, oy, oz, neg, tid, NT);
+  build_table(tab + 13 * 2 * kCH, kCH, C.g, 0, C.ncell, 6, 12, ox, oy, oz, neg, tid, NT);
+}
+static_assert(CI == kCH, "row and column tables share the stride");
+
+// one batch of a tabled class: lane's pair e (c1<<6|c2, 0xFFFF = none) from the point tables
+template <int C>
+__device__ __forceinline__ void tab_eval(Smem& S, const ChunkState& I, const ChunkState& J, unsigned e) {  // @region tab_eval
+  constexpr int N = C == 0 ? 6 : (C == 1 ? 7 : 12), OFF = C == 0 ? 7 : (C == 1 ? 13 : 20), PT = C == 0 ? 0 : (C == 1 ? 6 : 13);
+  if (e != 0xFFFFu) {
+    const int c1 = e >> 6, c2 = e & 63;
+    S.T[c1 * TS + c2] = far_tab<N, OFF>(S.tabI + PT * 2 * CI, S.u.tabJ + PT * 2 * kCH, c1, c2) * I.g[9 * kCH + c1] * J.g[9 * kCH + c2];
   }
 }
 
-// Stage 1 (after the pass barrier).  No atomics or warp votes inside the pair loop: every thread keeps a
-// packed histogram of its pairs; one warp scan gives the lane offsets and one shared atomic per (warp, class)
-// the warp's share of the bin.  Ends with the bins and the work queue complete (two barriers inside).
-__device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int flags, int tid,
-                                              unsigned long long& st_far, unsigned long long& st_eval) {
+// append the lanes' pairs of class C (flag `mine`, pair id `e`) to the warp's pending list and evaluate full batches
+template <int C>
+__device__ __forceinline__ void tab_push(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, unsigned short* __restrict__ pend, int& npd,
+                                         bool mine0, bool mine1, unsigned e0, unsigned e1, int lane) {
+  const unsigned lt = (1u << lane) - 1u;
+  const unsigned m0 = __ballot_sync(0xffffffffu, mine0), m1 = __ballot_sync(0xffffffffu, mine1);
+  if ((m0 | m1) == 0u) return;
+  if (mine0) pend[npd + __popc(m0 & lt)] = (unsigned short)e0;
+  npd += __popc(m0);
+  if (mine1) pend[npd + __popc(m1 & lt)] = (unsigned short)e1;
+  npd += __popc(m1);
+  __syncwarp();
+  while (npd >= 32) {
+    npd -= 32;
+    const unsigned e = pend[npd + lane];
+    __syncwarp();  // the slots may be overwritten by the next append
+    if (!(A.debug_skip & 2)) tab_eval<C>(S, I, J, e);
+  }
+}
+
+// ---- row sweep: classification of the pairs of one row cell at a time, tabled rules evaluated at once --------------
+__device__ __forceinline__ void sweep_rows(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int flags, int tid,  // @region sweep_rows
+                                           unsigned long long& st_far, unsigned long long& st_eval) {
   PassBuf& pb = S.pb;
   const int lane = tid & 31, warp = tid >> 5;
   const int ncI = I.ncell, ncJ = J.ncell;
   const bool diag = flags & 1, want2 = (flags & 4) && A.self;
-  float delta;
-  {
-    const double hx = 0.5 * (I.cx - J.cx), hy = 0.5 * (I.cy - J.cy), hz = 0.5 * (I.cz - J.cz);
-    const double X = sqrt(hx * hx + hy * hy + hz * hz) + fmax(I.rad, J.rad);
-    delta = (float)(X * 1.21e-7);  // two operands, each rounded to FP32 (2^-24 relative), 1% slack
-  }
-  // the order-4 prefilter pays only where most pairs pass: chunks at least ~25 cell sizes apart (block-uniform)
-  bool far_pass;
-  {
-    const double hx = I.cx - J.cx, hy = I.cy - J.cy, hz = I.cz - J.cz;
-    far_pass = sqrt(hx * hx + hy * hy + hz * hz) - I.rad - J.rad > 25.0 * (double)(S.u.w.cenI[0].w + S.u.w.cenJ[0].w);
-  }
-  // ---------------- classification --------------------------------------------------------------------  // @region A_classify
-  // a thread owns one row cell c1 and the kCH/TPR columns c2 = NIT * (t % TPR) + m: the pairs of a thread,
-  // and of the TPR threads of a row, are consecutive in a bin, so a batch of 32 pairs of the evaluation
-  // reads few distinct row-side table entries (broadcast) and consecutive column-side entries
-  constexpr int TPR = NTC / CI, NIT = kCH / TPR;
-  static_assert(NIT <= 8 && TPR * CI == NTC && NTC <= NT && NIT * TPR == kCH, "4-bit per-thread class counts");
-  unsigned mycls = 0;            // 4 bits per iteration: class + 1, 0 = no pair
-  unsigned long long hist = 0;   // 4 bits per class: pairs of this thread
-  int nboth = 0;
-  const int c1 = tid / TPR, c2b = NIT * (tid % TPR);
-  if (tid < NTC && c1 < ncI) {
+  // block-uniform geometry of the pass
+  const double hx = J.cx - I.cx, hy = J.cy - I.cy, hz = J.cz - I.cz;
+  const double D = sqrt(hx * hx + hy * hy + hz * hz);
+  // |v| <= X for every FP32 coordinate of the pass; delta = bound of the error of a vertex difference (two operands, each
+  // rounded to FP32: 2^-24 relative, 1% slack)
+  const float delta = (float)((D + fmax(I.rad, J.rad)) * 1.21e-7);
+  const double gap = D - I.rad - J.rad;
+  // every pair of the pass has order 4: dl_min >= gap, dl_max <= dl_min + emax_I + emax_J (vertices of a triangle are within
+  // one edge of each other; the floor sqrt(2 area) is below one edge), so rho >= gap / (gap + s) > c_thr[0]
+  const double s_e = I.emax + J.emax;
+  const bool uniform4 = gap > 0.0 && gap * (1.0 - c_thr[0]) > s_e * c_thr[0] * (1.0 + 1.0e-9);
+  // the per-pair order-4 prefilter pays only where most pairs pass: chunks at least ~25 cell sizes apart
+  const bool far_pass = gap > 25.0 * (double)(S.cenI[0].w + S.cenJ[0].w);
+  unsigned short* pend0 = pb.pend[warp][0];
+  unsigned short* pend1 = pb.pend[warp][1];
+  unsigned short* pend2 = pb.pend[warp][2];
+  int np0 = 0, np1 = 0, np2 = 0;
+#pragma unroll 1
+  for (;;) {
+    int c1 = 0;
+    if (lane == 0) c1 = atomicAdd(&pb.rowhead, 1);
+    c1 = __shfl_sync(0xffffffffu, c1, 0);
+    if (c1 >= ncI) break;
     float pi_[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) pi_[k] = S.u.w.vfI[k * CI + c1];
-    const float fli = S.u.w.flI[c1];
-    const float4 ci = S.u.w.cenI[c1];
+    for (int k = 0; k < 9; k++) pi_[k] = S.vfI[k * CI + c1];
+    const float fli = S.flI[c1];
+    const float4 ci = S.cenI[c1];
     const int dminI = I.x.dmin[c1], dmaxI = I.x.dmax[c1];
-#pragma unroll 2
-    for (int m = 0; m < NIT; m++) {
-      const int c2 = c2b + m;
+    int cls[2];
+    unsigned code[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int c2 = lane + 32 * h;
+      cls[h] = -1;
+      code[h] = 0;
       if (c2 < ncJ) {
         bool n1, n2 = false;
         if (A.self) {
@@ -520,50 +530,108 @@ __device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const 
           n1 = true;
         }
         if (n1 || n2) {
-          float pj_[9];
+          int iq = 4;
+          if (!uniform4) {
+            float pj_[9];
 #pragma unroll
-          for (int k = 0; k < 9; k++) pj_[k] = S.u.w.vfJ[k * kCH + c2];
-          int iq = -2;
-          if (far_pass) {
-            // order-4 prefilter.  u = unit vector between the centroids, a_k / b_k = projections of the vertices on u,
-            // R = sum of the cells' vertex radii (>= the part of any vertex difference perpendicular to u):
-            //   dl_min >= Lb = min b - max a,   dl_max <= Ub = (max b - min a) + R^2 / (2 Lb)
-            // (the floor sqrt(2 area) <= 1.62 R is below Ub once D > 10 R), so Lb/Ub > 0.9752 > c_thr[0] => iquad = 4.
-            const float4 cj = S.u.w.cenJ[c2];
-            float ux = cj.x - ci.x, uy = cj.y - ci.y, uz = cj.z - ci.z;
-            const float D2 = fmaf(uz, uz, fmaf(uy, uy, ux * ux)), rr = ci.w + cj.w + 4.0f * delta;
-            if (D2 > 100.0f * rr * rr) {
-              const float rD = rsqrtf(D2);
-              ux *= rD;
-              uy *= rD;
-              uz *= rD;
-              const float a0 = fmaf(pi_[2], uz, fmaf(pi_[1], uy, pi_[0] * ux)), a1 = fmaf(pi_[5], uz, fmaf(pi_[4], uy, pi_[3] * ux)),
-                          a2 = fmaf(pi_[8], uz, fmaf(pi_[7], uy, pi_[6] * ux));
-              const float b0 = fmaf(pj_[2], uz, fmaf(pj_[1], uy, pj_[0] * ux)), b1 = fmaf(pj_[5], uz, fmaf(pj_[4], uy, pj_[3] * ux)),
-                          b2 = fmaf(pj_[8], uz, fmaf(pj_[7], uy, pj_[6] * ux));
-              const float lb = fminf(b0, fminf(b1, b2)) - fmaxf(a0, fmaxf(a1, a2)) - 8.0f * delta;
-              const float ub = fmaxf(b0, fmaxf(b1, b2)) - fminf(a0, fminf(a1, a2)) + 8.0f * delta;
-              if (lb > 0.9752f * fmaf(0.5f * rr, __fdividef(rr, lb), ub)) iq = 4;
+            for (int k = 0; k < 9; k++) pj_[k] = S.vfJ[k * kCH + c2];
+            iq = -2;
+            if (far_pass) {
+              // order-4 prefilter.  u = unit vector between the centroids, a_k / b_k = projections of the vertices on u,
+              // R = sum of the cells' vertex radii (>= the part of any vertex difference perpendicular to u):
+              //   dl_min >= Lb = min b - max a,   dl_max <= Ub = (max b - min a) + R^2 / (2 Lb)
+              // (the floor sqrt(2 area) <= 1.62 R is below Ub once D > 10 R), so Lb/Ub > 0.9752 > c_thr[0] => iquad = 4.
+              const float4 cj = S.cenJ[c2];
+              float ux = cj.x - ci.x, uy = cj.y - ci.y, uz = cj.z - ci.z;
+              const float D2 = fmaf(uz, uz, fmaf(uy, uy, ux * ux)), rr = ci.w + cj.w + 4.0f * delta;
+              if (D2 > 100.0f * rr * rr) {
+                const float rD = rsqrtf(D2);
+                ux *= rD;
+                uy *= rD;
+                uz *= rD;
+                const float a0 = fmaf(pi_[2], uz, fmaf(pi_[1], uy, pi_[0] * ux)), a1 = fmaf(pi_[5], uz, fmaf(pi_[4], uy, pi_[3] * ux)),
+                            a2 = fmaf(pi_[8], uz, fmaf(pi_[7], uy, pi_[6] * ux));
+                const float b0 = fmaf(pj_[2], uz, fmaf(pj_[1], uy, pj_[0] * ux)), b1 = fmaf(pj_[5], uz, fmaf(pj_[4], uy, pj_[3] * ux)),
+                            b2 = fmaf(pj_[8], uz, fmaf(pj_[7], uy, pj_[6] * ux));
+                const float lb = fminf(b0, fminf(b1, b2)) - fmaxf(a0, fmaxf(a1, a2)) - 8.0f * delta;
+                const float ub = fmaxf(b0, fmaxf(b1, b2)) - fminf(a0, fminf(a1, a2)) + 8.0f * delta;
+                if (lb > 0.9752f * fmaf(0.5f * rr, __fdividef(rr, lb), ub)) iq = 4;
+              }
+            }
+            if (iq < 0) {
+              iq = iquad_screen(pi_, pj_, fmaxf(fli, S.flJ[c2]), delta);
+              if (iq < 0) iq = iquad_exact_cells(I.g, c1, J.g, c2);
             }
           }
-          if (iq < 0) {
-            iq = iquad_screen(pi_, pj_, fmaxf(fli, S.u.w.flJ[c2]), delta);
-            if (iq < 0) iq = iquad_exact_cells(I.g, c1, J.g, c2);
+          const int cl = cls_of(iq);
+          cls[h] = cl;
+          if (cl > kTabClsMax) code[h] = (unsigned)iq | (n1 ? 32u : 0u) | (n2 ? 64u : 0u);
+          if (cl < 7) {  // statistics: far pairs and 1/r evaluations
+            st_far++;
+            st_eval += (unsigned long long)(c_cls_np[cl] * c_cls_np[cl]);
           }
-          const int cls = cls_of(iq);
-          if (cls >= 7) {  // near pairs carry their order and roles (T of unused pairs is never read by a used entry)
-            pb.iqmap[c1 * kCH + c2] = (unsigned char)((unsigned)iq | (n1 ? 32u : 0u) | (n2 ? 64u : 0u));
-            nboth += (n1 && n2) ? 1 : 0;
-          }
-          mycls |= (unsigned)(cls + 1) << (4 * m);
-          hist += 1ull << (4 * cls);
         }
       }
+      pb.iqmap[c1 * kCH + c2] = (unsigned char)code[h];
+    }
+    // tabled rules: compact with warp votes, evaluate every full batch
+    const unsigned e0 = (unsigned)(c1 * kCH + lane), e1 = e0 + 32u;
+    tab_push<0>(S, A, I, J, pend0, np0, cls[0] == 0, cls[1] == 0, e0, e1, lane);
+    tab_push<1>(S, A, I, J, pend1, np1, cls[0] == 1, cls[1] == 1, e0, e1, lane);
+    tab_push<2>(S, A, I, J, pend2, np2, cls[0] == 2, cls[1] == 2, e0, e1, lane);
+    // other classes: counts for the block-wide bins
+    const unsigned mo = __ballot_sync(0xffffffffu, (code[0] | code[1]) != 0u);
+    if (mo) {
+      int mycount = 0;
+#pragma unroll
+      for (int c = kTabClsMax + 1; c < NCLS; c++) {
+        const int k = __popc(__ballot_sync(0xffffffffu, cls[0] == c)) + __popc(__ballot_sync(0xffffffffu, cls[1] == c));
+        if (lane == c) mycount = k;
+      }
+      if (mycount) atomicAdd(&pb.cnt[lane], mycount);
+      const int nboth = __popc(__ballot_sync(0xffffffffu, (code[0] & 96u) == 96u)) + __popc(__ballot_sync(0xffffffffu, (code[1] & 96u) == 96u));
+      if (lane == 0 && nboth) atomicAdd(&pb.both_count, nboth);
     }
   }
-  TW_MARK(S, 0, tid, 5)
-  // ---------------- bins: warp scan of the packed histograms (10-bit fields, 6 classes per word) -----------  // @region B_bin
-  unsigned long long h0 = 0, h1 = 0;
+  // hand the partial batches over
+  {
+    const int npd[3] = {np0, np1, np2};
+    unsigned short* const pd[3] = {pend0, pend1, pend2};
+#pragma unroll
+    for (int c = 0; c <= kTabClsMax; c++) {
+      if (npd[c] == 0) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&pb.nleft[c], npd[c]);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (lane < npd[c]) pb.left[c][base + lane] = pd[c][lane];
+    }
+  }
+}
+
+// ---- block-wide bins of the other classes (larger far rules, near pairs) from the per-pair codes ----------------------
+// pb.cnt is complete (barrier before).  A thread takes the codes of 8 consecutive pairs of a row; packed histograms +
+// one warp scan give the lane offsets, one shared atomic per (warp, class) the warp's share of the bin.  Bins: near
+// classes (largest rules) first, padded to whole batches.  The last warp builds the queue.  A barrier must follow.
+__device__ __forceinline__ void bin_others(Smem& S, const ChunkState& I, int tid) {  // @region bin_others
+  PassBuf& pb = S.pb;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int TPR = NT / CI, NIT = kCH / TPR;
+  static_assert(NIT == 8 && TPR * CI == NT, "8 pair codes per thread");
+  const int c1 = tid / TPR, c2b = NIT * (tid % TPR);
+  unsigned long long codes8 = 0;
+  if (c1 < I.ncell) codes8 = *reinterpret_cast<const unsigned long long*>(pb.iqmap + c1 * kCH + c2b);
+  unsigned mycls = 0;            // 4 bits per pair: class + 1, 0 = not in a bin
+  unsigned long long hist = 0;   // 4 bits per class
+#pragma unroll
+  for (int m = 0; m < NIT; m++) {
+    const unsigned cd = (unsigned)(codes8 >> (8 * m)) & 255u;
+    if (cd) {
+      const int cls = cls_of((int)(cd & 31u));
+      mycls |= (unsigned)(cls + 1) << (4 * m);
+      hist += 1ull << (4 * cls);
+    }
+  }
+  unsigned long long h0 = 0, h1 = 0;  // 10-bit fields, 6 classes per word
 #pragma unroll
   for (int c = 0; c < 6; c++) {
     h0 |= ((hist >> (4 * c)) & 15ull) << (10 * c);
@@ -581,18 +649,11 @@ __device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const 
   const unsigned long long w0 = __shfl_sync(0xffffffffu, s0, 31), w1 = __shfl_sync(0xffffffffu, s1, 31);  // warp totals
   s0 -= h0;  // exclusive
   s1 -= h1;
-  int wbase = 0;  // lane c < NCLS: offset of this warp's pairs within bin c
-  if (lane < NCLS) {
-    const int tot = (int)(((lane < 6 ? w0 : w1) >> (10 * (lane % 6))) & 1023ull);
-    if (tot) wbase = atomicAdd(&pb.cnt[lane], tot);
-  }
-  nboth = __reduce_add_sync(0xffffffffu, nboth);
-  if (lane == 0 && nboth) atomicAdd(&pb.both_count, nboth);
-  __syncthreads();
-  TW_MARK(S, 0, tid, 6)
-  // bin offsets: near classes (largest rules) first; bins padded to whole batches
   int start = 0;  // lane c < NCLS: first list slot of this warp's pairs of class c
   if (lane < NCLS) {
+    const int tot = (int)(((lane < 6 ? w0 : w1) >> (10 * (lane % 6))) & 1023ull);
+    int wbase = 0;
+    if (tot) wbase = atomicAdd(&pb.pos[lane], tot);
     int o = 0;
     for (int c = NCLS - 1; c > lane; c--) {
       const int n = pb.cnt[c];
@@ -603,75 +664,26 @@ __device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const 
       const int n = pb.cnt[lane];
       pb.off[lane] = o;
       const int padded = lane >= 7 ? ((n + 1) & ~1) : ((n + 31) & ~31);
-      for (int i = n; i < padded; i++) pb.list[o + i] = 0xFFFFu;  // padding of the last batch
+      for (int i = n; i < padded; i++) pb.olist[o + i] = 0xFFFFu;  // padding of the last batch
     }
   }
-  // the work queue, built by the lanes of the last warp (lane c = class c; the grouping of the table rules is computed
-  // redundantly by every lane from shuffled counts).  Items: near classes (largest rules first), far bins too small
-  // for a table (evaluated from the vertices), then the table rules by decreasing size.  Table rules are packed into
-  // groups whose point tables fit the shared-memory pool together; a group is one barrier interval.
-  if (warp == NW - 1) {
-    const int n = lane < NCLS ? pb.cnt[lane] : 0;
-    const bool near_c = lane >= 7;
-    const bool is_tab = lane <= kTabClsMax && n >= kTabMin;
-    const bool is_c0 = lane < NCLS && n > 0 && !is_tab;
-    const int nbat = near_c ? (n + 1) / 2 : (n + 31) / 32;
-    const unsigned m_c0 = __ballot_sync(0xffffffffu, is_c0), m_tab = __ballot_sync(0xffffffffu, is_tab);
-    const int nq0 = __popc(m_c0);
-    if (is_c0) {  // classes in descending order
-      const int q = __popc(m_c0 >> (lane + 1));
+  if (warp == NW - 1) {  // queue: classes in descending order (near rules first, largest first)
+    const int n = (lane < NCLS && lane > kTabClsMax) ? pb.cnt[lane] : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, n > 0);
+    const int nbat = lane >= 7 ? (n + 1) / 2 : (n + 31) / 32;
+    if (n > 0) {
+      const int q = __popc(m >> (lane + 1));
       pb.qcls[q] = lane;
       pb.qnb[q] = nbat;
     }
-    int nb0 = is_c0 ? nbat : 0;  // batches of the vertex / analytic items: all in group 0
+    int tot = n > 0 ? nbat : 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nb0 += __shfl_xor_sync(0xffffffffu, nb0, o);
-    // table rules, descending; every lane replays the packing
-    int nq = nq0, ng = 0, pts = 0, nb = nb0;
-    int my_q = -1, my_pt = 0;
-    int gq0_ = 0;  // first item of the open group
-#pragma unroll
-    for (int c = kTabClsMax; c >= 0; c--) {
-      const int nbc = __shfl_sync(0xffffffffu, nbat, c);
-      if (!((m_tab >> c) & 1u)) continue;
-      constexpr int npc[7] = {6, 7, 12, 15, 16, 19, 25};
-      if (pts + npc[c] > kTabPts) {  // close the group
-        if (lane == 0) {
-          pb.gq0[ng] = gq0_;
-          pb.gq1[ng] = nq;
-          pb.gnb[ng] = nb;
-        }
-        ng++;
-        gq0_ = nq;
-        nb = 0;
-        pts = 0;
-      }
-      if (lane == c) {
-        my_q = nq;
-        my_pt = pts;
-      }
-      nb += nbc;
-      pts += npc[c];
-      nq++;
-    }
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     if (lane == 0) {
-      pb.gq0[ng] = gq0_;
-      pb.gq1[ng] = nq;
-      pb.gnb[ng] = nb;
-      pb.ng = ng + 1;
-    }
-    if (my_q >= 0) {
-      pb.qcls[my_q] = lane | 16;  // bit 4: evaluate from the tables
-      pb.qnb[my_q] = nbat;
-      pb.qpt[my_q] = my_pt;
-    }
-    if (lane < 7) {  // statistics: far pairs and 1/r evaluations of this pass
-      constexpr int np2[7] = {36, 49, 144, 225, 256, 361, 625};
-      st_far += n;
-      st_eval += (unsigned long long)n * np2[lane];
+      pb.nq = __popc(m);
+      pb.qtotal = tot;
     }
   }
-  // ---------------- scatter the pair ids into the bins ------------------------------------------------------  // @region B_scatter
   unsigned long long used = 0;  // 4 bits per class: pairs of this thread already placed
 #pragma unroll 1
   for (int m = 0; m < NIT; m++) {
@@ -681,27 +693,26 @@ __device__ __forceinline__ void prep_classify(Smem& S, const LmatArgs& A, const 
       const int excl = (int)(((cls < 6 ? s0 : s1) >> (10 * (cls % 6))) & 1023ull);
       const int mine = (int)((used >> (4 * cls)) & 15ull);
       used += 1ull << (4 * cls);
-      pb.list[st + excl + mine] = (unsigned short)(c1 * kCH + c2b + m);
+      pb.olist[st + excl + mine] = (unsigned short)(c1 * kCH + c2b + m);
     }
   }
-  __syncthreads();  // lists, queue; the FP32 scratch is dead: the table region may be written
 }
 
-// ---- evaluation: T(c1,c2) of one pass -----------------------------------------------------------------
-// one batch of the work queue: 32 far pairs of one rule (from the vertices) or 2 near pairs.
+// ---- evaluation from the block-wide lists ------------------------------------------------------------------------
+// one batch of the other classes: 32 far pairs of one rule (from the vertices) or 2 near pairs.
 // List entries are (c1<<6 | c2).
 __device__ __forceinline__ void run_batch_c0(const ChunkState& I, const ChunkState& J, const PassBuf& pb, double* __restrict__ T,  // @region run_batch_c0
                                              int cls, int first, int lane, bool role2_pass, unsigned long long& st_near,
                                              unsigned long long& st_phi) {
   if (cls < 7) {
-    const unsigned e = pb.list[first + lane];
+    const unsigned e = pb.olist[first + lane];
     if (e != 0xFFFFu) {
       const int c1 = e >> 6, c2 = e & 63;
       T[c1 * TS + c2] = far_dispatch(I.g, c1, J.g, c2, cls + 4);
     }
   } else {
     const int hw = lane >> 4, hl = lane & 15;
-    const unsigned e = pb.list[first + hw];
+    const unsigned e = pb.olist[first + hw];
     unsigned m = 0;
     int c1 = 0, c2 = 0, iq = 18;
     if (e != 0xFFFFu) {
@@ -727,56 +738,52 @@ __device__ __forceinline__ void run_batch_c0(const ChunkState& I, const ChunkSta
   }
 }
 
-__device__ __forceinline__ void eval_pass(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int tid,
-                                          unsigned long long& st_near, unsigned long long& st_phi) {
+// partial batches of the tabled classes handed over by the warps (complete after the sweep's barrier)
+__device__ __forceinline__ void eval_leftovers(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int tid) {  // @region eval_leftovers
   PassBuf& pb = S.pb;
-  double* __restrict__ T = S.T;
   const int lane = tid & 31;
-  const int ncI = I.ncell, ncJ = J.ncell;
-  const double ox = 0.5 * (I.cx + J.cx), oy = 0.5 * (I.cy + J.cy), oz = 0.5 * (I.cz + J.cz);
-  const int ngroups = pb.ng;
-#pragma unroll 1
-  for (int g = 0; g < ngroups; g++) {  // @region C_eval
-    if (g > 0) {
-      __syncthreads();  // previous group is done with the table pool and the queue head
-      if (tid == 0) pb.qhead = 0;
+  const int n0 = pb.nleft[0], n1 = pb.nleft[1], n2 = pb.nleft[2];
+  const int b0 = (n0 + 31) >> 5, b1 = (n1 + 31) >> 5, b2 = (n2 + 31) >> 5;
+  const int total = b0 + b1 + b2;
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(&pb.lhead, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= total) break;
+    if (A.debug_skip & 2) continue;
+    if (b < b0) {
+      const int i = b * 32 + lane;
+      tab_eval<0>(S, I, J, i < n0 ? pb.left[0][i] : 0xFFFFu);
+    } else if (b < b0 + b1) {
+      const int i = (b - b0) * 32 + lane;
+      tab_eval<1>(S, I, J, i < n1 ? pb.left[1][i] : 0xFFFFu);
+    } else {
+      const int i = (b - b0 - b1) * 32 + lane;
+      tab_eval<2>(S, I, J, i < n2 ? pb.left[2][i] : 0xFFFFu);
     }
-    const int q0 = pb.gq0[g], q1 = pb.gq1[g], total = pb.gnb[g];
-    bool any_tab = false;
-    for (int k = q0; k < q1; k++) {
-      const int qc = pb.qcls[k];
-      if (!(qc & 16)) continue;
-      any_tab = true;
-      const int cls = qc & 15, pt = pb.qpt[k];
-      build_table(S.u.tab.tabI + pt * 2 * CI, CI, I.g, 0, ncI, cls + 4, c_cls_np[cls], ox, oy, oz, true, tid, NT);
-      build_table(S.u.tab.tabJ + pt * 2 * kCH, kCH, J.g, 0, ncJ, cls + 4, c_cls_np[cls], ox, oy, oz, false, tid, NT);
+  }
+}
+
+// other classes from the sorted list through the dynamic queue
+__device__ __forceinline__ void eval_others(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int tid,  // @region eval_others
+                                            unsigned long long& st_near, unsigned long long& st_phi) {
+  PassBuf& pb = S.pb;
+  const int lane = tid & 31;
+  const int total = pb.qtotal;
+  int bnext = 0;
+  if (lane == 0) bnext = atomicAdd(&pb.qhead, 1);
+  for (;;) {
+    const int b = __shfl_sync(0xffffffffu, bnext, 0);
+    if (b >= total) break;
+    if (lane == 0) bnext = atomicAdd(&pb.qhead, 1);  // the next batch index is fetched while this one is evaluated
+    int k = 0, lb = b;
+    while (lb >= pb.qnb[k]) {
+      lb -= pb.qnb[k];
+      k++;
     }
-    if (any_tab || g > 0) __syncthreads();
-    // dynamic queue; the next batch index is fetched while the current batch is evaluated
-    int bnext = 0;
-    if (lane == 0) bnext = atomicAdd(&pb.qhead, 1);
-    for (;;) {
-      const int b = __shfl_sync(0xffffffffu, bnext, 0);
-      if (b >= total) break;
-      if (lane == 0) bnext = atomicAdd(&pb.qhead, 1);
-      int k = q0, lb = b;
-      while (lb >= pb.qnb[k]) {
-        lb -= pb.qnb[k];
-        k++;
-      }
-      const int qc = pb.qcls[k], cls = qc & 15;
-      if (A.debug_skip && ((cls >= 7) ? (A.debug_skip & 1) : (A.debug_skip & 2))) continue;
-      if (qc & 16) {
-        const unsigned e = pb.list[pb.off[cls] + lb * 32 + lane];
-        if (e != 0xFFFFu) {
-          const int c1 = e >> 6, c2 = e & 63, pt = pb.qpt[k];
-          T[c1 * TS + c2] = far_tab_dispatch(S.u.tab.tabI + pt * 2 * CI, S.u.tab.tabJ + pt * 2 * kCH, c1, c2, cls) * I.g[9 * kCH + c1] *
-                            J.g[9 * kCH + c2];
-        }
-      } else {
-        run_batch_c0(I, J, pb, T, cls, pb.off[cls] + lb * (cls >= 7 ? 2 : 32), lane, false, st_near, st_phi);
-      }
-    }
+    const int cls = pb.qcls[k];
+    if (A.debug_skip && ((cls >= 7) ? (A.debug_skip & 1) : (A.debug_skip & 2))) continue;
+    run_batch_c0(I, J, pb, S.T, cls, pb.off[cls] + lb * (cls >= 7 ? 2 : 32), lane, false, st_near, st_phi);
   }
 }
 
@@ -807,107 +814,114 @@ __device__ __forceinline__ void eval_role2(Smem& S, const LmatArgs& A, const Chu
   }
 }
 
-// ---- drain: contraction of T onto the DOFs, added into L ------------------------------------------------
-// A warp takes column DOFs b = warp, warp+16, ... in blocks of DB.  For a block the old values of all its
-// entries (row DOFs a = lane, lane+32; entry (a,b) and its mirror) are loaded first, so one memory latency is
-// paid per block.  Then per b -- stage 1, lanes = row cells c1 (two per lane):
-// u(c1) = sum_{(c2,k2) of b} +-q2[c2][k2] T[c1][c2]; the three products q1[c1][k].u(c1) (cell c1's contribution
-// to its vertices) go to a per-warp scratch; stage 2, lanes = row DOFs a: sum of the scratch entries of a's
-// cells, added to the old value and stored.  Every entry is owned by this CTA: plain loads and stores, no
-// atomics, no block-wide barriers.
+// ---- contraction of T onto the DOFs, fused with the update of L -------------------------------------------------
+// A warp takes row DOFs a = warp, warp+16, ... of the row chunk.  Stage 1, lanes = column cells c2 (two per lane):
+// v(c2) = sum_{(c1,k1) of a} +-q1[c1][k1] T[c1][c2]; the three products q2[c2][k].v(c2) (cell c2's contribution to
+// its vertices) go to a per-warp scratch.  Stage 2, lanes = column DOFs b (ascending reference ids: neighbouring lanes
+// touch neighbouring addresses of row a): sum of the scratch entries of b's cells, added to the old value (loaded
+// before stage 1) and stored.  Transposed entries (tiles whose column patch's rows are owned and not left to the
+// symmetrisation pass) get the same value with one store per lane.  Every entry is owned by this CTA: plain loads
+// and stores, no atomics, no block-wide barriers.
 // role_sel 0: all entries; 1: only entries with a <= b (a second-role pass follows); 2: only a > b
-struct DrainSel {
-  const LmatArgs* A;
-  bool diag, mirror;  // mirror: write the transposed entry too
-  int role_sel;
-  // output addresses of entry (ia, ib) and of its mirror; false if the entry is not written in this pass
-  __device__ __forceinline__ bool addr(const ChunkState& I, const ChunkState& J, int ia, int ib, double*& pa, double*& pm) const {
-    pa = nullptr;
-    pm = nullptr;
-    const int oa = I.x.orig[ia], ob = J.x.orig[ib];
-    if (A->self) {
-      const bool role1 = oa <= ob;
-      if ((diag && !role1) || (role_sel == 1 && !role1) || (role_sel == 2 && role1)) return false;
-    }
-    const int ra = I.row[ia];
-    const int oc = A->col_map ? A->col_map[ob] : ob;
-    if (ra >= 0 && oc >= 0) pa = A->out + (long long)ra * A->ld + oc;
-    if (A->self && mirror && oa != ob) {
-      const int rb = J.row[ib];
-      if (rb >= 0) pm = A->out + (long long)rb * A->ld + oa;
-    }
-    return pa || pm;
-  }
-};
-
 __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int flags, int role_sel,  // @region D_drain
                                            int tid) {
   const double* __restrict__ T = S.T;
-  DrainSel sel;
-  sel.A = &A;
-  sel.diag = flags & 1;
-  sel.mirror = (flags & 3) && !(flags & 8);
-  sel.role_sel = role_sel;
+  const bool diag = flags & 1, mirror = A.self && (flags & 3) && !(flags & 8);
   const int ndI = I.ndof, ndJ = J.ndof;
   const int lane = tid & 31, warp = tid >> 5;
-  double* __restrict__ P = S.u.w.P[warp];  // [3][CI] products of this warp
-  double* __restrict__ E = S.u.w.E;        // [row DOF < 64][column DOF < 64] contribution of this pass, stride TS
-  const int lim = A.fast_lim;              // 64 (tests of the direct-write path: 32 or 0)
-  // ---- D1: contributions of the pass.  This lane's row DOFs a = lane, lane+32 with their incidence lists (scratch
-  // index k*64+cell = low 8 bits of the incidence code, bit 8 = negative) packed in registers (longer lists: slow path)
+  double* __restrict__ P = S.u.P[warp];  // [3][kCH] products of this warp
+  const int lim = A.fast_lim;            // 64 (tests of the generic path: 32 or 0)
+  // this lane's column DOFs b = lane, lane+32: reference id, output column, incidence list (scratch index k*64+cell = low 8
+  // bits of the incidence code, bit 8 = negative) packed in registers (longer lists: generic path)
   constexpr int MI = 8;
-  int ninc[2];
+  int ninc[2], ob[2], oc[2], rb[2];
   unsigned codes[2][MI / 2];
 #pragma unroll
   for (int r = 0; r < 2; r++) {
-    const int ia = lane + 32 * r;
-    ninc[r] = 0;
+    const int ib = lane + 32 * r;
+    ninc[r] = -1;  // -1: not handled here
+    ob[r] = 0;
+    oc[r] = -1;
+    rb[r] = -1;
 #pragma unroll
     for (int i = 0; i < MI / 2; i++) codes[r][i] = 0;
-    if (ia < ndI) {
-      const int i0 = I.x.iptr[ia];
-      ninc[r] = I.x.iptr[ia + 1] - i0;
+    if (ib < ndJ && ib < lim) {
+      const int i0 = J.x.iptr[ib];
+      const int n = J.x.iptr[ib + 1] - i0;
+      if (n <= MI) {
+        ninc[r] = n;
 #pragma unroll
-      for (int i = 0; i < MI; i++)
-        if (i < ninc[r]) codes[r][i >> 1] |= (unsigned)I.x.inc[i0 + i] << (16 * (i & 1));
+        for (int i = 0; i < MI; i++)
+          if (i < n) codes[r][i >> 1] |= (unsigned)J.x.inc[i0 + i] << (16 * (i & 1));
+      } else {
+        ninc[r] = MI + 1;  // long list: summed from shared memory
+      }
+      ob[r] = J.x.orig[ib];
+      oc[r] = A.col_map ? A.col_map[ob[r]] : ob[r];
+      rb[r] = mirror ? J.row[ib] : -1;
     }
   }
+  auto wanted = [&](int oa, int obv) {  // role rule of entry (a, b)
+    if (!A.self) return true;
+    const bool role1 = oa <= obv;
+    return !((diag && !role1) || (role_sel == 1 && !role1) || (role_sel == 2 && role1));
+  };
+  auto col_sum = [&](int ib) {  // generic: contribution to column DOF ib from the scratch
+    double acc = 0.0;
+    for (int i = J.x.iptr[ib]; i < J.x.iptr[ib + 1]; i++) {
+      const unsigned w = J.x.inc[i];
+      const double v = P[w & 255u];
+      acc += (w & 256u) ? -v : v;
+    }
+    return acc;
+  };
 #pragma unroll 1
-  for (int ib = warp; ib < ndJ; ib += NW) {
+  for (int ia = warp; ia < ndI; ia += NW) {
+    const int ra = I.row[ia];
+    if (ra < 0 && !mirror) continue;
+    const int oa = I.x.orig[ia];
+    double* const rowp = A.out + (long long)(ra >= 0 ? ra : 0) * A.ld;
+    // old values of the direct entries
+    double old[2];
+    bool use[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      use[r] = ninc[r] >= 0 && wanted(oa, ob[r]);
+      old[r] = 0.0;
+      if (use[r] && ra >= 0 && oc[r] >= 0) old[r] = __ldcg(rowp + oc[r]);
+    }
     // stage 1
-    double ux0 = 0.0, uy0 = 0.0, uz0 = 0.0, ux1 = 0.0, uy1 = 0.0, uz1 = 0.0;
-    const int i2e = J.x.iptr[ib + 1];
+    double vx0 = 0.0, vy0 = 0.0, vz0 = 0.0, vx1 = 0.0, vy1 = 0.0, vz1 = 0.0;
+    const int i1e = I.x.iptr[ia + 1];
 #pragma unroll 4
-    for (int i2 = J.x.iptr[ib]; i2 < i2e; i2++) {
-      const unsigned w2 = J.x.inc[i2];
-      const int c2 = w2 & 63, k2 = (w2 >> 6) & 3;
-      double t0 = T[lane * TS + c2], t1 = T[(lane + 32) * TS + c2];
-      if (w2 & 256) {
+    for (int i1 = I.x.iptr[ia]; i1 < i1e; i1++) {
+      const unsigned w1 = I.x.inc[i1];
+      const int c1 = w1 & 63, k1 = (w1 >> 6) & 3;
+      double t0 = T[c1 * TS + lane], t1 = T[c1 * TS + lane + 32];
+      if (w1 & 256) {
         t0 = -t0;
         t1 = -t1;
       }
-      const double qx = J.g[(10 + 3 * k2) * kCH + c2], qy = J.g[(11 + 3 * k2) * kCH + c2], qz = J.g[(12 + 3 * k2) * kCH + c2];
-      ux0 = fma(qx, t0, ux0);
-      uy0 = fma(qy, t0, uy0);
-      uz0 = fma(qz, t0, uz0);
-      ux1 = fma(qx, t1, ux1);
-      uy1 = fma(qy, t1, uy1);
-      uz1 = fma(qz, t1, uz1);
+      const double qx = I.g[(10 + 3 * k1) * kCH + c1], qy = I.g[(11 + 3 * k1) * kCH + c1], qz = I.g[(12 + 3 * k1) * kCH + c1];
+      vx0 = fma(qx, t0, vx0);
+      vy0 = fma(qy, t0, vy0);
+      vz0 = fma(qz, t0, vz0);
+      vx1 = fma(qx, t1, vx1);
+      vy1 = fma(qy, t1, vy1);
+      vz1 = fma(qz, t1, vz1);
     }
-    __syncwarp();  // stage 2 of the previous column DOF is done with the scratch
+    __syncwarp();  // stage 2 of the previous row DOF is done with the scratch
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      P[k * CI + lane] = fma(I.g[(12 + 3 * k) * kCH + lane], uz0, fma(I.g[(11 + 3 * k) * kCH + lane], uy0, I.g[(10 + 3 * k) * kCH + lane] * ux0));
-      P[k * CI + lane + 32] =
-          fma(I.g[(12 + 3 * k) * kCH + lane + 32], uz1, fma(I.g[(11 + 3 * k) * kCH + lane + 32], uy1, I.g[(10 + 3 * k) * kCH + lane + 32] * ux1));
+      P[k * kCH + lane] = fma(J.g[(12 + 3 * k) * kCH + lane], vz0, fma(J.g[(11 + 3 * k) * kCH + lane], vy0, J.g[(10 + 3 * k) * kCH + lane] * vx0));
+      P[k * kCH + lane + 32] =
+          fma(J.g[(12 + 3 * k) * kCH + lane + 32], vz1, fma(J.g[(11 + 3 * k) * kCH + lane + 32], vy1, J.g[(10 + 3 * k) * kCH + lane + 32] * vx1));
     }
     __syncwarp();
     // stage 2
-    const bool fast_b = ib < lim;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-      const int ia = lane + 32 * r;
-      if (ia >= ndI || 32 * r >= lim) continue;
+      if (!use[r]) continue;
       double acc = 0.0;
       if (ninc[r] <= MI) {
 #pragma unroll
@@ -919,111 +933,31 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
           }
         }
       } else {
-        for (int i1 = I.x.iptr[ia]; i1 < I.x.iptr[ia + 1]; i1++) {
-          const unsigned w1 = I.x.inc[i1];
-          const double v = P[w1 & 255u];
-          acc += (w1 & 256u) ? -v : v;
-        }
+        acc = col_sum(lane + 32 * r);
       }
-      if (fast_b) {
-        E[ia * TS + ib] = acc;
-      } else {  // more than 64 column DOFs in the chunk (rare): write directly
-        double *pa, *pm;
-        if (sel.addr(I, J, ia, ib, pa, pm)) {
-          if (pa) __stcg(pa, fma(acc, A.scale, __ldcg(pa)));  // (every path: one fused scale-and-add)
-          if (pm) __stcg(pm, fma(acc, A.scale, __ldcg(pm)));
-        }
+      if (ra >= 0 && oc[r] >= 0) __stcg(rowp + oc[r], fma(acc, A.scale, old[r]));  // (every path: one fused scale-and-add)
+      if (rb[r] >= 0 && oa != ob[r]) {
+        double* pm = A.out + (long long)rb[r] * A.ld + oa;
+        __stcg(pm, fma(acc, A.scale, __ldcg(pm)));
       }
     }
-    // more than 64 row DOFs in the chunk (rare): write directly
+    // column DOFs beyond the register-held ones (more than 64 per chunk: rare)
 #pragma unroll 1
-    for (int ia = lane + lim; ia < ndI; ia += 32) {
-      double *pa, *pm;
-      if (!sel.addr(I, J, ia, ib, pa, pm)) continue;
-      double acc = 0.0;
-      for (int i1 = I.x.iptr[ia]; i1 < I.x.iptr[ia + 1]; i1++) {
-        const unsigned w1 = I.x.inc[i1];
-        const double v = P[w1 & 255u];
-        acc += (w1 & 256u) ? -v : v;
-      }
-      if (pa) __stcg(pa, fma(acc, A.scale, __ldcg(pa)));  // (every path: one fused scale-and-add)
-      if (pm) __stcg(pm, fma(acc, A.scale, __ldcg(pm)));
-    }
-  }
-  __syncthreads();  // the block E is complete
-  TW_MARK(S, 0, tid, 7)
-  // ---- D2: add the block into L.  A warp takes rows a = warp, warp+16, ...; lanes run over the column DOFs, whose
-  // reference ids ascend within a chunk: neighbouring lanes touch neighbouring addresses of one matrix row.  The old
-  // values of all the warp's entries are loaded first (one memory latency), then added and stored.  Every entry is
-  // owned by this CTA: plain loads and stores, no atomics.
-  const int nbJ = min(ndJ, lim), naI = min(ndI, lim);
-  {
-    int ob[2], oc[2];  // reference id (role rule) and output column of this lane's column DOFs
-    ob[0] = lane < nbJ ? J.x.orig[lane] : 0;
-    ob[1] = lane + 32 < nbJ ? J.x.orig[lane + 32] : 0;
-    oc[0] = A.col_map ? (lane < nbJ ? A.col_map[ob[0]] : -1) : ob[0];
-    oc[1] = A.col_map ? (lane + 32 < nbJ ? A.col_map[ob[1]] : -1) : ob[1];
-    constexpr int RW = kCH / NW;  // rows per warp
-    double old[RW][2];
-    unsigned use = 0;
-#pragma unroll
-    for (int q = 0; q < RW; q++) {
-      const int ia = warp + NW * q;
-      double* rowp = nullptr;
-      int oa = 0;
-      if (ia < naI) {
-        const int ra = I.row[ia];
-        oa = I.x.orig[ia];
-        if (ra >= 0) rowp = A.out + (long long)ra * A.ld;
-      }
-#pragma unroll
-      for (int hb = 0; hb < 2; hb++) {
-        old[q][hb] = 0.0;
-        bool ok = rowp != nullptr && lane + 32 * hb < nbJ && oc[hb] >= 0;
-        if (ok && A.self) {
-          const bool role1 = oa <= ob[hb];
-          if ((sel.diag && !role1) || (role_sel == 1 && !role1) || (role_sel == 2 && role1)) ok = false;
-        }
-        if (ok) {
-          use |= 1u << (2 * q + hb);
-          old[q][hb] = __ldcg(rowp + oc[hb]);
+    for (int ib = lane + min(lim, 64); ib < ndJ; ib += 32) {
+      const int obv = J.x.orig[ib];
+      if (!wanted(oa, obv)) continue;
+      const double acc = col_sum(ib);
+      const int ocv = A.col_map ? A.col_map[obv] : obv;
+      if (ra >= 0 && ocv >= 0) __stcg(rowp + ocv, fma(acc, A.scale, __ldcg(rowp + ocv)));
+      if (mirror && oa != obv) {
+        const int rbv = J.row[ib];
+        if (rbv >= 0) {
+          double* pm = A.out + (long long)rbv * A.ld + oa;
+          __stcg(pm, fma(acc, A.scale, __ldcg(pm)));
         }
       }
     }
-#pragma unroll
-    for (int q = 0; q < RW; q++) {
-      const int ia = warp + NW * q;
-      if (ia >= naI) continue;
-      const int ra = I.row[ia];
-      double* rowp = A.out + (long long)(ra >= 0 ? ra : 0) * A.ld;
-#pragma unroll
-      for (int hb = 0; hb < 2; hb++)
-        if ((use >> (2 * q + hb)) & 1u) __stcg(rowp + oc[hb], fma(E[ia * TS + lane + 32 * hb], A.scale, old[q][hb]));
-    }
   }
-  if (sel.mirror) {  // transposed entries (rows of the column patch are in the output block, rows of this patch are not)
-    int oa[2];
-    oa[0] = lane < naI ? I.x.orig[lane] : 0;
-    oa[1] = lane + 32 < naI ? I.x.orig[lane + 32] : 0;
-#pragma unroll 1
-    for (int ib = warp; ib < nbJ; ib += NW) {
-      const int rb = J.row[ib];
-      if (rb < 0) continue;
-      const int ob = J.x.orig[ib];
-      double* rowp = A.out + (long long)rb * A.ld;
-#pragma unroll
-      for (int ha = 0; ha < 2; ha++) {
-        const int ia = lane + 32 * ha;
-        if (ia >= naI || oa[ha] == ob) continue;
-        if (A.self) {
-          const bool role1 = oa[ha] <= ob;
-          if ((sel.diag && !role1) || (role_sel == 1 && !role1) || (role_sel == 2 && role1)) continue;
-        }
-        __stcg(rowp + oa[ha], fma(E[ia * TS + ib], A.scale, __ldcg(rowp + oa[ha])));
-      }
-    }
-  }
-  TW_MARK(S, 0, tid, 8)
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------
@@ -1037,10 +971,6 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {  /
     mbar_init(&S.J[1].bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-#ifdef TW_LMAT_PROF
-  if (tid < 16) S.prof[tid] = 0;
-  if (tid < 2) S.prof_last[tid] = clock64();
-#endif
   __syncthreads();
   uint32_t phI = 0, phJ = 0;  // mbarrier phases: row slot, bit s = column slot s
   unsigned long long st_far = 0, st_near = 0, st_eval = 0, st_phi = 0;
@@ -1067,51 +997,65 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {  /
       stage_issue(S.J[0], 1, A, cj0);
     }
     __syncthreads();  // chunk headers written by the staging thread
-    mbar_wait(&S.I.bar, phI);
-    phI ^= 1;
-    TW_MARK(S, 0, tid, 0)
     for (int ci = ci0; ci < ci1; ci++) {  // @region chunk_loop
+      mbar_wait(&S.I.bar, phI);
+      phI ^= 1;
+      const ChunkState& I = S.I;
+      const double ox = I.cx, oy = I.cy, oz = I.cz;
+      // row side of the sweep (first used after the barrier of the first pass)
+      prep_chunk(I, S.vfI, S.flI, S.cenI, S.tabI, true, ox, oy, oz, tid);
       for (int cj = cj0; cj < cj1; cj++) {
-        const ChunkState& I = S.I;
         const ChunkState& J = S.J[js];
         mbar_wait(&S.J[js].bar, (phJ >> js) & 1u);
         phJ ^= 1u << js;
-        prep_stage(S, I, J, tid);
-        __syncthreads();  // pass barrier: FP32 copies ready; everybody is done with the previous pass
-        TW_MARK(S, 0, tid, 1)
+        // (everybody is done with the previous pass: barrier at its end)
         // prefetch the next column chunk (its slot was used by the previous pass)
         const bool lastj = cj + 1 == cj1, lasti = ci + 1 == ci1;
         if (tid == 0 && !(lastj && lasti)) stage_issue(S.J[js ^ 1], 1, A, lastj ? cj0 : cj + 1);
-        prep_classify(S, A, I, J, flags, tid, st_far, st_eval);
-        TW_MARK(S, 0, tid, 2)
+        prep_chunk(J, S.vfJ, S.flJ, S.cenJ, S.u.tabJ, false, ox, oy, oz, tid);
+        if (tid < NCLS) {
+          S.pb.cnt[tid] = 0;
+          S.pb.pos[tid] = 0;
+        }
+        if (tid < kTabClsMax + 1) S.pb.nleft[tid] = 0;
+        if (tid == 0) {
+          S.pb.rowhead = 0;
+          S.pb.lhead = 0;
+          S.pb.qhead = 0;
+          S.pb.both_count = 0;
+        }
+        __syncthreads();  // tables, FP32 copies and counters of the pass
+        sweep_rows(S, A, I, J, flags, tid, st_far, st_eval);
+        __syncthreads();  // T of the full batches, partial batches, pair codes and class counts complete
+        int nother = 0;
+#pragma unroll
+        for (int c = kTabClsMax + 1; c < NCLS; c++) nother += S.pb.cnt[c];
+        if (nother) bin_others(S, I, tid);
+        eval_leftovers(S, A, I, J, tid);
+        if (nother) {
+          __syncthreads();  // bins and queue of the other classes
+          eval_others(S, A, I, J, tid, st_near, st_phi);
+        }
         const bool two_pass = S.pb.both_count > 0;
-        eval_pass(S, A, I, J, tid, st_near, st_phi);
-        __syncthreads();  // T complete; the table region is free for the contraction scratch
-        TW_MARK(S, 0, tid, 3)
+        __syncthreads();  // T complete; the column tables are dead: their memory is the contraction scratch
         if (!(A.debug_skip & 4)) drain_pass(S, A, I, J, flags, two_pass ? 1 : 0, tid);
         if (two_pass) {
-          if (tid == 0) S.pb.qhead = 0;
           __syncthreads();  // first contraction done with T
+          if (tid == 0) S.pb.qhead = 0;
+          __syncthreads();
           eval_role2(S, A, I, J, tid, st_near, st_phi);
           __syncthreads();
           if (!(A.debug_skip & 4)) drain_pass(S, A, I, J, flags, 2, tid);
         }
-        TW_MARK(S, 0, tid, 4)
+        __syncthreads();  // pass done: T, lists, scratch and the other column slot are free
         js ^= 1;
       }
       if (ci + 1 < ci1) {
-        __syncthreads();  // everybody is done with the row chunk
-        if (tid == 0) stage_issue(S.I, 0, A, ci + 1);
-        __syncthreads();
-        mbar_wait(&S.I.bar, phI);
-        phI ^= 1;
+        if (tid == 0) stage_issue(S.I, 0, A, ci + 1);  // (the barrier at the end of the last pass: nobody reads the row chunk)
+        __syncthreads();  // chunk header
       }
     }
   }
-#ifdef TW_LMAT_PROF
-  __syncthreads();
-  if (A.stats && blockIdx.x == 0 && tid < 16) A.stats[8 + tid] = (unsigned long long)S.prof[tid];
-#endif
   if (A.stats && tid == 0) {  // load balance: first / last CTA finish time (ns, globaltimer)  // @region tail
     unsigned long long tend;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tend));

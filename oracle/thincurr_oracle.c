@@ -708,12 +708,17 @@ static int cell_dofs(const tco_model *m, int c, int *dof, double (*E)[3]) {
   return n;
 }
 
-void tco_lmat_rows(const tco_model *m, int nd, const int *dofs, double *out) {
+/* absum (optional): A[r][b] = sum of the magnitudes of the terms entry (a_r, b) is summed from.  |L| << A marks entries
+ * dominated by cancellation, where the reference's own result moves by ~eps*A with the (atomic, thread-dependent)
+ * summation order (thin_wall.F90:1092-1121). */
+void tco_lmat_rows2(const tco_model *m, int nd, const int *dofs, double *out, double *absum) {
   const long long N = m->nelems;
   memset(out, 0, sizeof(double) * (size_t)nd * (size_t)N);
+  if (absum) memset(absum, 0, sizeof(double) * (size_t)nd * (size_t)N);
   for (int r = 0; r < nd; r++) {
     const int a = dofs[r];
     double *row = out + (size_t)r * N;
+    double *arow = absum ? absum + (size_t)r * N : NULL;
     for (int c1 = 0; c1 < m->nc; c1++) {
       int d1[16];
       double E1[16][3];
@@ -745,8 +750,14 @@ void tco_lmat_rows(const tco_model *m, int nd, const int *dofs, double *out) {
           const double v = dot3(E1[s1], E2[s]) * T / (4.0 * PI);
 #pragma omp atomic
           row[b] += v;
+          if (arow) {
+#pragma omp atomic
+            arow[b] += fabs(v);
+          }
         }
       }
     }
   }
 }
+
+void tco_lmat_rows(const tco_model *m, int nd, const int *dofs, double *out) { tco_lmat_rows2(m, nd, dofs, out, NULL); }

@@ -512,14 +512,20 @@ class OracleModel:
             self.Lmat = Lm
         return Lm
 
-    def lmat_rows(self, dofs):
+    def lmat_rows(self, dofs, with_abs=False):
         """Rows of the self-inductance matrix (vertex/hole DOFs, 0-based) from the per-entry
-        definition; independent of the loop-nest restatement in compute_Lmat."""
+        definition; independent of the loop-nest restatement in compute_Lmat.
+        with_abs: also the sum of the magnitudes of the terms of every entry (conditioning of the sum)."""
         dofs = np.ascontiguousarray(dofs, np.int32)
         out = np.zeros((len(dofs), self.nelems))
-        lib().tco_lmat_rows(ctypes.byref(self.c), ctypes.c_int(len(dofs)), dofs.ctypes.data_as(ctypes.c_void_p),
-                            out.ctypes.data_as(ctypes.c_void_p))
-        return out
+        if not with_abs:
+            lib().tco_lmat_rows(ctypes.byref(self.c), ctypes.c_int(len(dofs)), dofs.ctypes.data_as(ctypes.c_void_p),
+                                out.ctypes.data_as(ctypes.c_void_p))
+            return out
+        ab = np.zeros_like(out)
+        lib().tco_lmat_rows2(ctypes.byref(self.c), ctypes.c_int(len(dofs)), dofs.ctypes.data_as(ctypes.c_void_p),
+                             out.ctypes.data_as(ctypes.c_void_p), ab.ctypes.data_as(ctypes.c_void_p))
+        return out, ab
 
     def cross_coupling(self, other):
         """tw_compute_LmatDirect(self, M, col_model=other); returns Python view (self.nelems, other.nelems)."""
