@@ -107,12 +107,14 @@ int visible_devices() {
   return n;
 }
 
-std::string ensure_plan(Model& m) {
+// nshards: how many devices the first build that needs the plan spreads the rows over (sizes the patches so that every
+// device still gets enough tiles); the plan is kept for the lifetime of the model whatever later calls ask for
+std::string ensure_plan(Model& m, int nshards) {
   if (m.plan) return "";
   auto pl = std::make_shared<Plan>();
   int P = 0;
   if (const char* e = std::getenv("THINCURR_B200_PATCH")) P = std::atoi(e);
-  std::string err = build_patches(m, P, pl->ps);
+  std::string err = build_patches(m, P, pl->ps, std::max(1, nshards));
   if (!err.empty()) return err;
   m.plan = pl;
   return "";
@@ -171,13 +173,16 @@ std::vector<int> band_cuts(const PatchSet& ps, int p0, int p1, int nbands) {
   return cuts;
 }
 
-// Number of bands of a single-device build whose rows go to the host: one band costs one extra kernel tail (~ the longest
-// tile), so small builds stay in one piece
+// Number of bands of a single-device build whose rows go to the host.  The copy of a band overlaps the build of the next
+// ones, so what stays exposed is the copy of the LAST band (1/n of the matrix at the ~55 GB/s of a PCIe 5 x16 link) plus
+// one kernel tail per band (about half a tile: 74 / ntiles of the build).  With c = copy time / build time (0.33 on
+// the 20k-vertex vessel, 0.85 at 100k) the sum c/n + n 74/ntiles is smallest at n = sqrt(c ntiles / 74).
 int auto_bands(const PatchSet& ps, int p0, int p1) {
   if (const char* e = std::getenv("THINCURR_B200_BANDS")) return std::max(1, std::atoi(e));
-  const long long np = p1 - p0;
-  const long long ntiles = np * (np + 1) / 2;
-  return (int)std::max(1LL, std::min(16LL, ntiles / 1200));
+  const double np = p1 - p0;
+  const double ntiles = np * (np + 1) / 2;
+  const double c = std::min(1.0, 0.25 + 0.6 * ps.ndof / 1.0e5);
+  return (int)std::max(1.0, std::min(16.0, std::floor(std::sqrt(c * ntiles / 74.0) + 0.5)));
 }
 
 // Build the self-inductance rows of one shard on the current device into d_out[nrows][ld]
@@ -191,7 +196,9 @@ std::string lmat_shard_device(Model& m, int nshards, int shard, double* d_out, l
   int device = 0;
   if (cudaGetDevice(&device) != cudaSuccess) return "No CUDA device available (there is no CPU fallback)";
   std::shared_ptr<DeviceState> ds;
-  std::string err = ensure_device(m, device, ds);
+  std::string err = ensure_plan(m, nshards);
+  if (!err.empty()) return err;
+  err = ensure_device(m, device, ds);
   if (!err.empty()) return err;
   if (m.n_vcoils > 0 && !m.have_coil_mutuals) return "Coil mutuals required if, # of Vcoils > 0";
   const PatchSet& ps = m.plan->ps;
@@ -508,7 +515,7 @@ static std::string lmat_full_host(Model& m, double* dst) {
   DeviceGuard guard;
   std::vector<int> devs_ids = build_devices();
   if (devs_ids.empty()) return "No CUDA device available (the B200 backend has no CPU fallback)";
-  std::string err = ensure_plan(m);
+  std::string err = ensure_plan(m, (int)devs_ids.size());
   if (!err.empty()) return err;
   const PatchSet& ps = m.plan->ps;
   int ndev = std::min((int)devs_ids.size(), std::max(1, ps.npatch));
@@ -994,7 +1001,7 @@ int thincurr_b200_msensor(void* tw_ptr, void* sensor_ptr, void** Ms_ptr, void** 
 
 int thincurr_b200_plan(void* tw_ptr, int nshards, int shard, int* nrows) {
   Model& m = *(Model*)tw_ptr;
-  std::string err = ensure_plan(m);
+  std::string err = ensure_plan(m, nshards);
   if (!err.empty()) return fail(err);
   if (nshards < 1 || shard < 0 || shard >= nshards) return fail("Invalid shard index");
   int p0, p1;
@@ -1052,7 +1059,7 @@ int thincurr_b200_plan_info(void* tw_ptr, int64_t* info) {
 
 int thincurr_b200_shard_rows(void* tw_ptr, int nshards, int shard, int* row_ids) {
   Model& m = *(Model*)tw_ptr;
-  std::string err = ensure_plan(m);
+  std::string err = ensure_plan(m, nshards);
   if (!err.empty()) return fail(err);
   int p0, p1;
   std::vector<int> rows;
@@ -1073,7 +1080,7 @@ int thincurr_b200_Lmat_shard(void* tw_ptr, int nshards, int shard, double* d_out
 
 int thincurr_b200_shard_rows_sym(void* tw_ptr, int nshards, int shard, int* nrows, int* row_ids) {
   Model& m = *(Model*)tw_ptr;
-  std::string err = ensure_plan(m);
+  std::string err = ensure_plan(m, nshards);
   if (!err.empty()) return fail(err);
   int p0, p1;
   std::vector<int> rows;
@@ -1105,7 +1112,7 @@ int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* 
   auto t0 = now();
   int device = 0;
   if (cudaGetDevice(&device) != cudaSuccess) return fail("No CUDA device available (there is no CPU fallback)");
-  std::string err = ensure_plan(m);
+  std::string err = ensure_plan(m, nshards);
   if (!err.empty()) return fail(err);
   std::shared_ptr<DeviceState> ds;
   err = ensure_device(m, device, ds);

@@ -61,7 +61,7 @@ constexpr int NCLS = 12;           // far classes 0..6 (iquad 4..10), near class
 constexpr int kTabMaxN = 25;       // largest rule far_tab is instantiated for (probes)
 constexpr int kTabClsMax = 2;      // far classes served from the shared-memory point tables by the tile kernel (rules 4, 5, 6)
 constexpr int kTabPts = 25;        // 6 + 7 + 12 points
-constexpr int kPend = 96;          // pending pairs per (warp, tabled class): < 32 left over + <= 64 of a new row
+constexpr int kPend = 64;          // pending pairs per (warp, tabled class): < 32 left over + <= 32 of a new unit
 constexpr int kLeft = 512;         // leftover pairs per tabled class and pass (< 32 per warp)
 constexpr int kOList = CI * kCH + (NCLS - 3) * 32;  // pairs of the other classes, bins padded to batches
 
@@ -111,7 +111,8 @@ struct alignas(16) PassBuf {
   unsigned char iqmap[CI * kCH];      // per pair: 0, or for a pair of another class iquad | need-role-1 << 5 | need-role-2 << 6
   int nleft[kTabClsMax + 1];
   int cnt[NCLS], pos[NCLS], off[NCLS + 1];
-  int qcls[NCLS], qnb[NCLS], nq, qtotal;
+  int qcls[NCLS], qnb[NCLS];          // queue items: class (| 16: whole-warp batches from on-demand tables), batches
+  int gq0[4], gq1[4], gnb[4], gcls[4], ngrp;  // groups: item range, batch count, tabled class (or -1)
   int rowhead, lhead, qhead, both_count;
 };
 
@@ -195,6 +196,117 @@ __device__ __noinline__ double far_dispatch(const double* gI, int c1, const doub
     case 8: return far_pair<16>(gI, c1, gJ, c2, iquad);
     case 9: return far_pair<19>(gI, c1, gJ, c2, iquad);
     default: return far_pair<25>(gI, c1, gJ, c2, iquad);
+  }
+}
+
+// ---- far field of the larger rules: a group of G lanes per pair -------------------------------------------------
+// The rules of 15..25 points are rare per pass (a few dozen pairs at the edge of the near field), so a pass cannot fill
+// warps with 32 pairs of one of them, and whole-warp batches would leave most warps idle.  G lanes share a pair: lane g
+// holds the column points q = g, g+G, ... in registers (frame centred on the row cell, (x,y,z,|x|^2)), the row points are
+// computed once per group (lane g takes p = g, g+G, ...) and handed round with shuffles, and the 1/r evaluation is the
+// same 10-instruction form as the table path.  Fixed summation order: deterministic.  All 32 lanes must call (shuffles).
+template <int N, int G>  // @region far_group
+__device__ __forceinline__ double far_group(const double* __restrict__ gI, int c1, const double* __restrict__ gJ, int c2, int iquad, int lane) {
+  constexpr int QG = (N + G - 1) / G;
+  const int g = lane & (G - 1), base = lane & ~(G - 1);
+  const double* bp = g_qpts + 3 * c_qoff[iquad];  // lane-dependent point index: global copy of the tables
+  const double* bwg = g_qwts + c_qoff[iquad];
+  const double* bwc = c_qwts + c_qoff[iquad];     // uniform index: constant bank
+  double Pi[9], Pj[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    Pi[k] = gI[k * kCH + c1];
+    Pj[k] = gJ[k * kCH + c2];
+  }
+  const double ox = (Pi[0] + Pi[3] + Pi[6]) * (1.0 / 3.0), oy = (Pi[1] + Pi[4] + Pi[7]) * (1.0 / 3.0), oz = (Pi[2] + Pi[5] + Pi[8]) * (1.0 / 3.0);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    Pi[3 * k] -= ox;
+    Pi[3 * k + 1] -= oy;
+    Pi[3 * k + 2] -= oz;
+    Pj[3 * k] -= ox;
+    Pj[3 * k + 1] -= oy;
+    Pj[3 * k + 2] -= oz;
+  }
+  double xj[QG], yj[QG], zj[QG], sj[QG], acc[QG];
+#pragma unroll
+  for (int m = 0; m < QG; m++) {
+    const int q = min(m * G + g, N - 1);  // the tail re-reads the last point (weight masked below)
+    const double b0 = bp[3 * q], b1 = bp[3 * q + 1], b2 = bp[3 * q + 2];
+    xj[m] = b0 * Pj[0] + b1 * Pj[3] + b2 * Pj[6];
+    yj[m] = b0 * Pj[1] + b1 * Pj[4] + b2 * Pj[7];
+    zj[m] = b0 * Pj[2] + b1 * Pj[5] + b2 * Pj[8];
+    sj[m] = fma(zj[m], zj[m], fma(yj[m], yj[m], xj[m] * xj[m]));
+    acc[m] = 0.0;
+  }
+#pragma unroll 1
+  for (int p0 = 0; p0 < N; p0 += G) {
+    // this lane's row point p0 + g as (-2x, -2y, -2z, |x|^2)
+    const int p = min(p0 + g, N - 1);
+    const double a0 = bp[3 * p], a1 = bp[3 * p + 1], a2 = bp[3 * p + 2];
+    const double xi = a0 * Pi[0] + a1 * Pi[3] + a2 * Pi[6], yi = a0 * Pi[1] + a1 * Pi[4] + a2 * Pi[7], zi = a0 * Pi[2] + a1 * Pi[5] + a2 * Pi[8];
+    const double si = fma(zi, zi, fma(yi, yi, xi * xi));
+    const double mx = -2.0 * xi, my = -2.0 * yi, mz = -2.0 * zi;
+#pragma unroll
+    for (int kk = 0; kk < G; kk++) {
+      if (p0 + kk < N) {  // uniform
+        const double ax = __shfl_sync(0xffffffffu, mx, base + kk), ay = __shfl_sync(0xffffffffu, my, base + kk),
+                     az = __shfl_sync(0xffffffffu, mz, base + kk), as = __shfl_sync(0xffffffffu, si, base + kk);
+        const double wp = bwc[p0 + kk];
+        double d2[QG], y0[QG], e[QG], h[QG];
+#pragma unroll
+        for (int m = 0; m < QG; m++) d2[m] = fma(ax, xj[m], fma(ay, yj[m], fma(az, zj[m], as + sj[m])));
+#pragma unroll
+        for (int m = 0; m < QG; m++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[m]) : "d"(d2[m]));
+#pragma unroll
+        for (int m = 0; m < QG; m++) h[m] = d2[m] * y0[m];
+#pragma unroll
+        for (int m = 0; m < QG; m++) e[m] = fma(-h[m], y0[m], 1.0);
+#pragma unroll
+        for (int m = 0; m < QG; m++) h[m] = fma(0.375, e[m], 0.5);
+#pragma unroll
+        for (int m = 0; m < QG; m++) e[m] = e[m] * y0[m];
+#pragma unroll
+        for (int m = 0; m < QG; m++) y0[m] = fma(e[m], h[m], y0[m]);
+#pragma unroll
+        for (int m = 0; m < QG; m++) acc[m] = fma(wp, y0[m], acc[m]);
+      }
+    }
+  }
+  double total = 0.0;
+#pragma unroll
+  for (int m = 0; m < QG; m++)
+    if (m * G + g < N) total = fma(bwg[m * G + g], acc[m], total);
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  return total * gI[9 * kCH + c1] * gJ[9 * kCH + c2];
+}
+
+// pairs per warp batch of a class of the block-wide lists: larger far rules in lane groups, near pairs in half-warps
+// (near pairs: whole warps while a pass holds only a few of them -- the finish time of the phase matters more than the
+// idle lanes of the short rules)
+__device__ __forceinline__ int batch_pairs(int cls, int near_ppb) { return cls >= 7 ? near_ppb : (cls == 6 ? 4 : 8); }
+__device__ __forceinline__ int near_batch_pairs(const int* cnt);
+// a larger far rule with at least kTabMin pairs in the pass is evaluated from point tables built on demand (whole-warp
+// batches); such pairs come in bulk in the passes between nearby chunks
+constexpr int kTabMin = 64;
+__device__ __forceinline__ bool big_rule_tabled(int cls, const int* cnt) { return cls > kTabClsMax && cls < 7 && cnt[cls] >= kTabMin; }
+__device__ __forceinline__ int list_batch_pairs(int cls, const int* cnt, int near_ppb) {
+  return big_rule_tabled(cls, cnt) ? 32 : batch_pairs(cls, near_ppb);
+}
+__device__ __forceinline__ int near_batch_pairs(const int* cnt) {
+  int n = 0;
+#pragma unroll
+  for (int c = 7; c < NCLS; c++) n += cnt[c];
+  return n < 96 ? 1 : 2;
+}
+
+__device__ __noinline__ double far_group_dispatch(const double* gI, int c1, const double* gJ, int c2, int cls, int lane) {  // @region far_group_dispatch
+  switch (cls) {
+    case 3: return far_group<15, 4>(gI, c1, gJ, c2, 7, lane);
+    case 4: return far_group<16, 4>(gI, c1, gJ, c2, 8, lane);
+    case 5: return far_group<19, 4>(gI, c1, gJ, c2, 9, lane);
+    default: return far_group<25, 8>(gI, c1, gJ, c2, 10, lane);
   }
 }
 
@@ -461,20 +573,17 @@ __device__ __forceinline__ void tab_eval(Smem& S, const ChunkState& I, const Chu
 // append the lanes' pairs of class C (flag `mine`, pair id `e`) to the warp's pending list and evaluate full batches
 template <int C>
 __device__ __forceinline__ void tab_push(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, unsigned short* __restrict__ pend, int& npd,
-                                         bool mine0, bool mine1, unsigned e0, unsigned e1, int lane) {
-  const unsigned lt = (1u << lane) - 1u;
-  const unsigned m0 = __ballot_sync(0xffffffffu, mine0), m1 = __ballot_sync(0xffffffffu, mine1);
-  if ((m0 | m1) == 0u) return;
-  if (mine0) pend[npd + __popc(m0 & lt)] = (unsigned short)e0;
-  npd += __popc(m0);
-  if (mine1) pend[npd + __popc(m1 & lt)] = (unsigned short)e1;
-  npd += __popc(m1);
+                                         bool mine, unsigned e, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, mine);
+  if (m == 0u) return;
+  if (mine) pend[npd + __popc(m & ((1u << lane) - 1u))] = (unsigned short)e;
+  npd += __popc(m);
   __syncwarp();
-  while (npd >= 32) {
+  if (npd >= 32) {
     npd -= 32;
-    const unsigned e = pend[npd + lane];
+    const unsigned eb = pend[npd + lane];
     __syncwarp();  // the slots may be overwritten by the next append
-    if (!(A.debug_skip & 2)) tab_eval<C>(S, I, J, e);
+    if (!(A.debug_skip & 2)) tab_eval<C>(S, I, J, eb);
   }
 }
 
@@ -504,92 +613,85 @@ __device__ __forceinline__ void sweep_rows(Smem& S, const LmatArgs& A, const Chu
   int np0 = 0, np1 = 0, np2 = 0;
 #pragma unroll 1
   for (;;) {
-    int c1 = 0;
-    if (lane == 0) c1 = atomicAdd(&pb.rowhead, 1);
-    c1 = __shfl_sync(0xffffffffu, c1, 0);
+    // unit = half a row: 32 pairs (c1, c2 = lane + 32 h), one per lane (small units keep the warps' finish times close)
+    int u = 0;
+    if (lane == 0) u = atomicAdd(&pb.rowhead, 1);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    const int c1 = u >> 1;
     if (c1 >= ncI) break;
-    float pi_[9];
+    const int c2 = lane + 32 * (u & 1);
+    int cls = -1;
+    unsigned code = 0;
+    if (c2 < ncJ) {
+      bool n1, n2 = false;
+      if (A.self) {
+        n1 = I.x.dmin[c1] <= J.x.dmax[c2];
+        n2 = want2 && !diag && (I.x.dmax[c1] > J.x.dmin[c2]);
+      } else {
+        n1 = true;
+      }
+      if (n1 || n2) {
+        int iq = 4;
+        if (!uniform4) {
+          float pi_[9], pj_[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) pi_[k] = S.vfI[k * CI + c1];
-    const float fli = S.flI[c1];
-    const float4 ci = S.cenI[c1];
-    const int dminI = I.x.dmin[c1], dmaxI = I.x.dmax[c1];
-    int cls[2];
-    unsigned code[2];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int c2 = lane + 32 * h;
-      cls[h] = -1;
-      code[h] = 0;
-      if (c2 < ncJ) {
-        bool n1, n2 = false;
-        if (A.self) {
-          n1 = dminI <= J.x.dmax[c2];
-          n2 = want2 && !diag && (dmaxI > J.x.dmin[c2]);
-        } else {
-          n1 = true;
+          for (int k = 0; k < 9; k++) {
+            pi_[k] = S.vfI[k * CI + c1];
+            pj_[k] = S.vfJ[k * kCH + c2];
+          }
+          iq = -2;
+          if (far_pass) {
+            // order-4 prefilter.  u = unit vector between the centroids, a_k / b_k = projections of the vertices on u,
+            // R = sum of the cells' vertex radii (>= the part of any vertex difference perpendicular to u):
+            //   dl_min >= Lb = min b - max a,   dl_max <= Ub = (max b - min a) + R^2 / (2 Lb)
+            // (the floor sqrt(2 area) <= 1.62 R is below Ub once D > 10 R), so Lb/Ub > 0.9752 > c_thr[0] => iquad = 4.
+            const float4 ci = S.cenI[c1], cj = S.cenJ[c2];
+            float ux = cj.x - ci.x, uy = cj.y - ci.y, uz = cj.z - ci.z;
+            const float D2 = fmaf(uz, uz, fmaf(uy, uy, ux * ux)), rr = ci.w + cj.w + 4.0f * delta;
+            if (D2 > 100.0f * rr * rr) {
+              const float rD = rsqrtf(D2);
+              ux *= rD;
+              uy *= rD;
+              uz *= rD;
+              const float a0 = fmaf(pi_[2], uz, fmaf(pi_[1], uy, pi_[0] * ux)), a1 = fmaf(pi_[5], uz, fmaf(pi_[4], uy, pi_[3] * ux)),
+                          a2 = fmaf(pi_[8], uz, fmaf(pi_[7], uy, pi_[6] * ux));
+              const float b0 = fmaf(pj_[2], uz, fmaf(pj_[1], uy, pj_[0] * ux)), b1 = fmaf(pj_[5], uz, fmaf(pj_[4], uy, pj_[3] * ux)),
+                          b2 = fmaf(pj_[8], uz, fmaf(pj_[7], uy, pj_[6] * ux));
+              const float lb = fminf(b0, fminf(b1, b2)) - fmaxf(a0, fmaxf(a1, a2)) - 8.0f * delta;
+              const float ub = fmaxf(b0, fmaxf(b1, b2)) - fminf(a0, fminf(a1, a2)) + 8.0f * delta;
+              if (lb > 0.9752f * fmaf(0.5f * rr, __fdividef(rr, lb), ub)) iq = 4;
+            }
+          }
+          if (iq < 0) {
+            iq = iquad_screen(pi_, pj_, fmaxf(S.flI[c1], S.flJ[c2]), delta);
+            if (iq < 0) iq = iquad_exact_cells(I.g, c1, J.g, c2);
+          }
         }
-        if (n1 || n2) {
-          int iq = 4;
-          if (!uniform4) {
-            float pj_[9];
-#pragma unroll
-            for (int k = 0; k < 9; k++) pj_[k] = S.vfJ[k * kCH + c2];
-            iq = -2;
-            if (far_pass) {
-              // order-4 prefilter.  u = unit vector between the centroids, a_k / b_k = projections of the vertices on u,
-              // R = sum of the cells' vertex radii (>= the part of any vertex difference perpendicular to u):
-              //   dl_min >= Lb = min b - max a,   dl_max <= Ub = (max b - min a) + R^2 / (2 Lb)
-              // (the floor sqrt(2 area) <= 1.62 R is below Ub once D > 10 R), so Lb/Ub > 0.9752 > c_thr[0] => iquad = 4.
-              const float4 cj = S.cenJ[c2];
-              float ux = cj.x - ci.x, uy = cj.y - ci.y, uz = cj.z - ci.z;
-              const float D2 = fmaf(uz, uz, fmaf(uy, uy, ux * ux)), rr = ci.w + cj.w + 4.0f * delta;
-              if (D2 > 100.0f * rr * rr) {
-                const float rD = rsqrtf(D2);
-                ux *= rD;
-                uy *= rD;
-                uz *= rD;
-                const float a0 = fmaf(pi_[2], uz, fmaf(pi_[1], uy, pi_[0] * ux)), a1 = fmaf(pi_[5], uz, fmaf(pi_[4], uy, pi_[3] * ux)),
-                            a2 = fmaf(pi_[8], uz, fmaf(pi_[7], uy, pi_[6] * ux));
-                const float b0 = fmaf(pj_[2], uz, fmaf(pj_[1], uy, pj_[0] * ux)), b1 = fmaf(pj_[5], uz, fmaf(pj_[4], uy, pj_[3] * ux)),
-                            b2 = fmaf(pj_[8], uz, fmaf(pj_[7], uy, pj_[6] * ux));
-                const float lb = fminf(b0, fminf(b1, b2)) - fmaxf(a0, fmaxf(a1, a2)) - 8.0f * delta;
-                const float ub = fmaxf(b0, fmaxf(b1, b2)) - fminf(a0, fminf(a1, a2)) + 8.0f * delta;
-                if (lb > 0.9752f * fmaf(0.5f * rr, __fdividef(rr, lb), ub)) iq = 4;
-              }
-            }
-            if (iq < 0) {
-              iq = iquad_screen(pi_, pj_, fmaxf(fli, S.flJ[c2]), delta);
-              if (iq < 0) iq = iquad_exact_cells(I.g, c1, J.g, c2);
-            }
-          }
-          const int cl = cls_of(iq);
-          cls[h] = cl;
-          if (cl > kTabClsMax) code[h] = (unsigned)iq | (n1 ? 32u : 0u) | (n2 ? 64u : 0u);
-          if (cl < 7) {  // statistics: far pairs and 1/r evaluations
-            st_far++;
-            st_eval += (unsigned long long)(c_cls_np[cl] * c_cls_np[cl]);
-          }
+        cls = cls_of(iq);
+        if (cls > kTabClsMax) code = (unsigned)iq | (n1 ? 32u : 0u) | (n2 ? 64u : 0u);
+        if (cls < 7) {  // statistics: far pairs and 1/r evaluations
+          st_far++;
+          st_eval += (unsigned long long)(c_cls_np[cls] * c_cls_np[cls]);
         }
       }
-      pb.iqmap[c1 * kCH + c2] = (unsigned char)code[h];
     }
+    pb.iqmap[c1 * kCH + c2] = (unsigned char)code;
     // tabled rules: compact with warp votes, evaluate every full batch
-    const unsigned e0 = (unsigned)(c1 * kCH + lane), e1 = e0 + 32u;
-    tab_push<0>(S, A, I, J, pend0, np0, cls[0] == 0, cls[1] == 0, e0, e1, lane);
-    tab_push<1>(S, A, I, J, pend1, np1, cls[0] == 1, cls[1] == 1, e0, e1, lane);
-    tab_push<2>(S, A, I, J, pend2, np2, cls[0] == 2, cls[1] == 2, e0, e1, lane);
+    const unsigned e = (unsigned)(c1 * kCH + c2);
+    tab_push<0>(S, A, I, J, pend0, np0, cls == 0, e, lane);
+    tab_push<1>(S, A, I, J, pend1, np1, cls == 1, e, lane);
+    tab_push<2>(S, A, I, J, pend2, np2, cls == 2, e, lane);
     // other classes: counts for the block-wide bins
-    const unsigned mo = __ballot_sync(0xffffffffu, (code[0] | code[1]) != 0u);
+    const unsigned mo = __ballot_sync(0xffffffffu, code != 0u);
     if (mo) {
       int mycount = 0;
 #pragma unroll
       for (int c = kTabClsMax + 1; c < NCLS; c++) {
-        const int k = __popc(__ballot_sync(0xffffffffu, cls[0] == c)) + __popc(__ballot_sync(0xffffffffu, cls[1] == c));
+        const int k = __popc(__ballot_sync(0xffffffffu, cls == c));
         if (lane == c) mycount = k;
       }
       if (mycount) atomicAdd(&pb.cnt[lane], mycount);
-      const int nboth = __popc(__ballot_sync(0xffffffffu, (code[0] & 96u) == 96u)) + __popc(__ballot_sync(0xffffffffu, (code[1] & 96u) == 96u));
+      const int nboth = __popc(__ballot_sync(0xffffffffu, (code & 96u) == 96u));
       if (lane == 0 && nboth) atomicAdd(&pb.both_count, nboth);
     }
   }
@@ -655,33 +757,60 @@ __device__ __forceinline__ void bin_others(Smem& S, const ChunkState& I, int tid
     int wbase = 0;
     if (tot) wbase = atomicAdd(&pb.pos[lane], tot);
     int o = 0;
+    const int nppb = near_batch_pairs(pb.cnt);
     for (int c = NCLS - 1; c > lane; c--) {
-      const int n = pb.cnt[c];
-      o += c >= 7 ? ((n + 1) & ~1) : ((n + 31) & ~31);
+      const int n = pb.cnt[c], bp_ = list_batch_pairs(c, pb.cnt, nppb);
+      o += (n + bp_ - 1) / bp_ * bp_;
     }
     start = o + wbase;
     if (warp == 0) {
-      const int n = pb.cnt[lane];
+      const int n = pb.cnt[lane], bp_ = list_batch_pairs(lane, pb.cnt, nppb);
       pb.off[lane] = o;
-      const int padded = lane >= 7 ? ((n + 1) & ~1) : ((n + 31) & ~31);
+      const int padded = (n + bp_ - 1) / bp_ * bp_;
       for (int i = n; i < padded; i++) pb.olist[o + i] = 0xFFFFu;  // padding of the last batch
     }
   }
-  if (warp == NW - 1) {  // queue: classes in descending order (near rules first, largest first)
+  if (warp == NW - 1) {
+    // queue.  Group 0: near classes (largest rules first) and the small bins of the larger far rules (lane groups), then
+    // the first tabled rule; every further tabled rule is a group of its own (a group is one barrier interval: its point
+    // tables occupy the table memory).  Items in descending class order.
+    const int cl = lane < NCLS ? lane : 0;
     const int n = (lane < NCLS && lane > kTabClsMax) ? pb.cnt[lane] : 0;
-    const unsigned m = __ballot_sync(0xffffffffu, n > 0);
-    const int nbat = lane >= 7 ? (n + 1) / 2 : (n + 31) / 32;
-    if (n > 0) {
-      const int q = __popc(m >> (lane + 1));
+    const int nppb = near_batch_pairs(pb.cnt);
+    const bool tabd = n > 0 && big_rule_tabled(cl, pb.cnt);
+    const int bp_ = list_batch_pairs(cl, pb.cnt, nppb);
+    const int nbat = (n + bp_ - 1) / bp_;
+    const unsigned m_c0 = __ballot_sync(0xffffffffu, n > 0 && !tabd), m_tab = __ballot_sync(0xffffffffu, tabd);
+    const int nq0 = __popc(m_c0), ntab = __popc(m_tab);
+    if (n > 0 && !tabd) {
+      const int q = __popc(m_c0 >> (lane + 1));
       pb.qcls[q] = lane;
       pb.qnb[q] = nbat;
     }
-    int tot = n > 0 ? nbat : 0;
+    if (tabd) {
+      const int q = nq0 + __popc(m_tab >> (lane + 1));
+      pb.qcls[q] = lane | 16;  // bit 4: from the tables
+      pb.qnb[q] = nbat;
+    }
+    int nb0 = (n > 0 && !tabd) ? nbat : 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    for (int o = 16; o > 0; o >>= 1) nb0 += __shfl_xor_sync(0xffffffffu, nb0, o);
+    if (tabd) {  // group of this rule: the first tabled rule shares group 0
+      const int k = __popc(m_tab >> (lane + 1));  // index among the tabled rules (descending)
+      const int g = k;                            // group index
+      pb.gq0[g] = k == 0 ? 0 : nq0 + k;
+      pb.gq1[g] = nq0 + k + 1;
+      pb.gnb[g] = nbat + (k == 0 ? nb0 : 0);
+      pb.gcls[g] = lane;
+    }
     if (lane == 0) {
-      pb.nq = __popc(m);
-      pb.qtotal = tot;
+      if (ntab == 0) {
+        pb.gq0[0] = 0;
+        pb.gq1[0] = nq0;
+        pb.gnb[0] = nb0;
+        pb.gcls[0] = -1;
+      }
+      pb.ngrp = ntab > 0 ? ntab : 1;
     }
   }
   unsigned long long used = 0;  // 4 bits per class: pairs of this thread already placed
@@ -702,16 +831,18 @@ __device__ __forceinline__ void bin_others(Smem& S, const ChunkState& I, int tid
 // one batch of the other classes: 32 far pairs of one rule (from the vertices) or 2 near pairs.
 // List entries are (c1<<6 | c2).
 __device__ __forceinline__ void run_batch_c0(const ChunkState& I, const ChunkState& J, const PassBuf& pb, double* __restrict__ T,  // @region run_batch_c0
-                                             int cls, int first, int lane, bool role2_pass, unsigned long long& st_near,
+                                             int cls, int first, int lane, bool role2_pass, int nppb, unsigned long long& st_near,
                                              unsigned long long& st_phi) {
   if (cls < 7) {
-    const unsigned e = pb.olist[first + lane];
-    if (e != 0xFFFFu) {
-      const int c1 = e >> 6, c2 = e & 63;
-      T[c1 * TS + c2] = far_dispatch(I.g, c1, J.g, c2, cls + 4);
-    }
+    const int G = cls == 6 ? 8 : 4;  // lanes per pair
+    const unsigned e = pb.olist[first + lane / G];
+    const bool ok = e != 0xFFFFu;
+    const int c1 = ok ? (int)(e >> 6) : 0, c2 = ok ? (int)(e & 63) : 0;
+    const double v = far_group_dispatch(I.g, c1, J.g, c2, cls, lane);
+    if (ok && (lane & (G - 1)) == 0) T[c1 * TS + c2] = v;
   } else {
-    const int hw = lane >> 4, hl = lane & 15;
+    const int nl = nppb == 1 ? 32 : 16;                 // lanes per pair
+    const int hw = nppb == 1 ? 0 : lane >> 4, hl = lane & (nl - 1);
     const unsigned e = pb.olist[first + hw];
     unsigned m = 0;
     int c1 = 0, c2 = 0, iq = 18;
@@ -725,10 +856,10 @@ __device__ __forceinline__ void run_batch_c0(const ChunkState& I, const ChunkSta
     // first pass: role 1 if needed, else role 2; second pass: role 2 of the pairs that need both
     const bool do1 = !role2_pass && n1, do2 = role2_pass ? (n1 && n2) : (!n1 && n2);
     if (do1 || do2) {  // uniform per half-warp; the shuffles name only this half
-      const unsigned mask = 0xFFFFu << (16 * hw);
+      const unsigned mask = nppb == 1 ? 0xffffffffu : 0xFFFFu << (16 * hw);
       double v;
-      if (do2) v = near_pair(J.g, J.g + 19 * kCH, c2, I.g, c1, iq, hl, 16, mask);
-      else v = near_pair(I.g, I.g + 19 * kCH, c1, J.g, c2, iq, hl, 16, mask);
+      if (do2) v = near_pair(J.g, J.g + 19 * kCH, c2, I.g, c1, iq, hl, nl, mask);
+      else v = near_pair(I.g, I.g + 19 * kCH, c1, J.g, c2, iq, hl, nl, mask);
       if (hl == 0) {
         T[c1 * TS + c2] = v;
         st_near++;
@@ -764,26 +895,35 @@ __device__ __forceinline__ void eval_leftovers(Smem& S, const LmatArgs& A, const
   }
 }
 
-// other classes from the sorted list through the dynamic queue
-__device__ __forceinline__ void eval_others(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int tid,  // @region eval_others
+// other classes from the sorted lists through the dynamic queue, group g
+__device__ __forceinline__ void eval_others(Smem& S, const LmatArgs& A, const ChunkState& I, const ChunkState& J, int tid, int g,  // @region eval_others
                                             unsigned long long& st_near, unsigned long long& st_phi) {
   PassBuf& pb = S.pb;
   const int lane = tid & 31;
-  const int total = pb.qtotal;
+  const int q0 = pb.gq0[g], total = pb.gnb[g];
+  const int nppb = near_batch_pairs(pb.cnt);
   int bnext = 0;
   if (lane == 0) bnext = atomicAdd(&pb.qhead, 1);
   for (;;) {
     const int b = __shfl_sync(0xffffffffu, bnext, 0);
     if (b >= total) break;
     if (lane == 0) bnext = atomicAdd(&pb.qhead, 1);  // the next batch index is fetched while this one is evaluated
-    int k = 0, lb = b;
+    int k = q0, lb = b;
     while (lb >= pb.qnb[k]) {
       lb -= pb.qnb[k];
       k++;
     }
-    const int cls = pb.qcls[k];
+    const int qc = pb.qcls[k], cls = qc & 15;
     if (A.debug_skip && ((cls >= 7) ? (A.debug_skip & 1) : (A.debug_skip & 2))) continue;
-    run_batch_c0(I, J, pb, S.T, cls, pb.off[cls] + lb * (cls >= 7 ? 2 : 32), lane, false, st_near, st_phi);
+    if (qc & 16) {
+      const unsigned e = pb.olist[pb.off[cls] + lb * 32 + lane];
+      if (e != 0xFFFFu) {
+        const int c1 = e >> 6, c2 = e & 63;
+        S.T[c1 * TS + c2] = far_tab_dispatch(S.tabI, S.u.tabJ, c1, c2, cls) * I.g[9 * kCH + c1] * J.g[9 * kCH + c2];
+      }
+    } else {
+      run_batch_c0(I, J, pb, S.T, cls, pb.off[cls] + lb * batch_pairs(cls, nppb), lane, false, nppb, st_near, st_phi);
+    }
   }
 }
 
@@ -792,11 +932,12 @@ __device__ __forceinline__ void eval_role2(Smem& S, const LmatArgs& A, const Chu
                                            unsigned long long& st_near, unsigned long long& st_phi) {
   PassBuf& pb = S.pb;
   const int lane = tid & 31;
+  const int nppb = near_batch_pairs(pb.cnt);
   int nearb = 0, first_cls_off[5], first_cls_nb[5];
 #pragma unroll
   for (int k = 0; k < 5; k++) {
     first_cls_off[k] = pb.off[11 - k];
-    first_cls_nb[k] = (pb.cnt[11 - k] + 1) / 2;
+    first_cls_nb[k] = (pb.cnt[11 - k] + nppb - 1) / nppb;
     nearb += first_cls_nb[k];
   }
   for (;;) {
@@ -810,7 +951,7 @@ __device__ __forceinline__ void eval_role2(Smem& S, const LmatArgs& A, const Chu
       k++;
     }
     if (A.debug_skip & 1) continue;
-    run_batch_c0(I, J, pb, S.T, 11 - k, first_cls_off[k] + lb * 2, lane, true, st_near, st_phi);
+    run_batch_c0(I, J, pb, S.T, 11 - k, first_cls_off[k] + lb * nppb, lane, true, nppb, st_near, st_phi);
   }
 }
 
@@ -1004,6 +1145,7 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {  /
       const double ox = I.cx, oy = I.cy, oz = I.cz;
       // row side of the sweep (first used after the barrier of the first pass)
       prep_chunk(I, S.vfI, S.flI, S.cenI, S.tabI, true, ox, oy, oz, tid);
+      bool tabI_dirty = false;
       for (int cj = cj0; cj < cj1; cj++) {
         const ChunkState& J = S.J[js];
         mbar_wait(&S.J[js].bar, (phJ >> js) & 1u);
@@ -1013,6 +1155,12 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {  /
         const bool lastj = cj + 1 == cj1, lasti = ci + 1 == ci1;
         if (tid == 0 && !(lastj && lasti)) stage_issue(S.J[js ^ 1], 1, A, lastj ? cj0 : cj + 1);
         prep_chunk(J, S.vfJ, S.flJ, S.cenJ, S.u.tabJ, false, ox, oy, oz, tid);
+        if (tabI_dirty) {  // the previous pass used the row tables' memory for a larger rule
+          build_table(S.tabI, CI, I.g, 0, I.ncell, 4, 6, ox, oy, oz, true, tid, NT);
+          build_table(S.tabI + 6 * 2 * CI, CI, I.g, 0, I.ncell, 5, 7, ox, oy, oz, true, tid, NT);
+          build_table(S.tabI + 13 * 2 * CI, CI, I.g, 0, I.ncell, 6, 12, ox, oy, oz, true, tid, NT);
+          tabI_dirty = false;
+        }
         if (tid < NCLS) {
           S.pb.cnt[tid] = 0;
           S.pb.pos[tid] = 0;
@@ -1033,8 +1181,23 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {  /
         if (nother) bin_others(S, I, tid);
         eval_leftovers(S, A, I, J, tid);
         if (nother) {
-          __syncthreads();  // bins and queue of the other classes
-          eval_others(S, A, I, J, tid, st_near, st_phi);
+          __syncthreads();  // bins and queue of the other classes; everybody is done with the tables of the sweep
+          const int ngrp = S.pb.ngrp;
+#pragma unroll 1
+          for (int g = 0; g < ngrp; g++) {
+            const int tc = S.pb.gcls[g];
+            if (g > 0) {
+              __syncthreads();  // previous group done with its tables and the queue head
+              if (tid == 0) S.pb.qhead = 0;
+            }
+            if (tc >= 0) {  // point tables of this rule: row side over the sweep's row tables (rebuilt before the next pass)
+              build_table(S.tabI, CI, I.g, 0, I.ncell, tc + 4, c_cls_np[tc], ox, oy, oz, true, tid, NT);
+              build_table(S.u.tabJ, kCH, J.g, 0, J.ncell, tc + 4, c_cls_np[tc], ox, oy, oz, false, tid, NT);
+              tabI_dirty = true;
+              __syncthreads();
+            }
+            eval_others(S, A, I, J, tid, g, st_near, st_phi);
+          }
         }
         const bool two_pass = S.pb.both_count > 0;
         __syncthreads();  // T complete; the column tables are dead: their memory is the contraction scratch

@@ -14,7 +14,7 @@ namespace tw {
 int visible_devices();
 // records the message returned by thincurr_b200_last_error(); returns 1
 int capi_fail(const std::string& msg);
-std::string ensure_plan(Model& m);
+std::string ensure_plan(Model& m, int nshards = 1);
 std::string ensure_device(Model& m, int device, std::shared_ptr<DeviceState>& out);
 void drop_device_state(Model& m);
 void shard_rows(const Model& m, int nshards, int shard, int& p0, int& p1, std::vector<int>& row_ids, bool sym = false);

@@ -37,19 +37,18 @@ void rcb(std::vector<int>& idx, int lo, int hi, const std::vector<double>& xyz, 
 }
 }  // namespace
 
-std::string build_patches(const Model& m, int P, PatchSet& ps) {
+std::string build_patches(const Model& m, int P, PatchSet& ps, int nshards) {
   const int nv = m.np_active, nh = m.nholes;
   ps = PatchSet();
   ps.ndof = nv + nh;
   if (P <= 0) {
-    // Large patches keep the halo (cells shared by neighbouring patches are evaluated once per patch) small, but
-    // the near-field-heavy diagonal tiles must stay short against a CTA's share of the build and the tile count
-    // must fill 148 SMs many times over: ~300 DOFs per patch (measured on the 20k vessel: 150 -> 186 ms,
-    // 300 -> 169 ms, 600 -> 235 ms), fewer on small meshes (>= ~1500 tiles, >= 32 DOFs).
-    // Larger meshes take larger patches (100k-vertex vessel: 300 -> 2261 ms, 650 -> 2120 ms, 1200 -> 2077 ms) as long as
-    // one device of eight still gets ~2000 tiles: P = nv / (66 sqrt(8)).  The rule depends on the mesh only, so every
-    // shard count works on the same patches and produces the same bits.
-    P = std::min(1200, std::max(300, nv / 187));
+    // Large patches keep the halo (cells shared by neighbouring patches are evaluated once per patch) small, but the tile
+    // count must fill the 148 SMs of every device many times over (>= ~1750 tiles per device of the upper triangle):
+    // P = nv / (59 sqrt(nshards)), between 300 and 1200 DOFs.  Measured with the round-2 kernel on the 100k-vertex vessel,
+    // one device: 526 -> 1732 ms, 800 -> 1659 ms, 1200 -> 1655 ms, 2000 -> 1670 ms; 20k vessel (round 1): 150 -> 186 ms,
+    // 300 -> 169 ms, 600 -> 235 ms.  Small meshes shrink the patches until there are ~1500 tiles (>= 32 DOFs).
+    // Meshes below ~60k vertices get the same patches for every shard count, i.e. the same bits.
+    P = std::min(1200, std::max(300, (int)(nv / (59.0 * std::sqrt((double)std::max(1, nshards))))));
     while (P > 32 && ((long)((nv + P - 1) / P) * ((nv + P - 1) / P)) / 2 < 1500) P = P * 3 / 4;
     P = std::max(P, 32);
   }
@@ -77,8 +76,13 @@ std::string build_patches(const Model& m, int P, PatchSet& ps) {
   ps.npatch = ps.nvert_patch + nh;
   ps.dof_orig.resize(ps.ndof);
   ps.patch_dof_ptr.assign(1, 0);
+  // Internal numbering inside a patch = ascending reference id (rows of a patch leave the device as a few long runs of
+  // consecutive reference rows); the kd order `idx` is kept for the traversal that forms the (compact) chunks.
+  std::vector<int> loc(std::max(nv, 1), 0);  // reference DOF -> internal index
   for (int p = 0; p < ps.nvert_patch; p++) {
     for (int i = cuts[p]; i < cuts[p + 1]; i++) ps.dof_orig[i] = idx[i];
+    std::sort(ps.dof_orig.begin() + cuts[p], ps.dof_orig.begin() + cuts[p + 1]);
+    for (int i = cuts[p]; i < cuts[p + 1]; i++) loc[ps.dof_orig[i]] = i;
     ps.patch_dof_ptr.push_back(cuts[p + 1]);
   }
   for (int h = 0; h < nh; h++) {
@@ -112,14 +116,14 @@ std::string build_patches(const Model& m, int P, PatchSet& ps) {
       incs.push_back({dl, cell_slot[c], code});
     };
     if (p < ps.nvert_patch) {
-      for (int di = d0; di < d1; di++) {
-        int d = ps.dof_orig[di];
+      for (int ti = d0; ti < d1; ti++) {
+        int d = idx[ti];
         for (int kv = kdv[d]; kv < kdv[d + 1]; kv++) {
           int v = ldv[kv];
           for (int j = m.kpc[v]; j < m.kpc[v + 1]; j++) {
             int c = m.lpc[j], k = 0;
             while (k < 3 && m.lc[3 * c + k] != v) k++;
-            add(di - d0, c, k);
+            add(loc[d] - d0, c, k);
           }
         }
       }

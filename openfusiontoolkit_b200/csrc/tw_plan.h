@@ -76,7 +76,7 @@ struct Plan {
 };
 
 // Build the patch decomposition of a model; P = target DOFs per patch (0 = choose automatically)
-std::string build_patches(const Model& m, int P, PatchSet& out);
+std::string build_patches(const Model& m, int P, PatchSet& out, int nshards = 1);
 // Unit normal of a triangle exactly as tw_compute_phipot evaluates it (thin_wall.F90:1942-1943): IEEE operations
 // in the reference's order, no contraction (the device reads these values instead of recomputing them).
 void phipot_normal(const double* P /*[3][3]*/, double* n);

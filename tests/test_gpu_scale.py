@@ -82,17 +82,16 @@ def test_ports_scale_eigenvalues_and_coupling_operators(env):
                        icoils=tw.CoilSets([dict(filaments=[(f['pts'], 1.0, -1.0, -1.0) for f in s]) for s in coils]))
     Mc = np.array(T.compute_Mcoil())
     Mco = O.compute_Mcoil()
-    assert _err(Mc, Mco, np.abs(Mco).max()) < 1e-10
+    # (entries of the coupling operators are sums over the ~6 cells of a vertex that cancel to a dipole moment: like the
+    # reference's regression tests of these operators, parity is judged against the largest entry)
+    relmax = lambda A, B: np.abs(A - B).max() / np.abs(B).max()
+    assert relmax(Mc, Mco) < 1e-12
+    # 64 toroidal flux loops on a ring inside the vessel (the reference's circular_flux_loop shape, 181 points)
     th = np.linspace(0.0, 2.0 * np.pi, 65)[:-1]
-    loops = []
-    for k, t in enumerate(th):
-        c = np.array([1.0 + 0.45 * np.cos(t), 0.0, 0.45 * np.sin(t)])
-        a = np.linspace(0.0, 2.0 * np.pi, 33)
-        pts = c + 0.02 * np.stack([np.cos(a) * np.sin(t), np.sin(a), -np.cos(a) * np.cos(t)], 1)
-        loops.append((pts, 1.0))
+    loops = [(ref_circle(1.0 + 0.3 * np.cos(t), 0.3 * np.sin(t), 181), 1.0) for t in th]
     Ms, Msc, _ = T.compute_Msensor(sensors=loops)
     Mso, Msco = O.compute_Msensor(loops)
-    assert _err(np.array(Ms), Mso, np.abs(Mso).max()) < 1e-10 and _err(np.array(Msc), Msco, np.abs(Msco).max()) < 1e-10
+    assert relmax(np.array(Ms), Mso) < 1e-12 and relmax(np.array(Msc), Msco) < 1e-12
     # L: sampled rows vs the oracle, then the leading L/R eigenvalues: Lanczos on the device vs dense eigh on the host
     T.compute_Lmat()
     L = T.Lmat
