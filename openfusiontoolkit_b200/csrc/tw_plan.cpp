@@ -285,14 +285,52 @@ double mean_cell_size(const PatchSet& ps) {
     }
   return n ? std::sqrt(2.0 * a / n) : 1.0;
 }
+// Relative cost of one cell pair by the distance D of its chunks' centres in mean cell sizes h: the quadrature order falls
+// with D (thin_wall.F90:1055-1059: order >= k while 1 - dl_min/dl_max >= exp(ln(1e-8)/k), and dl_max - dl_min is about one
+// cell size), the cost of a far pair is its n^2 evaluations plus ~25 evaluation-equivalents of classification and
+// contraction, a near pair costs 28..72 analytic potentials of ~50 evaluation-equivalents each.  Normalised to order 4.
+double pair_weight(double D_over_h) {
+  const double x = D_over_h;
+  if (x > 39.8) return 1.0;     // order 4 (6 points)
+  if (x > 21.5) return 1.21;    // 5 (7)
+  if (x > 13.9) return 2.8;     // 6 (12)
+  if (x > 10.0) return 4.1;     // 7 (15)
+  if (x > 7.7) return 4.6;      // 8 (16)
+  if (x > 6.3) return 6.3;      // 9 (19)
+  if (x > 5.3) return 10.7;     // 10 (25)
+  return 42.0;                  // near field
+}
 float tile_cost(const PatchSet& A, const PatchSet& B, const std::vector<Ball>& ba, const std::vector<Ball>& bb, int pa,
                 int pb, double h) {
+  // chunk pair by chunk pair when the patches are close (the mix of orders varies across the tile), one weight otherwise
   double d = 0;
   for (int k = 0; k < 3; k++) d += (ba[pa].c[k] - bb[pb].c[k]) * (ba[pa].c[k] - bb[pb].c[k]);
-  d = std::sqrt(d) - ba[pa].r - bb[pb].r;
-  double pairs = (double)A.patch_ncell[pa] * B.patch_ncell[pb];
-  double w = d < 11.0 * h ? 40.0 : (d < 45.0 * h ? 3.0 : 1.0);  // near field / high-order far field / plain
-  return (float)(pairs * w);
+  d = std::sqrt(d);
+  if (d - ba[pa].r - bb[pb].r > 39.8 * h) return (float)((double)A.patch_ncell[pa] * B.patch_ncell[pb]);
+  double cost = 0.0;
+  for (int ci = A.patch_chunk_ptr[pa]; ci < A.patch_chunk_ptr[pa + 1]; ci++) {
+    const ChunkMeta& I = A.chunks[ci];
+    for (int cj = B.patch_chunk_ptr[pb]; cj < B.patch_chunk_ptr[pb + 1]; cj++) {
+      const ChunkMeta& J = B.chunks[cj];
+      const double dx = I.cx - J.cx, dy = I.cy - J.cy, dz = I.cz - J.cz;
+      cost += (double)I.ncell * J.ncell * pair_weight(std::sqrt(dx * dx + dy * dy + dz * dz) / h);
+    }
+  }
+  return (float)cost;
+}
+// cost estimates of all self tiles of a patch set (symmetric), computed once per plan
+const std::vector<float>& self_costs(const PatchSet& ps) {
+  if (ps.self_cost.size() == (size_t)ps.npatch * ps.npatch) return ps.self_cost;
+  auto balls = patch_balls(ps);
+  const double h = mean_cell_size(ps);
+  ps.self_cost.assign((size_t)ps.npatch * ps.npatch, 0.f);
+  for (int p = 0; p < ps.npatch; p++)
+    for (int q = p; q < ps.npatch; q++) {
+      const float c = tile_cost(ps, ps, balls, balls, p, q, h);
+      ps.self_cost[(size_t)p * ps.npatch + q] = c;
+      ps.self_cost[(size_t)q * ps.npatch + p] = c;
+    }
+  return ps.self_cost;
 }
 }  // namespace
 
@@ -316,12 +354,11 @@ void phipot_normal(const double* P, double* n) {
 void shard_range_sym(const PatchSet& ps, int nshards, int shard, int& p0, int& p1) {
   // work of row patch p in the upper-trapezoid build = cost of its tiles against the patches >= p (the same cost
   // model that orders the tile queue: near-field tiles weigh more)
-  auto balls = patch_balls(ps);
-  const double h = mean_cell_size(ps);
+  const std::vector<float>& cost = self_costs(ps);
   std::vector<double> w(ps.npatch, 0.0);
   double total = 0.0;
   for (int p = 0; p < ps.npatch; p++) {
-    for (int q = p; q < ps.npatch; q++) w[p] += (double)tile_cost(ps, ps, balls, balls, p, q, h) * (q == p ? 0.5 : 1.0);
+    for (int q = p; q < ps.npatch; q++) w[p] += (double)cost[(size_t)p * ps.npatch + q] * (q == p ? 0.5 : 1.0);
     total += w[p];
   }
   auto cut = [&](int s) {
@@ -340,8 +377,7 @@ void shard_range_sym(const PatchSet& ps, int nshards, int shard, int& p0, int& p
 
 void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles, bool upper_only, int skip_lo) {
   tiles.clear();
-  auto balls = patch_balls(ps);
-  double h = mean_cell_size(ps);
+  const std::vector<float>& cost = self_costs(ps);
   std::vector<int> omin(ps.npatch, 0x7fffffff), omax(ps.npatch, -1);
   for (int p = 0; p < ps.npatch; p++)
     for (int i = ps.patch_dof_ptr[p]; i < ps.patch_dof_ptr[p + 1]; i++) {
@@ -370,7 +406,7 @@ void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& til
         else if (owned) t.flags |= 2 | 8;  // both row blocks owned: the transposed entries are filled by the symmetrisation pass
       }
       if (t.pa != t.pb && omax[t.pa] > omin[t.pb]) t.flags |= 4;
-      t.cost = tile_cost(ps, ps, balls, balls, t.pa, t.pb, h) * ((t.flags & 1) ? 0.5f : 1.0f);
+      t.cost = cost[(size_t)t.pa * ps.npatch + t.pb] * ((t.flags & 1) ? 0.5f : 1.0f);
       tiles.push_back(t);
     }
   std::stable_sort(tiles.begin(), tiles.end(), [](const Tile& a, const Tile& b) { return a.cost > b.cost; });

@@ -58,6 +58,7 @@ struct PatchSet {
   std::vector<int> chunk_inc_ptr;    // per chunk: ndof+1 offsets (relative to inc_off), stored at dof_off+chunk
   std::vector<uint16_t> inc;         // cell(6b) | local vertex(2b)<<6 | negative<<8
   std::vector<int> cell_ids;         // [nchunk][kCH] reference cell id (debug / stats)
+  mutable std::vector<float> self_cost;  // [npatch][npatch] cost estimate of the self tiles (filled on first use)
 };
 
 struct Tile {
