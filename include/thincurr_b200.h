@@ -178,13 +178,15 @@ int64_t thincurr_b200_model_bytes(void* tw_ptr);
  * bytes of the model upload and [6] device->host bytes of the rows. */
 int thincurr_b200_Lmat_shard(void* tw_ptr, int nshards, int shard, double* d_out, int64_t ld, void* stream,
                              int64_t* stats);
-/* Symmetric multi-device build.  The row partition equalises the work of the UPPER trapezoid: shard s builds
- * d_out[nrows][ld] for its rows against the DOFs of shards >= s only; the columns of the DOFs of earlier shards are
- * left zero and are the transposes of blocks earlier shards computed (L is symmetric, thin_wall.F90:1146-1151).  The
- * caller completes them with one exchange after the assembly (ThinCurr.exchange_symmetric: NCCL send/recv of the
- * blocks), so no pair integral is evaluated twice across devices.  thincurr_b200_shard_rows_sym: row count and/or
- * reference DOF ids of the rows of a shard (either pointer may be NULL). */
+/* Symmetric multi-device build: every pair integral is evaluated on exactly one device.  The row partition gives every
+ * shard the same work; shard s builds d_out[nrows][ld] for its rows: its diagonal block completely, and of every block it
+ * shares with another shard the tiles (row patch pa, column patch pb) with ((pa + pb) even) == (pa < pb) -- a checkerboard,
+ * half of the block; the other entries are left zero and are the transposes of entries the other shard computed (L is
+ * symmetric, thin_wall.F90:1146-1151).  thincurr_b200_Lmat_exchange (block 3) completes them after the assembly by
+ * reading the peers' rows.  thincurr_b200_shard_rows_sym: row count and/or reference DOF ids of the rows of a shard (either
+ * pointer may be NULL); thincurr_b200_dof_patches: patch index of every vertex / hole DOF (reference id). */
 int thincurr_b200_shard_rows_sym(void* tw_ptr, int nshards, int shard, int* nrows, int* row_ids);
+int thincurr_b200_dof_patches(void* tw_ptr, int nshards, int* patch_of_dof);
 int thincurr_b200_Lmat_shard_sym(void* tw_ptr, int nshards, int shard, double* d_out, int64_t ld, void* stream,
                                  int64_t* stats);
 /* Same from HOST mesh each call (uploads model, builds, copies rows back to h_out[nrows][ld]);
@@ -238,11 +240,12 @@ int thincurr_b200_ipc_open(const unsigned char* handle64, void** d_ptr);
 int thincurr_b200_ipc_close(void* d_ptr);
 int thincurr_b200_enable_peer(int peer_device);
 
-/* Exchange after a symmetric build (thin_wall.F90:1146-1151 across shards): shard `shard` fills the columns of the
- * DOFs of every earlier shard s < shard of its rows d_out[nrows][ld] with the transposes of the blocks those shards
- * computed, READING peer_rows[s] (device pointer to shard s's row block with the same ld: a peer device of this process
- * or a cudaIpc-mapped pointer of another rank) over NVLink.  Asynchronous on `stream`; the caller orders it after the
- * peers' builds (event / stream-ordered collective) and keeps the peers' blocks unchanged until it has run. */
+/* Exchange after a symmetric build (thin_wall.F90:1146-1151 across shards): shard `shard` fills the entries of its rows
+ * d_out[nrows][ld] that the other shards evaluated (see thincurr_b200_Lmat_shard_sym) with their transposes, READING
+ * peer_rows[s] (device pointer to shard s's row block with the same ld: a peer device of this process or a cudaIpc-mapped
+ * pointer of another rank; needed for every s != shard) over NVLink.  Asynchronous on `stream`; the caller orders it after
+ * the peers' builds (event / stream-ordered collective).  Peers may run their own exchange at the same time (the entries
+ * read here are not the ones they write). */
 int thincurr_b200_Lmat_exchange(void* tw_ptr, int nshards, int shard, double* d_out, int64_t ld,
                                 const double* const* peer_rows, void* stream);
 /* "One gather over NVLink when the full matrix is requested on one device": rows of all shards (pointers readable from

@@ -319,12 +319,27 @@ class ThinCurr():
                                    st.ctypes.data_as(c_void_p) if stats else None))
         return st
 
-    def exchange_symmetric(self, out, nshards, shard, group=None, row_ids=None, one_shot=True):
-        '''! Complete the rows built by `compute_Lmat_shard_sym`: L[rows of shard r][DOFs of shard s] for s < r is the
-        transpose of the block shard s computed (thin_wall.F90:1146-1151 mirrors the same way).  `out` is this rank's
-        [nrows, ld] tensor; `row_ids[s]` (optional) the DOF ids of every shard.  `one_shot`: all blocks in a single
-        all-to-all (NCCL on GPUs; staging buffers as large as the exchanged blocks); otherwise nshards-1 rounds of one
-        send/recv per rank with a single block staged at a time.'''
+    def sym_computed_mask(self, nshards, shard, row_ids=None):
+        '''! Boolean mask `[nrows, nelems]` of the entries `compute_Lmat_shard_sym` evaluates in place for `shard`: its
+        diagonal block and, of every block shared with another shard, the checkerboard half that belongs to its rows.'''
+        from .._interface import b200_dof_patches
+        pat = numpy.zeros(self.nelems, dtype=numpy.int32)
+        _check(b200_dof_patches(self.tw_obj, nshards, pat))
+        if row_ids is None:
+            row_ids = [self.shard_rows_sym(nshards, s) for s in range(nshards)]
+        owner = numpy.zeros(self.nelems, dtype=numpy.int32)
+        for s, ids in enumerate(row_ids):
+            owner[ids] = s
+        pa = pat[row_ids[shard]][:, None]
+        pb = pat[None, :]
+        mine = (((pa + pb) & 1) == 0) == (pa < pb)
+        return numpy.where(owner[None, :] == shard, True, mine)
+
+    def exchange_symmetric(self, out, nshards, shard, group=None, row_ids=None):
+        '''! Host-side reference of the exchange after `compute_Lmat_shard_sym` with torch.distributed collectives (any
+        backend; the GPU path is `exchange_symmetric_peer`, inside the library): the entries of `out[nrows, ld]` that
+        another shard evaluated are the transposes of entries of that shard's rows (thin_wall.F90:1146-1151 mirrors the
+        same way).  Every rank sends each peer the block of its rows against the peer's DOFs.'''
         import torch
         import torch.distributed as dist
         if nshards == 1:
@@ -332,38 +347,19 @@ class ThinCurr():
         if row_ids is None:
             row_ids = [self.shard_rows_sym(nshards, s) for s in range(nshards)]
         ids = [torch.as_tensor(numpy.ascontiguousarray(r, dtype=numpy.int64), device=out.device) for r in row_ids]
-        nr = [len(r) for r in row_ids]
-        nmine = nr[shard]
+        nmine = len(row_ids[shard])
         mine = out[:nmine]
-        if one_shot:
-            send_split = [nmine * nr[s] if s > shard else 0 for s in range(nshards)]
-            recv_split = [nr[s] * nmine if s < shard else 0 for s in range(nshards)]
-            later = torch.cat(ids[shard + 1:]) if shard + 1 < nshards else ids[shard][:0]
-            # [DOFs of later shards, my rows]: the receiver's layout (its rows x my rows), one contiguous piece per shard
-            send = mine.index_select(1, later).t().contiguous().view(-1) if sum(send_split) else out.new_empty(0)
-            recv = out.new_empty(sum(recv_split))
-            dist.all_to_all_single(recv, send, recv_split, send_split, group=group)
-            off = 0
-            for s in range(shard):
-                if recv_split[s]:
-                    # sender s packed [my rows, its rows]; L[my rows][its DOFs] = that block as it is
-                    mine.index_copy_(1, ids[s], recv[off:off + recv_split[s]].view(nmine, nr[s]))
-                    off += recv_split[s]
-            return
+        mask = torch.as_tensor(self.sym_computed_mask(nshards, shard, row_ids), device=out.device)
         for d in range(1, nshards):
-            dst, src = shard + d, shard - d
-            ops, recv = [], None
-            if dst < nshards and nmine and nr[dst]:
-                send = mine.index_select(1, ids[dst]).contiguous()   # [my rows, DOFs of the later shard]
-                ops.append(dist.P2POp(dist.isend, send, dst, group=group))
-            if src >= 0 and nmine and nr[src]:
-                recv = torch.empty((nr[src], nmine), dtype=out.dtype, device=out.device)
-                ops.append(dist.P2POp(dist.irecv, recv, src, group=group))
-            if ops:
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-            if recv is not None:
-                mine.index_copy_(1, ids[src], recv.t())
+            dst, src = (shard + d) % nshards, (shard - d) % nshards
+            send = mine.index_select(1, ids[dst]).contiguous()                      # [my rows, DOFs of dst]
+            recv = torch.empty((len(row_ids[src]), nmine), dtype=out.dtype, device=out.device)  # [rows of src, my DOFs]
+            ops = [dist.P2POp(dist.isend, send, dst, group=group), dist.P2POp(dist.irecv, recv, src, group=group)]
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            cur = mine.index_select(1, ids[src])
+            keep = mask.index_select(1, ids[src])
+            mine.index_copy_(1, ids[src], torch.where(keep, cur, recv.t()))
 
     def compute_Lmat_shard_host(self, nshards, shard, out, stats=False):
         '''! End-to-end variant: host mesh -> device build -> host rows (`out` is a numpy array).'''

@@ -84,6 +84,7 @@ b200_shard_rows = ctypes_subroutine(oftpy_lib.thincurr_b200_shard_rows, [c_void_
 b200_Lmat_shard = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard,
     [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p], c_int)
 b200_shard_rows_sym = ctypes_subroutine(oftpy_lib.thincurr_b200_shard_rows_sym, [c_void_p, c_int, c_int, c_int_ptr, c_void_p], c_int)
+b200_dof_patches = ctypes_subroutine(oftpy_lib.thincurr_b200_dof_patches, [c_void_p, c_int, ctypes_numpy_array(int32, 1)], c_int)
 b200_Lmat_shard_sym = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard_sym,
     [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p], c_int)
 b200_Lmat_shard_host = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard_host,

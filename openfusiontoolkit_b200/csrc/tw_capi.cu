@@ -109,6 +109,7 @@ int visible_devices() {
 
 // nshards: how many devices the first build that needs the plan spreads the rows over (sizes the patches so that every
 // device still gets enough tiles); the plan is kept for the lifetime of the model whatever later calls ask for
+static int g_plan_serial = 0;
 std::string ensure_plan(Model& m, int nshards) {
   if (m.plan) return "";
   auto pl = std::make_shared<Plan>();
@@ -116,8 +117,17 @@ std::string ensure_plan(Model& m, int nshards) {
   if (const char* e = std::getenv("THINCURR_B200_PATCH")) P = std::atoi(e);
   std::string err = build_patches(m, P, pl->ps, std::max(1, nshards));
   if (!err.empty()) return err;
+  pl->nshards_hint = std::max(1, nshards);
+  pl->serial = ++g_plan_serial;
   m.plan = pl;
   return "";
+}
+// Plan sized for `nshards` pieces of work even if another one exists (builds whose rows leave the device band by band
+// need many more tiles than a device-resident build); device mirrors follow on their next use.
+std::string replan(Model& m, int nshards) {
+  if (m.plan && m.plan->nshards_hint == std::max(1, nshards)) return "";
+  m.plan.reset();
+  return ensure_plan(m, nshards);
 }
 
 std::string ensure_device(Model& m, int device, std::shared_ptr<DeviceState>& out) {
@@ -125,6 +135,15 @@ std::string ensure_device(Model& m, int device, std::shared_ptr<DeviceState>& ou
   if (!err.empty()) return err;
   for (auto& d : m.dev)
     if (d->device == device) {
+      if (d->plan_serial != m.plan->serial) {  // the model was re-planned: refresh the mirror (on its own device)
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != device) cudaSetDevice(device);
+        err = d->ps.upload_from(m.plan->ps);
+        if (cur != device) cudaSetDevice(cur);
+        if (!err.empty()) return err;
+        d->plan_serial = m.plan->serial;
+      }
       out = d;
       return "";
     }
@@ -133,6 +152,7 @@ std::string ensure_device(Model& m, int device, std::shared_ptr<DeviceState>& ou
   ds->device = device;
   err = ds->ps.upload_from(m.plan->ps);
   if (!err.empty()) return err;
+  ds->plan_serial = m.plan->serial;
   m.dev.push_back(ds);
   out = ds;
   return "";
@@ -157,32 +177,43 @@ void shard_rows(const Model& m, int nshards, int shard, int& p0, int& p1, std::v
     for (int j = 0; j < m.n_vcoils; j++) row_ids.push_back(m.np_active + m.nholes + j);
 }
 
-// Bands of a shard: contiguous patch ranges with (nearly) equal row counts.  A band's rows are complete (all columns of
-// this and later shards) as soon as its own tiles and the transposed copies from the earlier bands are done, so the
-// rows of band k can leave the device while band k+1 is being built.
+// Bands of a shard: contiguous patch ranges.  A band's rows are complete (all columns of this and later shards) as soon
+// as its own tiles and the transposed copies from the earlier bands are done, so the rows of band k can leave the device
+// while band k+1 is being built.  What stays exposed at the end is the copy of the LAST band, so it is made as thin as
+// the tile count allows (a band of w row patches at the bottom of the matrix holds w^2/2 tiles and must still feed every
+// SM: >= ~300 tiles); the patches before it are split into bands of (nearly) equal row counts.
 std::vector<int> band_cuts(const PatchSet& ps, int p0, int p1, int nbands) {
   std::vector<int> cuts{p0};
-  const int i0 = ps.patch_dof_ptr[p0], i1 = ps.patch_dof_ptr[p1];
-  for (int b = 1; b < nbands; b++) {
-    const long long target = i0 + (long long)(i1 - i0) * b / nbands;
-    int p = cuts.back();
-    while (p < p1 && ps.patch_dof_ptr[p] < target) p++;
-    if (p > cuts.back() && p < p1) cuts.push_back(p);
+  nbands = std::max(1, nbands);
+  int plast = p1;  // first patch of the last band
+  if (nbands > 1) {
+    const int w = std::max((int)std::ceil(std::sqrt(2.0 * 300.0)), (p1 - p0) / 16);
+    plast = p1 - w;
+    if (plast <= p0 + 1) plast = p1, nbands = 1;  // too few patches for bands
   }
+  const int i0 = ps.patch_dof_ptr[p0], i1 = ps.patch_dof_ptr[plast];
+  const int nfirst = nbands > 1 ? nbands - 1 : 1;
+  for (int b = 1; b < nfirst; b++) {
+    const long long target = i0 + (long long)(i1 - i0) * b / nfirst;
+    int p = cuts.back();
+    while (p < plast && ps.patch_dof_ptr[p] < target) p++;
+    if (p > cuts.back() && p < plast) cuts.push_back(p);
+  }
+  if (plast < p1 && plast > cuts.back()) cuts.push_back(plast);
   cuts.push_back(p1);
   return cuts;
 }
 
-// Number of bands of a single-device build whose rows go to the host.  The copy of a band overlaps the build of the next
-// ones, so what stays exposed is the copy of the LAST band (1/n of the matrix at the ~55 GB/s of a PCIe 5 x16 link) plus
-// one kernel tail per band (about half a tile: 74 / ntiles of the build).  With c = copy time / build time (0.33 on
-// the 20k-vertex vessel, 0.85 at 100k) the sum c/n + n 74/ntiles is smallest at n = sqrt(c ntiles / 74).
+// Number of bands of a single-device build whose rows go to the host.  Every band costs one kernel tail (about half a tile:
+// 74 / ntiles of the build); the bands before the last one only have to keep the copy engine busy, so a handful is enough
+// (the copy of the whole matrix takes 0.33 of the build on the 20k-vertex vessel, 0.85 at 100k vertices).
 int auto_bands(const PatchSet& ps, int p0, int p1) {
   if (const char* e = std::getenv("THINCURR_B200_BANDS")) return std::max(1, std::atoi(e));
   const double np = p1 - p0;
   const double ntiles = np * (np + 1) / 2;
-  const double c = std::min(1.0, 0.25 + 0.6 * ps.ndof / 1.0e5);
-  return (int)std::max(1.0, std::min(16.0, std::floor(std::sqrt(c * ntiles / 74.0) + 0.5)));
+  // (a band cannot finish before its longest tile -- a near-field-heavy diagonal tile -- so small builds get few bands)
+  if (ntiles < 2400) return 1;
+  return ntiles < 6000 ? 2 : 6;
 }
 
 // Build the self-inductance rows of one shard on the current device into d_out[nrows][ld]
@@ -515,7 +546,8 @@ static std::string lmat_full_host(Model& m, double* dst) {
   DeviceGuard guard;
   std::vector<int> devs_ids = build_devices();
   if (devs_ids.empty()) return "No CUDA device available (the B200 backend has no CPU fallback)";
-  std::string err = ensure_plan(m, (int)devs_ids.size());
+  // one device: the rows leave band by band and every band needs enough tiles for all SMs: patches as for 8 shards
+  std::string err = replan(m, devs_ids.size() == 1 ? 8 : (int)devs_ids.size());
   if (!err.empty()) return err;
   const PatchSet& ps = m.plan->ps;
   int ndev = std::min((int)devs_ids.size(), std::max(1, ps.npatch));
@@ -582,6 +614,7 @@ static std::string lmat_full_host(Model& m, double* dst) {
     if (!err.empty()) break;
     err = D.ds->ps.upload_from(ps);  // the call's inputs: host model -> device, every call
     if (!err.empty()) break;
+    D.ds->plan_serial = m.plan->serial;
     err = scratch_rows(*D.ds, D.rows.size() * N * 8, &D.d);  // row block kept between calls
     if (!err.empty()) break;
     const int nb = ndev == 1 ? auto_bands(ps, p0, p1) : 1;
@@ -606,8 +639,8 @@ static std::string lmat_full_host(Model& m, double* dst) {
       Dev& D = devs[g];
       if (!D.d) continue;
       if (!ck(cudaSetDevice(devs_ids[g]), "cudaSetDevice")) break;
-      for (int s = 0; s < g && sym && err.empty(); s++) {
-        if (!devs[s].d) continue;
+      for (int s = 0; s < ndev && sym && err.empty(); s++) {
+        if (s == g || !devs[s].d) continue;
         cudaError_t pe = cudaDeviceEnablePeerAccess(devs_ids[s], 0);
         if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
           ck(pe, "cudaDeviceEnablePeerAccess");
@@ -615,7 +648,7 @@ static std::string lmat_full_host(Model& m, double* dst) {
         }
         cudaGetLastError();
         if (!ck(cudaStreamWaitEvent(D.s, devs[s].built, 0), "cudaStreamWaitEvent")) break;
-        err = gpu_symmetrize_cross(D.ds->ps, D.i0, D.i1, devs[s].i0, devs[s].i1, D.d, devs[s].d, (long long)N, D.s);
+        err = gpu_symmetrize_cross(D.ds->ps, D.i0, D.i1, devs[s].i0, devs[s].i1, D.d, devs[s].d, (long long)N, D.s, true);
       }
     }
     for (int g = 0; g < ndev && err.empty(); g++) {
@@ -633,7 +666,9 @@ static std::string lmat_full_host(Model& m, double* dst) {
     if (!devs[g].s) continue;
     cudaSetDevice(devs_ids[g]);
     cudaError_t ce = cudaStreamSynchronize(devs[g].s);
+    if (trace) std::fprintf(stderr, "[lmat_full_host] device %d: build stream done at %.1f ms\n", devs_ids[g], since(tr0));
     if (ce == cudaSuccess && devs[g].cs) ce = cudaStreamSynchronize(devs[g].cs);
+    if (trace) std::fprintf(stderr, "[lmat_full_host] device %d: copies done at %.1f ms\n", devs_ids[g], since(tr0));
     if (ce != cudaSuccess && err.empty()) err = std::string("Kernel execution failed: ") + cudaGetErrorString(ce);
     if (copier[g]) {
       std::string ce2 = copier[g]->finish();
@@ -1008,6 +1043,19 @@ int thincurr_b200_plan(void* tw_ptr, int nshards, int shard, int* nrows) {
   std::vector<int> rows;
   shard_rows(m, nshards, shard, p0, p1, rows);
   *nrows = (int)rows.size();
+  return 0;
+}
+
+int thincurr_b200_dof_patches(void* tw_ptr, int nshards, int* patch_of_dof) {
+  // patch index of every vertex / hole DOF (reference id) in the plan made for `nshards` shards: with
+  // thincurr_b200_shard_rows_sym this tells which entries of a symmetric shard were evaluated in place -- tile {pa,pb}
+  // between two shards belongs to the rows of pa iff ((pa + pb) even) == (pa < pb)
+  Model& m = *(Model*)tw_ptr;
+  std::string err = ensure_plan(m, nshards);
+  if (!err.empty()) return fail(err);
+  const PatchSet& ps = m.plan->ps;
+  for (int p = 0; p < ps.npatch; p++)
+    for (int i = ps.patch_dof_ptr[p]; i < ps.patch_dof_ptr[p + 1]; i++) patch_of_dof[ps.dof_orig[i]] = p;
   return 0;
 }
 

@@ -28,6 +28,7 @@ struct DevicePatchSet {
 
 struct DeviceState {
   int device = 0;
+  int plan_serial = -1;  // plan the mirror `ps` was uploaded from
   DevicePatchSet ps;
   double* scratch = nullptr;  // row block of the host-buffer entry points, kept between calls
   size_t scratch_bytes = 0;
@@ -49,10 +50,11 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
                            const std::vector<int>& row_out, bool self, double* d_out, long long ld, cudaStream_t stream,
                            unsigned long long* h_stats, const int* d_col_map = nullptr, bool symmetrize = true);
 
-// dst[i-i0][orig(j)] = src[j-j0][orig(i)] for internal DOFs i in [i0,i1), j in [j0,j1): the transposed block of an earlier
-// shard (src may be peer memory of another device); A = patch set mirror on the device that runs the kernel
+// dst[i-i0][orig(j)] = src[j-j0][orig(i)] for internal DOFs i in [i0,i1), j in [j0,j1): the transposed block of another
+// shard or band (src may be peer memory of another device); A = patch set mirror on the device that runs the kernel.
+// checker: symmetric shards -- only the entries of the tiles the other shard evaluated (sym_tile_is_mine).
 std::string gpu_symmetrize_cross(const DevicePatchSet& A, int i0, int i1, int j0, int j1, double* dst, const double* src, long long ld,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, bool checker = false);
 
 // FP64 DFMA peak microbenchmark (TFLOP/s)
 double gpu_dfma_peak(int device, double* sm_clock_mhz);

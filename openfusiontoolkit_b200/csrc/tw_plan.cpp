@@ -352,13 +352,15 @@ void phipot_normal(const double* P, double* n) {
 }
 
 void shard_range_sym(const PatchSet& ps, int nshards, int shard, int& p0, int& p1) {
-  // work of row patch p in the upper-trapezoid build = cost of its tiles against the patches >= p (the same cost
-  // model that orders the tile queue: near-field tiles weigh more)
+  // Every tile {p,q} between two shards is evaluated by exactly one of them (sym_tile_is_mine: a checkerboard, so each
+  // off-diagonal block is split evenly between its two shards), tiles inside a shard by that shard.  The work attributable
+  // to row patch p is therefore half the cost of its whole row of tiles (same cost model as the tile queue: near-field
+  // tiles weigh more); contiguous patch ranges with equal sums.
   const std::vector<float>& cost = self_costs(ps);
   std::vector<double> w(ps.npatch, 0.0);
   double total = 0.0;
   for (int p = 0; p < ps.npatch; p++) {
-    for (int q = p; q < ps.npatch; q++) w[p] += (double)cost[(size_t)p * ps.npatch + q] * (q == p ? 0.5 : 1.0);
+    for (int q = 0; q < ps.npatch; q++) w[p] += 0.5 * (double)cost[(size_t)p * ps.npatch + q];
     total += w[p];
   }
   auto cut = [&](int s) {
@@ -388,11 +390,16 @@ void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& til
     for (int pb = 0; pb < ps.npatch; pb++) {
       bool owned = pb >= p0 && pb < p1;
       if (owned && pb < pa) continue;  // produced by the mirror write of tile (pb,pa)
-      if (upper_only && !owned && pb < pa) continue;  // transposed block of an earlier shard (exchanged afterwards)
       if (skip_lo >= 0 && pb >= skip_lo && pb < p0) continue;  // rows of an earlier band of the same device (copied afterwards)
       Tile t;
       t.flags = 0;
-      if (!owned && pb < pa) {
+      if (upper_only && !owned) {
+        // symmetric shards: a tile between two shards belongs to one of them and is evaluated with the owner's rows as the
+        // row side (direct, coalesced writes); the other shard copies the transposed block afterwards (exchange)
+        if (!sym_tile_is_mine(pa, pb)) continue;
+        t.pa = pa;
+        t.pb = pb;
+      } else if (!owned && pb < pa) {
         // rows of pa against an unowned lower patch: evaluate the tile in the orientation (pb,pa) the
         // single-device build uses and keep only its mirror writes, so that every shard count
         // produces the same bits (row_out is -1 on the unowned side: no direct write happens)

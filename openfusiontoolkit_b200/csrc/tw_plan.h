@@ -73,6 +73,8 @@ struct Tile {
 
 struct Plan {
   int patch_size = 0;
+  int nshards_hint = 1;  // shard count the patch size was chosen for
+  int serial = 0;        // distinguishes successive plans of a model (device mirrors are re-uploaded when it changes)
   PatchSet ps;
 };
 
@@ -83,12 +85,21 @@ std::string build_patches(const Model& m, int P, PatchSet& out, int nshards = 1)
 void phipot_normal(const double* P /*[3][3]*/, double* n);
 // Contiguous patch range [p0,p1) of shard `shard` out of `nshards`, balanced by pair count
 void shard_range(const PatchSet& ps, int nshards, int shard, int& p0, int& p1);
-// Same for the symmetric (upper-trapezoid) build: shard s computes rows [p0,p1) x columns of patches >= p0 only, so the
-// ranges equalise ncell(p) * (sum_{q>p} ncell(q) + ncell(p)/2); the missing blocks are the transposes of blocks computed
-// by earlier shards (one exchange after the assembly).
+// Same for the symmetric build: every pair integral is evaluated on exactly one shard.  Tiles inside a shard's diagonal
+// block are its own; a tile {pa,pb} between two shards is evaluated by the shard owning `pa` iff sym_tile_is_mine(pa,pb)
+// (a checkerboard over the patch pairs: every off-diagonal block is split evenly between its two shards, so all shards
+// do the same work, hold the same number of rows and exchange the same volume); the other shard copies the transposed
+// block afterwards (one exchange after the assembly).
 void shard_range_sym(const PatchSet& ps, int nshards, int shard, int& p0, int& p1);
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline bool sym_tile_is_mine(int pa /*my row patch*/, int pb /*patch of another shard*/) {
+  const int lo = pa < pb ? pa : pb;
+  return (((pa + pb) & 1) == 0) == (lo == pa);
+}
 // Tiles of a self-inductance build for row patches [p0,p1)
-// upper_only: skip the tiles against earlier (unowned) patches
+// upper_only: symmetric shards -- of the tiles against unowned patches only those sym_tile_is_mine assigns to these rows
 // skip_lo >= 0: also skip the tiles against patches [skip_lo, p0) -- the rows of earlier bands of the same build, whose
 // transposed blocks are copied into place afterwards (banded builds, tw_capi.cu)
 void build_self_tiles(const PatchSet& ps, int p0, int p1, std::vector<Tile>& tiles, bool upper_only = false, int skip_lo = -1);

@@ -1,9 +1,10 @@
 // tw_shard.cu -- multi-device data plane of the sharded dense operators (C ABI, include/thincurr_b200.h block 3).
 //
 // The assembly itself needs no inter-device traffic (tw_lmat.cu).  What follows it does:
-//   * exchange  -- a symmetric shard computed only the upper trapezoid of its row block; the missing blocks
-//                  L[rows r][DOFs of shard s<r] are the transposes of blocks the earlier shards hold
-//                  (thin_wall.F90:1146-1151).  The owner of the rows READS them from its peers' memory over
+//   * exchange  -- a symmetric shard computed its diagonal block and its half of the tiles of every block it shares with
+//                  another shard (a checkerboard over the patch pairs); the missing entries L[rows r][DOFs of shard s]
+//                  are the transposes of entries shard s holds (thin_wall.F90:1146-1151).  The owner of the rows READS
+//                  them from its peers' memory over
 //                  NVLink/NVSwitch (symmetrize_cross_kernel: 32x32 transposing tiles, coalesced on both sides) -- peer
 //                  pointers of the same process, or cudaIpc-mapped pointers of other ranks.
 //   * gather    -- "one gather over NVLink when the full matrix is requested on one device": every shard's rows are
@@ -134,13 +135,14 @@ int thincurr_b200_Lmat_exchange(void* tw_ptr, int nshards, int shard, double* d_
   int p0, p1;
   shard_range_sym(ps, nshards, shard, p0, p1);
   const int i0 = ps.patch_dof_ptr[p0], i1 = ps.patch_dof_ptr[p1];
-  for (int s = 0; s < shard; s++) {
+  for (int s = 0; s < nshards; s++) {
+    if (s == shard) continue;
     int q0, q1;
     shard_range_sym(ps, nshards, s, q0, q1);
     const int j0 = ps.patch_dof_ptr[q0], j1 = ps.patch_dof_ptr[q1];
     if (j1 <= j0 || i1 <= i0) continue;
-    if (!peer_rows || !peer_rows[s]) return sfail("thincurr_b200_Lmat_exchange: missing row block of an earlier shard");
-    err = gpu_symmetrize_cross(ds->ps, i0, i1, j0, j1, d_out, peer_rows[s], ld, stream);
+    if (!peer_rows || !peer_rows[s]) return sfail("thincurr_b200_Lmat_exchange: missing row block of another shard");
+    err = gpu_symmetrize_cross(ds->ps, i0, i1, j0, j1, d_out, peer_rows[s], ld, stream, true);
     if (!err.empty()) return sfail(err);
   }
   return 0;

@@ -51,8 +51,10 @@ def test_sharded_equals_full(env, nshards):
 
 @pytest.mark.parametrize('nshards', [2, 5])
 def test_symmetric_shards_equal_full(env, nshards):
-    """upper-trapezoid shards (thincurr_b200_Lmat_shard_sym): the computed part is bitwise the single-device
-    matrix, the part left to the exchange is zero, the row sets partition the DOFs."""
+    """symmetric shards (thincurr_b200_Lmat_shard_sym): the row sets partition the DOFs; every entry is evaluated on
+    exactly one shard (its diagonal block, and a checkerboard half of every block shared with another shard); what a
+    shard evaluates is the single-device matrix -- bit for bit where the tile keeps the single-device orientation (row
+    patch < column patch), to rounding of the summation order otherwise -- and the rest is left zero for the exchange."""
     import torch
     from openfusiontoolkit_b200.ThinCurr import ThinCurr
     m = load_mesh('ex_torus')
@@ -60,18 +62,32 @@ def test_symmetric_shards_equal_full(env, nshards):
     T.setup_model(r=m['r'], lc=m['lc'], reg=m['reg'], nodesets=m['nodesets'], closures=m['sidesets'][0] if m['sidesets'] else None)
     T.compute_Lmat()
     full = np.array(T.Lmat)
+    scale = np.abs(full).max()
     ids = [T.shard_rows_sym(nshards, s) for s in range(nshards)]
     assert np.array_equal(np.sort(np.concatenate(ids)), np.arange(T.nelems))
+    covered = np.zeros((T.nelems, T.nelems), np.int32)
+    sizes = []
     for s in range(nshards):
         out = torch.empty((len(ids[s]), T.nelems), dtype=torch.float64, device='cuda')
         T.compute_Lmat_shard_sym(nshards, s, out)
         torch.cuda.synchronize()
         got = out.cpu().numpy()
-        later = np.concatenate(ids[s:])
-        assert np.array_equal(got[:, later], full[np.ix_(ids[s], later)]), 'shard %d' % s
-        if s:
-            earlier = np.concatenate(ids[:s])
-            assert not got[:, earlier].any()
+        mask = T.sym_computed_mask(nshards, s, ids)
+        ref = full[ids[s]]
+        assert not got[~mask].any(), 'shard %d wrote entries that belong to another shard' % s
+        assert np.abs(got[mask] - ref[mask]).max() <= 1e-13 * scale, 'shard %d' % s
+        own = np.isin(np.arange(T.nelems), ids[s])
+        assert np.array_equal(got[:, own], ref[:, own]), 'diagonal block of shard %d must be the single-device bits' % s
+        covered[ids[s]] += mask
+        sizes.append(mask.sum())
+    # every entry evaluated exactly once: an entry and its transpose never both on different shards
+    owner = np.zeros(T.nelems, np.int32)
+    for s, i in enumerate(ids):
+        owner[i] = s
+    off = owner[:, None] != owner[None, :]
+    assert np.array_equal((covered + covered.T)[off], np.ones(off.sum(), np.int32)), 'off-diagonal-block entries: exactly one of (a,b), (b,a)'
+    assert covered[~off].all()
+    assert max(sizes) / (sum(sizes) / nshards) < 1.25, 'shards evaluate similar numbers of entries'
 
 
 def test_ports_mesh_rows(env):

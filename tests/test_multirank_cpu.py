@@ -50,8 +50,9 @@ def test_two_rank_row_partition():
 
 
 def _worker_sym(rank, world, port, q):
-    """symmetric partition + exchange on CPU tensors (gloo): every rank holds the upper trapezoid of a known
-    symmetric matrix and must end up with its complete rows."""
+    """symmetric partition + exchange on CPU tensors (gloo): every rank holds the entries of a known symmetric matrix
+    that the symmetric build evaluates on it (diagonal block + its checkerboard half of the shared blocks) and must end
+    up with its complete rows."""
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -69,13 +70,10 @@ def _worker_sym(rank, world, port, q):
     A = rng.standard_normal((N, N))
     A = A + A.T
     mine = ids[rank]
-    out = torch.from_numpy(A[mine].copy())
-    for s in range(rank):                      # what the upper-trapezoid build leaves empty
-        out[:, torch.as_tensor(ids[s].astype(np.int64))] = 0.0
-    out2 = out.clone()
-    T.exchange_symmetric(out, world, rank, row_ids=ids)                    # one all-to-all
-    T.exchange_symmetric(out2, world, rank, row_ids=ids, one_shot=False)   # rounds of send/recv
-    ok = bool(np.array_equal(out.numpy(), A[mine])) and bool(np.array_equal(out2.numpy(), A[mine]))
+    mask = T.sym_computed_mask(world, rank, ids)
+    out = torch.from_numpy(np.where(mask, A[mine], 0.0))   # what the symmetric build leaves for the exchange is zero
+    T.exchange_symmetric(out, world, rank, row_ids=ids)
+    ok = bool(np.array_equal(out.numpy(), A[mine])) and 0.3 < mask.mean() < 0.8
     res = [None] * world
     dist.all_gather_object(res, (ok, [len(i) for i in ids], int(sum(len(i) for i in ids)), N))
     if rank == 0:
@@ -100,7 +98,7 @@ def test_symmetric_exchange(world):
     for ok, sizes, total, N in res:
         assert ok, 'rows incomplete after the exchange'
         assert total == N
-        assert sizes[0] < sizes[-1], 'earlier shards own fewer rows (their rows are longer in the upper trapezoid)'
+        assert max(sizes) < 1.6 * min(sizes), 'shards own similar numbers of rows'
 
 
 def test_bench_workloads_are_the_baseline_configs():

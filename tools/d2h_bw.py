@@ -1,16 +1,21 @@
-"""Pinned device->host bandwidth of the box (what bounds the e2e leg): one 2 GiB cudaMemcpyAsync, and 1024 x 2 MiB."""
+"""Pinned device->host bandwidth of the box (what bounds the e2e leg): small and large pinned destinations."""
+import sys
 import time
 import torch
-n = 1 << 28
-d = torch.empty(n, dtype=torch.float64, device='cuda')
-h = torch.empty(n, dtype=torch.float64, pin_memory=True)
-for tag, chunks in (('1 x 2 GiB', 1), ('1024 x 2 MiB', 1024)):
+for gib in (2, 16, 64):
+    n = gib << 27
+    try:
+        h = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    except Exception as e:
+        print('pin %d GiB failed: %s' % (gib, e))
+        break
+    d = torch.empty(min(n, 1 << 30), dtype=torch.float64, device='cuda')
     for rep in range(2):
         torch.cuda.synchronize()
         t = time.perf_counter()
-        step = n // chunks
-        for c in range(chunks):
-            h[c * step:(c + 1) * step].copy_(d[c * step:(c + 1) * step], non_blocking=True)
+        for off in range(0, n, d.numel()):
+            h[off:off + d.numel()].copy_(d[:min(d.numel(), n - off)], non_blocking=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t
-    print('D2H %s: %.1f GB/s' % (tag, n * 8 / dt / 1e9))
+    print('D2H into a %d GiB pinned buffer (8 GiB pieces): %.1f GB/s' % (gib, n * 8 / dt / 1e9), flush=True)
+    del h
