@@ -69,9 +69,14 @@ def main():
         os.environ['THINCURR_B200_NDEV'] = '1'
         T.compute_Lmat()
         ref = np.array(T.Lmat)
-        if not np.array_equal(full, ref):
+        # a tile evaluated with the larger patch index as row side sums in another order than the single-device build:
+        # equal to rounding, and exactly symmetric (every entry is evaluated once and mirrored)
+        if not (np.abs(full - ref).max() <= 1e-13 * np.abs(ref).max()):
             ok = False
             msgs.append('gathered matrix differs from the single-device build: max abs %.3e' % np.abs(full - ref).max())
+        if not np.array_equal(full, full.T):
+            ok = False
+            msgs.append('gathered matrix is not exactly symmetric')
         if N <= 4000:   # dense generalised eigen solve on the host (torchrun pins OMP_NUM_THREADS=1: small meshes only)
             import scipy.linalg as sl
             w = np.sort(sl.eigh(ref, T.Rmat.toarray(), eigvals_only=True))[::-1][:4]

@@ -2,8 +2,9 @@
  * one process per GPU over NCCL: symmetric shards + the library's peer-memory exchange + gather == the single-device
    matrix bit for bit; sharded mat-vec + Lanczos eigenvalues == dense eigen solve to 1e-8;
  * one process driving several devices: the reference-facing thincurr_Lmat with NDEV = 1, NDEV = n (symmetric shards,
-   transposed blocks fetched from peer memory) and NDEV = n with full-row shards gives identical bits, for pinned
-   (library-owned) and pageable (Fortran-host) destinations."""
+   transposed entries fetched from peer memory) and NDEV = n with full-row shards: full-row shards give the bits of the
+   single-device build, symmetric shards the same values to rounding (tiles are evaluated with the owner's rows as row
+   side) and an exactly symmetric matrix; pinned (library-owned) and pageable (Fortran-host) destinations agree bit for bit."""
 import os
 import subprocess
 import sys
@@ -58,7 +59,12 @@ for tag, env in (('one', {'THINCURR_B200_NDEV': '1'}), ('sym', {'THINCURR_B200_N
 ref = res['one']
 assert np.array_equal(ref, ref.T)
 for k, v in res.items():
-    assert np.array_equal(v, ref), k
+    assert np.array_equal(v, v.T), k
+    if k.startswith('full') or k.startswith('one'):
+        assert np.array_equal(v, ref), k          # full-row shards keep the single-device orientation of every tile
+    else:
+        assert np.abs(v - ref).max() <= 1e-13 * np.abs(ref).max(), k   # symmetric shards: to rounding (summation order)
+assert np.array_equal(res['sym'], res['sym_pageable'])
 print('INPROC_OK')
 """
 
