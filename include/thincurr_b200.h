@@ -254,7 +254,8 @@ int thincurr_b200_Lmat_exchange(void* tw_ptr, int nshards, int shard, double* d_
 int thincurr_b200_Lmat_gather(void* tw_ptr, int nshards, int sym, const double* const* shard_rows, int64_t ld_src,
                               double* d_full, int64_t ld_full, void* stream);
 /* Export of a shard's rows (device) into a host matrix h_full[nelems][ld_full] in the reference layout, streamed
- * through pinned buffers (matrices that fit no single device: 150k-vertex vessel, 180 GB). */
+ * through pinned buffers (matrices that fit no single device: 150k-vertex vessel, 180 GB).  h_full == NULL: stream only
+ * (the rows pass through the pinned staging buffers and are dropped; measures what an export sees). */
 int thincurr_b200_rows_to_host(void* tw_ptr, int nshards, int shard, int sym, const double* d_rows, int64_t ld,
                                double* h_full, int64_t ld_full);
 /* Export into the reference's `Lmat.save` cache (thin_wall.F90:1161-1171): _begin writes the header record and sizes the

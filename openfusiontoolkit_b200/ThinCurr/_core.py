@@ -513,6 +513,9 @@ class ThinCurr():
 
     def rows_to_host(self, nshards, shard, sym, rows_ptr, ld, full_host):
         '''! (extension) Stream this shard's rows (device) into the host matrix `full_host[nelems, ld_full]` (numpy).'''
+        if full_host is None:   # stream only (rows pass through the pinned staging buffers and are dropped)
+            _check(b200_rows_to_host(self.tw_obj, nshards, shard, 1 if sym else 0, c_void_p(rows_ptr), ld, c_void_p(), ld))
+            return
         _check(b200_rows_to_host(self.tw_obj, nshards, shard, 1 if sym else 0, c_void_p(rows_ptr), ld,
                                  full_host.ctypes.data_as(c_void_p), full_host.shape[1]))
 

@@ -195,8 +195,10 @@ int thincurr_b200_rows_to_host(void* tw_ptr, int nshards, int shard, int sym, co
   auto flush = [&](int k) {
     if (!pend_n[k]) return;
     cudaEventSynchronize(ev[k]);
-    for (size_t r = 0; r < pend_n[k]; r++)
-      std::memcpy(h_full + (size_t)rows[pend_r0[k] + r] * ld_full, stage[k] + r * N, N * 8);
+    if (h_full)  // (h_full == NULL: the rows are only streamed through the pinned buffers -- throughput of an export whose
+                 // consumer is not host memory, e.g. a file writer that takes the staging buffers)
+      for (size_t r = 0; r < pend_n[k]; r++)
+        std::memcpy(h_full + (size_t)rows[pend_r0[k] + r] * ld_full, stage[k] + r * N, N * 8);
     pend_n[k] = 0;
   };
   int k = 0;
