@@ -352,6 +352,7 @@ void thincurr_setup(const char* mesh_file, int np, const double* r_loc, int nc, 
         if (std::abs(jumper_start) > nsets) err = "\"jumper_start\" exceeds number of nodesets in file";
         int js = jumper_start < 0 ? nsets + 1 + jumper_start : jumper_start;
         nholes = js - 1;
+        m->n_jumper_sets = nsets - nholes;
       }
       for (int h = 0; h < nholes && err.empty(); h++) {
         holes.emplace_back();
@@ -639,8 +640,9 @@ static std::string lmat_full_host(Model& m, double* dst) {
       Dev& D = devs[g];
       if (!D.d) continue;
       if (!ck(cudaSetDevice(devs_ids[g]), "cudaSetDevice")) break;
-      for (int s = 0; s < ndev && sym && err.empty(); s++) {
-        if (s == g || !devs[s].d) continue;
+      for (int k = 1; k < ndev && sym && err.empty(); k++) {  // rotated order: every device reads from a different peer
+        const int s = (g + k) % ndev;
+        if (!devs[s].d) continue;
         cudaError_t pe = cudaDeviceEnablePeerAccess(devs_ids[s], 0);
         if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
           ck(pe, "cudaDeviceEnablePeerAccess");

@@ -95,6 +95,7 @@ struct Model {
   std::vector<int> lfh;        // [nfh][2] (signed 1-based hole id, 0-based local vertex)
   std::vector<std::vector<int>> hole_chain;
   std::vector<int> closures;   // closure vertices (0-based)
+  int n_jumper_sets = 0;       // nodesets from `jumper_start` on (thincurr_f.F90:172-190): kept as a count only
   // ---- physics inputs ----
   std::vector<double> eta_surf, eta_vol, thickness;  // eta stored as eta/mu0 (thin_wall.F90:2864)
   std::vector<int> sens_mask;                         // [nreg]

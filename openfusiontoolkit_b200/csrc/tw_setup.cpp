@@ -488,7 +488,15 @@ std::string Model::setup_from_arrays(int np_, const double* r_, int nc_, const i
   nc = nc_;
   r.assign(r_, r_ + 3 * (size_t)np);
   lc.resize(3 * (size_t)nc);
-  for (size_t i = 0; i < lc.size(); i++) lc[i] = lc1[i] - 1;
+  for (size_t i = 0; i < lc.size(); i++) {
+    if (lc1[i] < 1 || lc1[i] > np) return "Cell list refers to a vertex outside [1, np] (lc is 1-based on this interface)";
+    lc[i] = lc1[i] - 1;
+  }
+  for (auto& ns : nodesets0)
+    for (int v : ns)
+      if (v < 0 || v >= np) return "Nodeset refers to a vertex outside the mesh";
+  for (int c : closure_cells0)
+    if (c < 0 || c >= nc) return "Closure (sideset 1) refers to a cell outside the mesh";
   reg.assign(nc, 1);
   if (reg_) reg.assign(reg_, reg_ + nc);
   nreg = 1;
@@ -546,7 +554,10 @@ std::string Model::setup_from_tw(int np_, const double* r_, int nc_, const int* 
   nc = nc_;
   r.assign(r_, r_ + 3 * (size_t)np);
   lc.resize(3 * (size_t)nc);
-  for (size_t i = 0; i < lc.size(); i++) lc[i] = lc1[i] - 1;
+  for (size_t i = 0; i < lc.size(); i++) {
+    if (lc1[i] < 1 || lc1[i] > np) return "Cell list refers to a vertex outside [1, np] (lc is 1-based on this interface)";
+    lc[i] = lc1[i] - 1;
+  }
   reg.assign(nc, 1);
   if (reg_) reg.assign(reg_, reg_ + nc);
   nreg = 1;

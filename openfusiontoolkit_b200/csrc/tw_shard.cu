@@ -135,8 +135,10 @@ int thincurr_b200_Lmat_exchange(void* tw_ptr, int nshards, int shard, double* d_
   int p0, p1;
   shard_range_sym(ps, nshards, shard, p0, p1);
   const int i0 = ps.patch_dof_ptr[p0], i1 = ps.patch_dof_ptr[p1];
-  for (int s = 0; s < nshards; s++) {
-    if (s == shard) continue;
+  // peers in rotated order (shard+1, shard+2, ...): at any moment every rank reads from a different source, so no
+  // device's memory and NVLink egress serves all readers at once
+  for (int k = 1; k < nshards; k++) {
+    const int s = (shard + k) % nshards;
     int q0, q1;
     shard_range_sym(ps, nshards, s, q0, q1);
     const int j0 = ps.patch_dof_ptr[q0], j1 = ps.patch_dof_ptr[q1];

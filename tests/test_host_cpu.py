@@ -93,6 +93,12 @@ def test_error_conventions(env):
         T.set_eta_values(eta_surf=-np.ones(1))
     with pytest.raises(Exception, match='HODLR'):
         T.compute_Lmat(use_hodlr=True)
+    bad = m['lc'].copy()
+    bad[3, 1] = m['r'].shape[0] + 5      # malformed connectivity is refused, not read out of bounds
+    with pytest.raises(Exception, match='outside'):
+        ThinCurr(env).setup_model(r=m['r'], lc=bad, reg=m['reg'])
+    with pytest.raises(Exception, match='outside'):
+        ThinCurr(env).setup_model(r=m['r'], lc=m['lc'], reg=m['reg'], nodesets=[np.array([0, 1, 10 ** 6])])
 
 
 def test_no_cpu_fallback(env):
