@@ -77,7 +77,8 @@ void thincurr_set_eta(void* tw_ptr, const double* eta_surf, const double* eta_vo
  * OpenFUSIONToolkit.ThinCurr package loads against this library.  Answered natively: thincurr_scale_va (F:453-466),
  * thincurr_get_eta_vol (F:721-731), thincurr_get_thickness (F:887-902), thincurr_apply_Lmat (F:470-497: dense mat-vec on
  * the device, vals overwritten), thincurr_eigenvalues (F:975-1013: iterative path = Lanczos on the device-resident L,
- * direct=true is refused).  The others belong to the reference's downstream solvers / plotting and report
+ * direct=true is refused), thincurr_cross_eval (F:525-541: matrix-free mutual apply, tw_compute_Lmat_MF on the device),
+ * thincurr_reduce_model (F:1208-1247: projections on the device, root-level datasets of the reduced-model file).  The others belong to the reference's downstream solvers / plotting and report
  * "not provided" through error_str (those without an error_str print the message and call the abort callback that
  * oftpy_init received, the reference's oft_abort convention). */
 void thincurr_setup_io(void* tw_ptr, const char* basepath, bool save_debug, bool legacy_hdf5, char* error_str);
@@ -201,8 +202,29 @@ int thincurr_b200_Lmat_shard_host(void* tw_ptr, int nshards, int shard, double* 
  * tile, so thin strips cost as much as the patches they touch. */
 int thincurr_b200_Lmat_block(void* tw_ptr, int nrows, const int* row_ids, int ncols, const int* col_ids, double* d_out,
                              int64_t ld, void* stream);
+/* HODLR dense-block builders with the reference's own semantics.  Blocks are VERTEX subsets (0-based mesh
+ * vertex ids, no duplicates: oft_tw_block%ipts); the cells touching them (icell) and the inverse map are derived here.
+ * `out` may be HOST or DEVICE memory (detected); host output makes the call synchronous.  The device-side cell arrays of
+ * a model are uploaded on the first call and kept (ACA+ asks for thousands of one-row strips, thin_wall_hodlr.F90:1224-1428).
+ *  - Lmatblock = tw_compute_Lmatblock (thin_wall_hodlr.F90:289-404): out[a][b] = Lmat(col_pts[b], row_pts[a]); the ROW
+ *    block's cell is the analytic side of every near pair, no pair is skipped, vertex DOFs only.  tw_col NULL = tw_row.
+ *  - LmatHole = tw_compute_LmatHole(self,self,...) (:136-285): out[h][:] = Lmat(:, h), h over the nholes + n_vcoils
+ *    hole / V-coil columns of hole_Vcoil_mat, ld >= nelems.
+ *  - Bops_block = tw_compute_Bops_block (:580-691): out[a][b] = Bop(col_pts[b], row_pts[a]) for component dir = 0,1,2;
+ *    dir < 0: all three in one sweep, out[3][nrp][ld].
+ * Work per call: (cells of the row block) x (cells or vertices of the column block) pair integrals, nothing else. */
+int thincurr_b200_Lmatblock(void* tw_row, void* tw_col, int nrp, const int* row_pts, int ncp, const int* col_pts, double* out,
+                            int64_t ld, void* stream);
+int thincurr_b200_LmatHole(void* tw_ptr, double* out, int64_t ld, void* stream);
+int thincurr_b200_Bops_block(void* tw_ptr, int nrp, const int* row_pts, int ncp, const int* col_pts, int dir, double* out,
+                             int64_t ld, void* stream);
+/* Matrix-free apply between two models = tw_compute_Lmat_MF (thin_wall.F90:1190-1414; what thincurr_cross_eval calls):
+ * vec2[q][:] = M vec1[q][:] for host arrays vec1[nrhs][nelems1], vec2[nrhs][nelems2]; counts[3] (optional) returns the
+ * number of cell pairs per class of its quadrature heuristic (far / close / very close). */
+int thincurr_b200_cross_eval(void* tw_ptr1, void* tw_ptr2, int nrhs, const double* vec1, double* vec2, int64_t* counts);
 /* Minimal HDF5 writer (no libhdf5 needed): root-level contiguous little-endian datasets, float64 (is_f64[i] != 0) or
- * int32, dims[] = the dimensions of all items concatenated in C order (slowest first); at most 8 items.  This is the
+ * int32, dims[] = the dimensions of all items concatenated in C order (slowest first); at most 32 items (one symbol-table
+ * node: group leaf K = 4 up to 8 items, the libhdf5 default, 16 above).  This is the
  * container of the reference's Bmat cache (thin_wall.F90:2208-2225: MODEL_hash, Bel_X|Y|Z, Bdr_X|Y|Z), which
  * thincurr_Bmat writes and reads through it. */
 int thincurr_b200_h5_write(const char* path, int nitems, const char* const* names, const int* is_f64, const int* ranks,

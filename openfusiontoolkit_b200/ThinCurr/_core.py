@@ -4,8 +4,9 @@ build path (setup_model :99-166, compute_Lmat :269-288, compute_Bmat :307-331, c
 :333-348, compute_Msensor :350-387, compute_Rmat :491-513, cross_coupling :515-531).  All
 matrices are zero-copy numpy views of library-owned buffers in the reference's layouts.
 `get_eigs` (iterative path, _core.py:563-580) and `apply_Lmat` (:472-489 region) run on the device-resident matrix.
-Methods of the reference that belong to the remaining downstream solvers (time stepping, frequency response, plotting,
-reduced models) are out of scope and raise NotImplementedError.
+`cross_eval` (:533-549, matrix-free mutual apply) and `build_reduced_model` (:717-739) run on the device as well.
+Methods of the reference that belong to the remaining downstream solvers (time stepping, frequency response, plotting)
+are out of scope and raise NotImplementedError.
 """
 import ctypes
 from ctypes import c_bool, c_double, c_int, c_void_p
@@ -21,7 +22,7 @@ from .._interface import (B200_APPLY_FN, b200_device_alloc, b200_device_free, b2
                           b200_set_sensors, b200_setup, b200_shard_rows, c_double_ptr, c_int_ptr, mu0, oftpy_load_xml,
                           thincurr_Bmat, thincurr_cross_coupling, thincurr_get_eta, thincurr_get_sensor_name,
                           thincurr_Lmat, thincurr_Mcoil, thincurr_Msensor, thincurr_Rmat, thincurr_set_eta,
-                          thincurr_setup)
+                          thincurr_setup, thincurr_cross_eval, thincurr_reduce_model)
 
 
 def _check(rc):
@@ -376,6 +377,83 @@ class ThinCurr():
         sptr = c_void_p(stream) if stream else c_void_p()
         _check(b200_Lmat_block(self.tw_obj, len(rows), rows, len(cols), cols, c_void_p(out.data_ptr()), out.stride(0), sptr))
 
+    # ---- HODLR dense-block builders, matrix-free apply, reduced model ---------------------------------
+    @staticmethod
+    def _out_ptr(out):
+        """host numpy array or CUDA tensor -> (pointer, leading dimension)"""
+        if isinstance(out, numpy.ndarray):
+            return out.ctypes.data_as(c_void_p), out.strides[-2] // 8
+        return c_void_p(out.data_ptr()), out.stride(-2)
+
+    def compute_Lmatblock(self, row_pts, col_pts, out=None, col_model=None, stream=None):
+        '''! (extension) `tw_compute_Lmatblock` (thin_wall_hodlr.F90:289-404): dense block between two VERTEX blocks
+        (0-based mesh vertex ids), `out[a, b] = Lmat(col_pts[b], row_pts[a])`, row block's cells analytic for near pairs.
+        `out`: numpy array or CUDA tensor `[len(row_pts), ld >= len(col_pts)]` (allocated on the host when None).'''
+        from .._interface import b200_Lmatblock
+        rows = numpy.ascontiguousarray(row_pts, dtype=numpy.int32)
+        cols = numpy.ascontiguousarray(col_pts, dtype=numpy.int32)
+        if out is None:
+            out = numpy.zeros((len(rows), len(cols)))
+        ptr, ld = self._out_ptr(out)
+        _check(b200_Lmatblock(self.tw_obj, col_model.tw_obj if col_model is not None else c_void_p(), len(rows), rows, len(cols), cols,
+                              ptr, ld, c_void_p(stream) if stream else c_void_p()))
+        return out
+
+    def compute_LmatHole(self, out=None, stream=None):
+        '''! (extension) `tw_compute_LmatHole(self, self)` (thin_wall_hodlr.F90:136-285): `out[h, :] = Lmat(:, h)` for the
+        hole and V-coil columns, `[nholes + n_vcoils, nelems]`.'''
+        from .._interface import b200_LmatHole
+        if out is None:
+            out = numpy.zeros((self.nholes + self.n_vcoils, self.nelems))
+        ptr, ld = self._out_ptr(out)
+        _check(b200_LmatHole(self.tw_obj, ptr, ld, c_void_p(stream) if stream else c_void_p()))
+        return out
+
+    def compute_Bops_block(self, row_pts, col_pts, direction=-1, out=None, stream=None):
+        '''! (extension) `tw_compute_Bops_block` (thin_wall_hodlr.F90:580-691): `out[a, b] = Bop(col_pts[b], row_pts[a])`
+        for Cartesian component `direction` (0, 1, 2), or all three (`direction < 0`, `out[3, nrows, ncols]`).'''
+        from .._interface import b200_Bops_block
+        rows = numpy.ascontiguousarray(row_pts, dtype=numpy.int32)
+        cols = numpy.ascontiguousarray(col_pts, dtype=numpy.int32)
+        if out is None:
+            out = numpy.zeros((3, len(rows), len(cols)) if direction < 0 else (len(rows), len(cols)))
+        ptr, ld = self._out_ptr(out)
+        _check(b200_Bops_block(self.tw_obj, len(rows), rows, len(cols), cols, int(direction), ptr, ld,
+                               c_void_p(stream) if stream else c_void_p()))
+        return out
+
+    def cross_eval(self, model2, field, counts=None):
+        '''! Flux induced on `model2` by current fields on this model (`tw_compute_Lmat_MF`, thin_wall.F90:1190-1414;
+        reference `_core.py:533-549`): `field [nrhs, nelems]` -> `[nrhs, model2.nelems]`.'''
+        field = numpy.atleast_2d(field)
+        nrhs = field.shape[0]
+        if field.shape[1] != self.nelems:
+            raise IndexError('Incorrect shape of "field", should be [:,nelems]')
+        vec_out = numpy.zeros((nrhs, model2.nelems), dtype=numpy.float64)
+        vec_in = numpy.ascontiguousarray(field.copy(), dtype=numpy.float64)
+        if counts is not None:
+            from .._interface import b200_cross_eval
+            _check(b200_cross_eval(self.tw_obj, model2.tw_obj, c_int(nrhs), vec_in, vec_out, counts.ctypes.data_as(c_void_p)))
+            return vec_out
+        error_string = self._oft_env.get_c_errorbuff()
+        thincurr_cross_eval(self.tw_obj, model2.tw_obj, c_int(nrhs), vec_in, vec_out, error_string)
+        if error_string.value != b'':
+            raise Exception(error_string.value.decode())
+        return vec_out
+
+    def build_reduced_model(self, basis_set, filename='tCurr_reduced.h5', compute_B=False, sensor_obj=None):
+        '''! Project the model onto a basis of currents (`tw_reduce_model`, thin_wall_solvers.F90:1180-1359; reference
+        `_core.py:717-739`) and write the reduced-model file.  Returns the file name (reading it back needs h5py, as in the
+        reference's `ThinCurr_reduced`).'''
+        basis_set = numpy.ascontiguousarray(basis_set, dtype=numpy.float64)
+        sensor_ptr = sensor_obj['ptr'] if sensor_obj is not None else c_void_p()
+        error_string = self._oft_env.get_c_errorbuff()
+        thincurr_reduce_model(self.tw_obj, self._oft_env.path2c(filename), c_int(basis_set.shape[0]), basis_set, c_bool(compute_B),
+                              sensor_ptr, c_void_p(), error_string)
+        if error_string.value != b'':
+            raise Exception(error_string.value.decode())
+        return filename
+
     def compute_Bel_shard(self, nshards, shard, out, stream=None):
         '''! Rows of the B operator into the CUDA tensor `out[3, np, nrows]`.'''
         sptr = c_void_p(stream) if stream else c_void_p()
@@ -534,5 +612,5 @@ class ThinCurr():
     def _oos(self, *a, **k):
         raise NotImplementedError('Not part of the B200 operator-build backend; use the reference library for this step')
 
-    compute_freq_response = run_td = plot_td = build_reduced_model = cross_eval = _oos
+    compute_freq_response = run_td = plot_td = _oos
     setup_io = save_current = save_scalar = reconstruct_current = reconstruct_Bfield = get_regmat = _oos

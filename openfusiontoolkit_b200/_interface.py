@@ -91,6 +91,13 @@ b200_Lmat_shard_host = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard_host
     [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p], c_int)
 b200_Lmat_block = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_block,
     [c_void_p, c_int, ctypes_numpy_array(int32, 1), c_int, ctypes_numpy_array(int32, 1), c_void_p, c_int64, c_void_p], c_int)
+b200_Lmatblock = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmatblock,
+    [c_void_p, c_void_p, c_int, ctypes_numpy_array(int32, 1), c_int, ctypes_numpy_array(int32, 1), c_void_p, c_int64, c_void_p], c_int)
+b200_LmatHole = ctypes_subroutine(oftpy_lib.thincurr_b200_LmatHole, [c_void_p, c_void_p, c_int64, c_void_p], c_int)
+b200_Bops_block = ctypes_subroutine(oftpy_lib.thincurr_b200_Bops_block,
+    [c_void_p, c_int, ctypes_numpy_array(int32, 1), c_int, ctypes_numpy_array(int32, 1), c_int, c_void_p, c_int64, c_void_p], c_int)
+b200_cross_eval = ctypes_subroutine(oftpy_lib.thincurr_b200_cross_eval,
+    [c_void_p, c_void_p, c_int, ctypes_numpy_array(float64, 2), ctypes_numpy_array(float64, 2), c_void_p], c_int)
 b200_h5_write = ctypes_subroutine(oftpy_lib.thincurr_b200_h5_write,
     [c_char_p, c_int, ctypes.POINTER(c_char_p), ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int64), ctypes.POINTER(c_void_p)], c_int)
 b200_Bel_shard = ctypes_subroutine(oftpy_lib.thincurr_b200_Bel_shard, [c_void_p, c_int, c_int, c_void_p, c_void_p], c_int)

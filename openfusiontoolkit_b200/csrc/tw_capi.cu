@@ -164,6 +164,7 @@ void drop_device_state(Model& m) {
     d.reset();
   }
   m.dev.clear();
+  m.block_ctx.reset();
 }
 
 // rows of a shard: internal DOF range of its patches (+ the V-coil rows on the last shard)
@@ -893,11 +894,26 @@ void thincurr_time_domain(void*, bool, double, int, double, double, bool, int, i
 void thincurr_time_domain_plot(void*, bool, bool, int, int, void*, const double*, int, void*, char* error_str) {
   set_err(error_str, std::string("thincurr_time_domain_plot ") + kNotProvided);
 }
-void thincurr_reduce_model(void*, const char*, int, const double*, bool, void*, void*, char* error_str) {
-  set_err(error_str, std::string("thincurr_reduce_model ") + kNotProvided);
+void thincurr_reduce_model(void* tw_ptr, const char* filename, int neigs, const double* eig_vec, bool compute_B, void* sensor_ptr,
+                           void* hodlr_ptr, char* error_str) {
+  // thincurr_f.F90:1208-1247 -> tw_reduce_model (thin_wall_solvers.F90:1180-1359), dense L only
+  Model& m = *(Model*)tw_ptr;
+  if (m.nelems <= 0) return set_err(error_str, "Invalid ThinCurr model, may not be setup yet");
+  if (hodlr_ptr) return set_err(error_str, "HODLR compression is not provided by the B200 dense backend");
+  if (!m.Lmat.p) return set_err(error_str, "Inductance matrix required, but not computed");
+  if (m.R_kr.empty()) return set_err(error_str, "Resistance matrix required, but not computed");
+  set_err(error_str, "");
+  std::string err = reduce_model(m, (const Sensors*)sensor_ptr, filename ? filename : "", neigs, eig_vec, compute_B);
+  if (!err.empty()) set_err(error_str, err);
 }
-void thincurr_cross_eval(void*, void*, int, const double*, double*, char* error_str) {
-  set_err(error_str, std::string("thincurr_cross_eval ") + kNotProvided);
+void thincurr_cross_eval(void* tw_ptr1, void* tw_ptr2, int nrhs, const double* vec1, double* vec2, char* error_str) {
+  // thincurr_f.F90:525-541 -> tw_compute_Lmat_MF (thin_wall.F90:1190-1414)
+  set_err(error_str, "");
+  if (!tw_ptr1 || !tw_ptr2) return set_err(error_str, "Invalid ThinCurr model, may not be setup yet");
+  Model &m1 = *(Model*)tw_ptr1, &m2 = *(Model*)tw_ptr2;
+  if (m1.verbose) std::printf(" Applying MF element<->element inductance matrix\n");
+  std::string err = gpu_cross_eval(m1, m2, nrhs, vec1, vec2, nullptr);
+  if (!err.empty()) set_err(error_str, err);
 }
 void thincurr_apply_Lmat(void* tw_ptr, double* vals, void* hodlr_ptr) {
   Model& m = *(Model*)tw_ptr;
@@ -1284,6 +1300,37 @@ int thincurr_b200_Lmat_block(void* tw_ptr, int nrows, const int* row_ids, int nc
   err = gpu_lmat_tiles(ds->ps, ds->ps, tiles, row_out, true, d_out, ld, stream, nullptr, d_col_map, false);
   cudaFreeAsync(d_col_map, stream);
   if (!err.empty()) return fail(err);
+  return 0;
+}
+
+int thincurr_b200_Lmatblock(void* tw_row, void* tw_col, int nrp, const int* row_pts, int ncp, const int* col_pts, double* out, int64_t ld,
+                            void* stream) {
+  if (!tw_row) return fail("thincurr_b200_Lmatblock: no model");
+  Model &mr = *(Model*)tw_row, &mc = tw_col ? *(Model*)tw_col : mr;
+  std::string err = gpu_lmatblock(mr, mc, nrp, row_pts, ncp, col_pts, out, ld, (cudaStream_t)stream);
+  if (!err.empty()) return fail(err);
+  return 0;
+}
+
+int thincurr_b200_LmatHole(void* tw_ptr, double* out, int64_t ld, void* stream) {
+  std::string err = gpu_lmathole(*(Model*)tw_ptr, out, ld, (cudaStream_t)stream);
+  if (!err.empty()) return fail(err);
+  return 0;
+}
+
+int thincurr_b200_Bops_block(void* tw_ptr, int nrp, const int* row_pts, int ncp, const int* col_pts, int dir, double* out, int64_t ld,
+                             void* stream) {
+  std::string err = gpu_bops_block(*(Model*)tw_ptr, nrp, row_pts, ncp, col_pts, dir, out, ld, (cudaStream_t)stream);
+  if (!err.empty()) return fail(err);
+  return 0;
+}
+
+int thincurr_b200_cross_eval(void* tw_ptr1, void* tw_ptr2, int nrhs, const double* vec1, double* vec2, int64_t* counts) {
+  long long c[3] = {0, 0, 0};
+  std::string err = gpu_cross_eval(*(Model*)tw_ptr1, *(Model*)tw_ptr2, nrhs, vec1, vec2, counts ? c : nullptr);
+  if (!err.empty()) return fail(err);
+  if (counts)
+    for (int k = 0; k < 3; k++) counts[k] = c[k];
   return 0;
 }
 

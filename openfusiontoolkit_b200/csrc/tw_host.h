@@ -109,6 +109,7 @@ struct Model {
   // ---- device side ----
   std::shared_ptr<Plan> plan;
   std::vector<std::shared_ptr<DeviceState>> dev;  // one per CUDA device used
+  std::shared_ptr<void> block_ctx;                // plain cell arrays on the device for the list sweeps (tw_blocks.cu)
   bool verbose = true;
 
   // setup (tw_setup.cpp)

@@ -490,8 +490,11 @@ void pad8(std::vector<uint8_t>& v) { while (v.size() % 8) v.push_back(0); }
 }  // namespace
 
 std::string write_h5_file(const std::string& path, const std::vector<H5Item>& items_in) {
-  constexpr int kLeafK = 4, kNodeK = 16;
-  if (items_in.size() > 2 * kLeafK) return "write_h5_file: at most 8 datasets";
+  // symbol-table nodes hold 2 * "group leaf node K" entries (a superblock field): libhdf5's default 4 for up to 8
+  // datasets (the Bmat cache), 16 above that (reduced-model files: up to 13 datasets) -- still one node
+  constexpr int kNodeK = 16;
+  const int kLeafK = items_in.size() > 8 ? 16 : 4;
+  if (items_in.size() > (size_t)(2 * kLeafK)) return "write_h5_file: at most 32 datasets";
   std::vector<H5Item> items = items_in;
   std::sort(items.begin(), items.end(), [](const H5Item& a, const H5Item& b) { return a.name < b.name; });
   const uint64_t UNDEF = ~0ull;

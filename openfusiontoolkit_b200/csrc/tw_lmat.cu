@@ -1281,33 +1281,41 @@ __global__ void symmetrize_kernel(int i0, int i1, const int* __restrict__ dof_or
 // whole block: bands of one device); 1: only the entries of the tiles the OTHER shard evaluated (symmetric shards: tile
 // {patch(i), patch(j)} belongs to the shard of j iff !sym_tile_is_mine(patch(i), patch(j))) -- the rest of dst's block was
 // computed in place, and the corresponding part of src is what src's owner is copying from here at the same time.
+constexpr int kCrossI = 4;  // 32-row sub-tiles of dst a block handles against the same 32 rows of src (page reuse on the peer)
 __global__ void symmetrize_cross_kernel(int i0, int i1, int j0, int j1, const int* __restrict__ dof_orig, const int* __restrict__ dof_patch,
                                         int checker, double* __restrict__ dst, const double* __restrict__ src, long long ld) {
   __shared__ double tile[32][33];
   __shared__ int oi_s[32], oj_s[32], pi_s[32], pj_s[32];
-  const int ib = i0 + 32 * blockIdx.x, jb = j0 + 32 * blockIdx.y;
+  const int jb = j0 + 32 * blockIdx.y;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-  if (ty == 0) {
-    oi_s[tx] = ib + tx < i1 ? dof_orig[ib + tx] : -1;
-    pi_s[tx] = ib + tx < i1 ? dof_patch[ib + tx] : -1;
-  } else if (ty == 1) {
+  if (ty == 1) {
     oj_s[tx] = jb + tx < j1 ? dof_orig[jb + tx] : -1;
     pj_s[tx] = jb + tx < j1 ? dof_patch[jb + tx] : -1;
   }
-  __syncthreads();
-  if (checker) {  // block-uniform early exit: the block lies in one patch pair whose tile is mine (patches are contiguous ranges)
-    const int il = min(31, i1 - 1 - ib), jl = min(31, j1 - 1 - jb);
-    if (pi_s[0] == pi_s[il] && pj_s[0] == pj_s[jl] && tw::sym_tile_is_mine(pi_s[0], pj_s[0])) return;
-  }
-  for (int jj = ty; jj < 32; jj += 8) {  // read src[j][orig(i)], lanes over i
-    const int j = jb + jj;
-    if (j < j1 && oi_s[tx] >= 0 && !(checker && tw::sym_tile_is_mine(pi_s[tx], pj_s[jj])))
-      tile[jj][tx] = __ldcg(src + (long long)(j - j0) * ld + oi_s[tx]);
-  }
-  __syncthreads();
-  for (int ii = ty; ii < 32; ii += 8) {  // write dst[i][orig(j)], lanes over j
-    const int i = ib + ii;
-    if (i < i1 && oj_s[tx] >= 0 && !(checker && tw::sym_tile_is_mine(pi_s[ii], pj_s[tx]))) dst[(long long)(i - i0) * ld + oj_s[tx]] = tile[tx][ii];
+#pragma unroll 1
+  for (int sub = 0; sub < kCrossI; sub++) {
+    const int ib = i0 + 32 * (blockIdx.x * kCrossI + sub);
+    if (ib >= i1) break;
+    __syncthreads();  // previous sub-tile done with the shared arrays
+    if (ty == 0) {
+      oi_s[tx] = ib + tx < i1 ? dof_orig[ib + tx] : -1;
+      pi_s[tx] = ib + tx < i1 ? dof_patch[ib + tx] : -1;
+    }
+    __syncthreads();
+    if (checker) {  // block-uniform skip: the sub-tile lies in one patch pair whose tile is mine (patches are contiguous ranges)
+      const int il = min(31, i1 - 1 - ib), jl = min(31, j1 - 1 - jb);
+      if (pi_s[0] == pi_s[il] && pj_s[0] == pj_s[jl] && tw::sym_tile_is_mine(pi_s[0], pj_s[0])) continue;
+    }
+    for (int jj = ty; jj < 32; jj += 8) {  // read src[j][orig(i)], lanes over i
+      const int j = jb + jj;
+      if (j < j1 && oi_s[tx] >= 0 && !(checker && tw::sym_tile_is_mine(pi_s[tx], pj_s[jj])))
+        tile[jj][tx] = __ldcg(src + (long long)(j - j0) * ld + oi_s[tx]);
+    }
+    __syncthreads();
+    for (int ii = ty; ii < 32; ii += 8) {  // write dst[i][orig(j)], lanes over j
+      const int i = ib + ii;
+      if (i < i1 && oj_s[tx] >= 0 && !(checker && tw::sym_tile_is_mine(pi_s[ii], pj_s[tx]))) dst[(long long)(i - i0) * ld + oj_s[tx]] = tile[tx][ii];
+    }
   }
 }
 
@@ -1466,7 +1474,7 @@ void DevicePatchSet::release() {
 std::string gpu_symmetrize_cross(const DevicePatchSet& A, int i0, int i1, int j0, int j1, double* dst, const double* src, long long ld,
                                  cudaStream_t stream, bool checker) {
   if (i1 <= i0 || j1 <= j0) return "";
-  twk::symmetrize_cross_kernel<<<dim3((i1 - i0 + 31) / 32, (j1 - j0 + 31) / 32), dim3(32, 8), 0, stream>>>(i0, i1, j0, j1, A.dof_orig, A.dof_patch,
+  twk::symmetrize_cross_kernel<<<dim3((i1 - i0 + 32 * twk::kCrossI - 1) / (32 * twk::kCrossI), (j1 - j0 + 31) / 32), dim3(32, 8), 0, stream>>>(i0, i1, j0, j1, A.dof_orig, A.dof_patch,
                                                                                                       checker ? 1 : 0, dst, src, ld);
   CK(cudaGetLastError());
   note_launch();

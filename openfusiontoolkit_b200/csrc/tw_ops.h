@@ -43,6 +43,17 @@ std::string gpu_lr_eigenmodes_host(Model& m, int neigs, double* eig_vals, double
 std::string lr_eigs_lanczos(int n, const int* kr, const int* lc, const double* rv, int neigs, double tol, int max_dim,
                             const std::function<std::string(const double*, double*)>& apply_L, double* eig_vals, double* eig_vec,
                             int* iters_out);
+// cell-list sweeps (tw_blocks.cu): HODLR dense-block builders, matrix-free apply, reduced-model products
+std::string gpu_lmatblock(Model& mr, Model& mc, int nrp, const int* row_pts, int ncp, const int* col_pts, double* out, long long ld,
+                          cudaStream_t stream);
+std::string gpu_lmathole(Model& m, double* out, long long ld, cudaStream_t stream);
+std::string gpu_bops_block(Model& m, int nrp, const int* row_pts, int ncp, const int* col_pts, int dir, double* out, long long ld,
+                           cudaStream_t stream);
+std::string gpu_cross_eval(Model& m1, Model& m2, int nrhs, const double* vec1, double* vec2, long long* counts);
+std::string gpu_host_matrix_multi(const double* A, size_t nrows, size_t n, int nq, const double* d_X, long long ldx, double* d_Y,
+                                  long long ldy);
+std::string gpu_gram(const double* d_U, long long ldu, int na, const double* d_W, long long ldw, int nb, int n, double* h_G);
+std::string reduce_model(Model& m, const Sensors* sens, const std::string& filename, int neigs, const double* eig_vec, bool compute_B);
 // iquad histogram + visited-pair count of the reference loop nest
 std::string gpu_pair_stats(Model& m, int64_t* hist, int64_t* visited);
 

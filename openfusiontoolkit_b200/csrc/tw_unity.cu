@@ -2,6 +2,7 @@
 // tw_device.cuh must have exactly one instance per device image).
 #include "tw_lmat.cu"
 #include "tw_ops.cu"
+#include "tw_blocks.cu"
 #ifdef TW_TEST_HOOKS
 #include "tw_probe.cu"
 #endif

@@ -761,3 +761,305 @@ void tco_lmat_rows2(const tco_model *m, int nd, const int *dofs, double *out, do
 }
 
 void tco_lmat_rows(const tco_model *m, int nd, const int *dofs, double *out) { tco_lmat_rows2(m, nd, dofs, out, NULL); }
+
+/* ================================================================== */
+/* matrix-free apply, HODLR dense-block builders        */
+/* ================================================================== */
+
+/* Pair integral of tw_compute_Lmat_MF, thin_wall.F90:1243-1337: the 3-level heuristic
+ * (subtended angle > pi/8 or dl_min/dl_max < 0.95 -> order 10, 25 points; angle > pi/4 or ratio
+ * < 0.75 -> analytic potential of cell i at the 25 points of cell j; else order 6, 12 points).
+ * cls_out: 0 far, 1 close, 2 very close. */
+static const double MF_TOLS[2] = {0.75, 0.95}; /* quad_tols(1:2), thin_wall.F90:156 */
+double tco_mf_pair_T(const double pts_i[3][3], double area_i, const double pts_j[3][3], double area_j,
+                     int *cls_out) {
+  int close_flag = 0, vvclose_flag = 0;
+  double dl_max = -1.e99, dl_min;
+  for (int ii = 0; ii < 3; ii++) {
+    double pt_j[3], pt_i[3], tmp;
+    for (int d = 0; d < 3; d++) pt_j[d] = pts_j[0][d] - pts_i[ii][d];
+    tmp = sqrt(pt_j[0] * pt_j[0] + pt_j[1] * pt_j[1] + pt_j[2] * pt_j[2]);
+    if (tmp < 1.e-10) { close_flag = 1; break; }
+    for (int d = 0; d < 3; d++) pt_j[d] = pt_j[d] / tmp;
+    for (int d = 0; d < 3; d++) pt_i[d] = pts_j[1][d] - pts_i[ii][d];
+    tmp = sqrt(pt_i[0] * pt_i[0] + pt_i[1] * pt_i[1] + pt_i[2] * pt_i[2]);
+    if (tmp < 1.e-10) { close_flag = 1; break; }
+    for (int d = 0; d < 3; d++) pt_i[d] = pt_i[d] / tmp;
+    dl_max = fmax(dl_max, fabs(acos(dot3(pt_j, pt_i))));
+    for (int d = 0; d < 3; d++) pt_i[d] = pts_j[2][d] - pts_i[ii][d];
+    tmp = sqrt(pt_i[0] * pt_i[0] + pt_i[1] * pt_i[1] + pt_i[2] * pt_i[2]);
+    if (tmp < 1.e-10) { close_flag = 1; break; }
+    for (int d = 0; d < 3; d++) pt_i[d] = pt_i[d] / tmp;
+    dl_max = fmax(dl_max, fabs(acos(dot3(pt_j, pt_i))));
+  }
+  if (dl_max > PI / 8.0) {
+    close_flag = 1;
+    if (dl_max > PI / 4.0) vvclose_flag = 1;
+  } else {
+    dl_min = 1.e99;
+    dl_max = -1.e99;
+    for (int ii = 0; ii < 3; ii++)
+      for (int jj = 0; jj < 3; jj++) {
+        double dx = pts_i[ii][0] - pts_j[jj][0], dy = pts_i[ii][1] - pts_j[jj][1], dz = pts_i[ii][2] - pts_j[jj][2];
+        double d = sqrt(dx * dx + dy * dy + dz * dz);
+        dl_min = fmin(dl_min, d);
+        dl_max = fmax(dl_max, d);
+      }
+    if (dl_min / dl_max < MF_TOLS[1]) close_flag = 1;
+    if (dl_min / dl_max < MF_TOLS[0]) vvclose_flag = 1;
+  }
+  double tmp = 0.0;
+  if (cls_out) *cls_out = close_flag ? (vvclose_flag ? 2 : 1) : 0;
+  if (close_flag && vvclose_flag) {
+    const int iq = 10, nq = TCQ_NP[iq];
+    const double *w = TCQ_WTS + TCQ_OFF[iq];
+    for (int jj = 0; jj < nq; jj++) {
+      double pt_j[3];
+      quad_point(iq, jj, pts_j, pt_j);
+      tmp = tmp + w[jj] * tco_phipot(pts_i, pt_j);
+    }
+    return tmp * area_j;
+  }
+  const int iq = close_flag ? 10 : 6, nq = TCQ_NP[iq];
+  const double *w = TCQ_WTS + TCQ_OFF[iq];
+  for (int ii = 0; ii < nq; ii++) {
+    double pt_i[3];
+    quad_point(iq, ii, pts_i, pt_i);
+    for (int jj = 0; jj < nq; jj++) {
+      double pt_j[3];
+      quad_point(iq, jj, pts_j, pt_j);
+      double dx = pt_i[0] - pt_j[0], dy = pt_i[1] - pt_j[1], dz = pt_i[2] - pt_j[2];
+      tmp = tmp + w[jj] * w[ii] / sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  }
+  return tmp * area_i * area_j;
+}
+
+/* tw_compute_Lmat_MF, thin_wall.F90:1190-1414: b(:,irhs) = M a(:,irhs), a Fortran (row%nelems,nrhs),
+ * b Fortran (col%nelems,nrhs); V-coil parts are not computed by the reference either (:1385).
+ * counts[3] (optional): pairs per class. */
+void tco_lmat_mf(const tco_model *row, const tco_model *col, int nrhs, const double *a, double *b,
+                 long long *counts) {
+  const long long nr = row->nelems, ncl = col->nelems;
+  memset(b, 0, sizeof(double) * (size_t)ncl * nrhs);
+  long long c0 = 0, c1 = 0, c2 = 0;
+#pragma omp parallel for schedule(dynamic, 100) reduction(+ : c0, c1, c2)
+  for (int i = 0; i < row->nc; i++) {
+    double pts_i[3][3], evec_i[3][3], pts_j[3][3], evec_j[3][3];
+    load_cell(row, i, pts_i, evec_i);
+    for (int j = 0; j < col->nc; j++) {
+      load_cell(col, j, pts_j, evec_j);
+      int cls;
+      const double tmp = tco_mf_pair_T(pts_i, row->ca[i], pts_j, col->ca[j], &cls);
+      if (cls == 0) c0++; else if (cls == 1) c1++; else c2++;
+      for (int ii = 0; ii < 3; ii++) {
+        int ik = row->pmap[row->lc[3 * i + ii]];
+        if (ik == 0) continue;
+        for (int jj = 0; jj < 3; jj++) {
+          int jk = col->pmap[col->lc[3 * j + jj]];
+          if (jk == 0) continue;
+          double v = dot3(evec_i[ii], evec_j[jj]) * tmp;
+          for (int q = 0; q < nrhs; q++) {
+#pragma omp atomic
+            b[q * ncl + (jk - 1)] += v * a[q * nr + (ik - 1)];
+          }
+        }
+        for (int jj = col->kfh[j]; jj < col->kfh[j + 1]; jj++) {
+          int jk = abs(col->lfh[2 * jj]) + col->np_active;
+          double v = isign(col->lfh[2 * jj]) * dot3(evec_i[ii], evec_j[col->lfh[2 * jj + 1]]) * tmp;
+          for (int q = 0; q < nrhs; q++) {
+#pragma omp atomic
+            b[q * ncl + (jk - 1)] += v * a[q * nr + (ik - 1)];
+          }
+        }
+      }
+      for (int ii = row->kfh[i]; ii < row->kfh[i + 1]; ii++) {
+        int ik = abs(row->lfh[2 * ii]) + row->np_active;
+        const double *ei = evec_i[row->lfh[2 * ii + 1]];
+        int si = isign(row->lfh[2 * ii]);
+        for (int jj = 0; jj < 3; jj++) {
+          int jk = col->pmap[col->lc[3 * j + jj]];
+          if (jk == 0) continue;
+          double v = si * dot3(ei, evec_j[jj]) * tmp;
+          for (int q = 0; q < nrhs; q++) {
+#pragma omp atomic
+            b[q * ncl + (jk - 1)] += v * a[q * nr + (ik - 1)];
+          }
+        }
+        for (int jj = col->kfh[j]; jj < col->kfh[j + 1]; jj++) {
+          int jk = abs(col->lfh[2 * jj]) + col->np_active;
+          double v = si * isign(col->lfh[2 * jj]) * dot3(ei, evec_j[col->lfh[2 * jj + 1]]) * tmp;
+          for (int q = 0; q < nrhs; q++) {
+#pragma omp atomic
+            b[q * ncl + (jk - 1)] += v * a[q * nr + (ik - 1)];
+          }
+        }
+      }
+    }
+  }
+  for (long long k = 0; k < ncl * nrhs; k++) b[k] = b[k] / (4.0 * PI);
+  if (counts) { counts[0] = c0; counts[1] = c1; counts[2] = c2; }
+}
+
+/* tw_compute_Lmatblock, thin_wall_hodlr.F90:289-404: dense block over cell sub-lists.  The ROW block's cell is always
+ * the analytic side of a near pair, every listed pair is visited (no jmax<imin skip), vertex DOFs only.
+ * row_cells/col_cells 0-based; row_inv/col_inv [np] = 1-based index in the block or 0 (oft_tw_block%inv_map).
+ * Lmat Fortran (ncol_out,nrow_out): Lmat[(ik-1)*ncol_out + (jk-1)]. */
+void tco_lmat_block(const tco_model *row, const tco_model *col, int nrc, const int *row_cells, const int *row_inv,
+                    int ncc, const int *col_cells, const int *col_inv, int nrow_out, int ncol_out, double *Lmat) {
+  memset(Lmat, 0, sizeof(double) * (size_t)nrow_out * ncol_out);
+  for (int irow = 0; irow < nrc; irow++) {
+    const int i = row_cells[irow];
+    double pts_i[3][3], evec_i[3][3];
+    load_cell(row, i, pts_i, evec_i);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int jcol = 0; jcol < ncc; jcol++) {
+      const int j = col_cells[jcol];
+      double pts_j[3][3], evec_j[3][3];
+      load_cell(col, j, pts_j, evec_j);
+      const double tmp = tco_pair_T(pts_i, row->ca[i], pts_j, col->ca[j], NULL);
+      for (int ii = 0; ii < 3; ii++) {
+        int ik = row_inv[row->lc[3 * i + ii]];
+        if (ik == 0) continue;
+        for (int jj = 0; jj < 3; jj++) {
+          int jk = col_inv[col->lc[3 * j + jj]];
+          if (jk == 0) continue;
+          double v = dot3(evec_i[ii], evec_j[jj]) * tmp;
+#pragma omp atomic
+          Lmat[(size_t)(ik - 1) * ncol_out + (jk - 1)] += v;
+        }
+      }
+    }
+  }
+  for (size_t k = 0; k < (size_t)nrow_out * ncol_out; k++) Lmat[k] = Lmat[k] / (4.0 * PI);
+}
+
+/* tw_compute_LmatHole, thin_wall_hodlr.F90:136-285: columns of L for the hole (and V-coil) DOFs of the row model.
+ * Lmat Fortran (col%nelems, row%nholes + row%n_vcoils): Lmat[ik*col%nelems + jk]; Ael2coil Fortran (nelems,n_vcoils),
+ * Acoil2coil (n_vcoils,n_vcoils), NULL without V-coils. */
+void tco_lmat_hole(const tco_model *row, const tco_model *col, const double *Ael2coil, const double *Acoil2coil,
+                   double *Lmat) {
+  const long long ncl = col->nelems;
+  const int nk = row->nholes + row->n_vcoils;
+  memset(Lmat, 0, sizeof(double) * (size_t)ncl * nk);
+#pragma omp parallel for schedule(dynamic, 100)
+  for (int i = 0; i < row->nc; i++) {
+    if (row->kfh[i + 1] - row->kfh[i] == 0) continue;
+    double pts_i[3][3], evec_i[3][3], pts_j[3][3], evec_j[3][3];
+    load_cell(row, i, pts_i, evec_i);
+    for (int j = 0; j < col->nc; j++) {
+      load_cell(col, j, pts_j, evec_j);
+      const double tmp = tco_pair_T(pts_i, row->ca[i], pts_j, col->ca[j], NULL);
+      for (int ii = row->kfh[i]; ii < row->kfh[i + 1]; ii++) {
+        const int ik = abs(row->lfh[2 * ii]);
+        const double *ei = evec_i[row->lfh[2 * ii + 1]];
+        const int si = isign(row->lfh[2 * ii]);
+        for (int jj = 0; jj < 3; jj++) {
+          int jk = col->pmap[col->lc[3 * j + jj]];
+          if (jk <= 0) continue;
+          double v = si * dot3(ei, evec_j[jj]) * tmp;
+#pragma omp atomic
+          Lmat[(size_t)(ik - 1) * ncl + (jk - 1)] += v;
+        }
+        for (int jj = col->kfh[j]; jj < col->kfh[j + 1]; jj++) {
+          int jk = abs(col->lfh[2 * jj]) + col->np_active;
+          double v = si * isign(col->lfh[2 * jj]) * dot3(ei, evec_j[col->lfh[2 * jj + 1]]) * tmp;
+#pragma omp atomic
+          Lmat[(size_t)(ik - 1) * ncl + (jk - 1)] += v;
+        }
+      }
+    }
+  }
+  if (Ael2coil && Acoil2coil) { /* :253-276 (row == col in every call site) */
+    const long long ne = row->nelems;
+    for (int i = 0; i < row->np_active + row->nholes; i++)
+      for (int j = 0; j < col->n_vcoils; j++) Lmat[(size_t)(col->nholes + j) * ncl + i] = Ael2coil[(size_t)j * ne + i];
+    for (int i = 0; i < row->nholes; i++)
+      for (int j = 0; j < col->n_vcoils; j++)
+        Lmat[(size_t)i * ncl + (row->np_active + col->nholes + j)] = Ael2coil[(size_t)j * ne + row->np_active + i];
+    for (int i = 0; i < row->n_vcoils; i++)
+      for (int j = 0; j < col->n_vcoils; j++)
+        Lmat[(size_t)(row->nholes + i) * ncl + (col->np_active + col->nholes + j)] = Acoil2coil[(size_t)j * row->n_vcoils + i];
+  }
+  for (size_t k = 0; k < (size_t)ncl * nk; k++) Lmat[k] = Lmat[k] / (4.0 * PI);
+}
+
+/* tw_compute_Bops_block, thin_wall_hodlr.F90:580-691: one Cartesian component (dir = 0,1,2) of the B operator for the
+ * vertex DOFs of a row block (cells row_cells, inv_map row_inv) at the mesh vertices col_pts (0-based).
+ * Bop Fortran (ncp, nrow_out): Bop[(ik-1)*ncp + jcol]. */
+void tco_bops_block(const tco_model *m, int nrc, const int *row_cells, const int *row_inv, int nrow_out, int ncp,
+                    const int *col_pts, int dir, double *Bop) {
+  const double B_dx = 1.e-6;
+  memset(Bop, 0, sizeof(double) * (size_t)ncp * nrow_out);
+  for (int irow = 0; irow < nrc; irow++) {
+    const int i = row_cells[irow];
+    double pts_i[3][3], evec_i[3][3];
+    const double area_i = m->ca[i];
+    load_cell(m, i, pts_i, evec_i);
+    const double *norm_j = m->norm + 3 * i;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int jcol = 0; jcol < ncp; jcol++) {
+      const int j = col_pts[jcol];
+      double pt_j[3] = {m->r[3 * j], m->r[3 * j + 1], m->r[3 * j + 2]};
+      double dl_min = 1.e99;
+      double dl_max = sqrt(fmax(area_i, m->va[j] / (PI * PI)));
+      for (int ii = 0; ii < 3; ii++) {
+        double dx = pts_i[ii][0] - pt_j[0], dy = pts_i[ii][1] - pt_j[1], dz = pts_i[ii][2] - pt_j[2];
+        double d = sqrt(dx * dx + dy * dy + dz * dz);
+        dl_min = fmin(dl_min, d);
+        dl_max = fmax(dl_max, d);
+      }
+      const int is_neighbor = (dl_min < 1.e-8);
+      const int iquad = tco_iquad(dl_min, dl_max);
+      double a[9];
+      if (iquad > 10) {
+        double diffvec[3] = {0.0, 0.0, 0.0};
+        if (is_neighbor)
+          for (int d = 0; d < 3; d++) pt_j[d] = pt_j[d] - norm_j[d] * 10.0 * B_dx;
+        for (int ik = 1; ik <= 2; ik++) {
+          if (ik == 2)
+            for (int d = 0; d < 3; d++) pt_j[d] = pt_j[d] + norm_j[d] * 20.0 * B_dx;
+          for (int jj = 0; jj < 3; jj++) {
+            pt_j[jj] = pt_j[jj] + B_dx;
+            double tmp = tco_phipot(pts_i, pt_j);
+            diffvec[jj] = diffvec[jj] + tmp / (2.0 * B_dx);
+            pt_j[jj] = pt_j[jj] - 2.0 * B_dx;
+            tmp = tco_phipot(pts_i, pt_j);
+            diffvec[jj] = diffvec[jj] - tmp / (2.0 * B_dx);
+            pt_j[jj] = pt_j[jj] + B_dx;
+          }
+          if (!is_neighbor) break;
+        }
+        if (is_neighbor)
+          for (int d = 0; d < 3; d++) diffvec[d] = diffvec[d] / 2.0;
+        for (int ik = 0; ik < 3; ik++) {
+          a[3 * ik + 0] = diffvec[1] * evec_i[ik][2] - diffvec[2] * evec_i[ik][1];
+          a[3 * ik + 1] = diffvec[2] * evec_i[ik][0] - diffvec[0] * evec_i[ik][2];
+          a[3 * ik + 2] = diffvec[0] * evec_i[ik][1] - diffvec[1] * evec_i[ik][0];
+        }
+      } else {
+        const int nq = TCQ_NP[iquad];
+        const double *w = TCQ_WTS + TCQ_OFF[iquad];
+        for (int ik = 0; ik < 3; ik++) {
+          double diffvec[3] = {0.0, 0.0, 0.0};
+          for (int ii = 0; ii < nq; ii++) {
+            double x[3], pt_i[3], cr[3];
+            quad_point(iquad, ii, pts_i, x);
+            for (int d = 0; d < 3; d++) pt_i[d] = pt_j[d] - x[d];
+            cross3(evec_i[ik], pt_i, cr);
+            double s2 = pt_i[0] * pt_i[0] + pt_i[1] * pt_i[1] + pt_i[2] * pt_i[2];
+            double den = pow(s2, 1.5);
+            for (int d = 0; d < 3; d++) diffvec[d] = diffvec[d] + cr[d] * w[ii] / den;
+          }
+          for (int d = 0; d < 3; d++) a[3 * ik + d] = diffvec[d] * area_i;
+        }
+      }
+      for (int ii = 0; ii < 3; ii++) {
+        int ik = row_inv[m->lc[3 * i + ii]];
+        if (ik == 0) continue;
+        Bop[(size_t)(ik - 1) * ncp + jcol] += a[3 * ii + dir]; /* distinct jcol per thread, serial over irow */
+      }
+    }
+  }
+  for (size_t k = 0; k < (size_t)ncp * nrow_out; k++) Bop[k] = Bop[k] / (4.0 * PI);
+}

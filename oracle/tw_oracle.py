@@ -580,6 +580,57 @@ class OracleModel:
         Bdr = Bdr[:, :self.n_icoils] * MU0 / (4.0 * np.pi)
         return Bel, Bdr
 
+    # ---- SURVEY 8f rows ---------------------------------------------------------------
+    def cross_eval(self, other, field, counts=None):
+        """tw_compute_Lmat_MF(self, other, nrhs, a, b) as ThinCurr.cross_eval sees it (thin_wall.F90:1190-1414,
+        _core.py:533-549): field (nrhs, self.nelems) -> (nrhs, other.nelems)."""
+        a = np.ascontiguousarray(field, np.float64)
+        b = np.zeros((a.shape[0], other.nelems))
+        cp = counts.ctypes.data_as(ctypes.c_void_p) if counts is not None else None
+        lib().tco_lmat_mf(ctypes.byref(self.c), ctypes.byref(other.c), ctypes.c_int(a.shape[0]), a.ctypes.data_as(ctypes.c_void_p),
+                          b.ctypes.data_as(ctypes.c_void_p), cp)
+        return b
+
+    def block(self, pts):
+        """oft_tw_block of a vertex subset (thin_wall_hodlr.F90:60-70): 0-based vertex ids -> (cells touching them in
+        ascending order, inv_map [np] with the 1-based position in the block or 0)."""
+        pts = np.asarray(pts, np.int32)
+        inv = np.zeros(self.np_, np.int32)
+        inv[pts] = np.arange(1, len(pts) + 1)
+        cells = np.nonzero((inv[self.lc] > 0).any(axis=1))[0].astype(np.int32)
+        return np.ascontiguousarray(cells), inv
+
+    def lmat_block(self, row_pts, col_pts, other=None):
+        """tw_compute_Lmatblock (thin_wall_hodlr.F90:289-404); returns [len(row_pts)][len(col_pts)]
+        (= Fortran Lmat(col, row))."""
+        col = self if other is None else other
+        rc, rinv = self.block(row_pts)
+        cc, cinv = col.block(col_pts)
+        out = np.zeros((len(row_pts), len(col_pts)))
+        lib().tco_lmat_block(ctypes.byref(self.c), ctypes.byref(col.c), ctypes.c_int(len(rc)), rc.ctypes.data_as(ctypes.c_void_p),
+                             rinv.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(len(cc)), cc.ctypes.data_as(ctypes.c_void_p),
+                             cinv.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(len(row_pts)), ctypes.c_int(len(col_pts)),
+                             out.ctypes.data_as(ctypes.c_void_p))
+        return out
+
+    def lmat_hole(self):
+        """tw_compute_LmatHole(self, self) (thin_wall_hodlr.F90:136-285); returns [nholes + n_vcoils][nelems]."""
+        out = np.zeros((self.nholes + self.n_vcoils, self.nelems))
+        a2c = self.Ael2coil.ctypes.data_as(ctypes.c_void_p) if self.n_vcoils else None
+        c2c = self.Acoil2coil.ctypes.data_as(ctypes.c_void_p) if self.n_vcoils else None
+        lib().tco_lmat_hole(ctypes.byref(self.c), ctypes.byref(self.c), a2c, c2c, out.ctypes.data_as(ctypes.c_void_p))
+        return out
+
+    def bops_block(self, row_pts, col_pts, direction):
+        """tw_compute_Bops_block (thin_wall_hodlr.F90:580-691), direction 0/1/2; returns [len(row_pts)][len(col_pts)]."""
+        rc, rinv = self.block(row_pts)
+        cp = np.ascontiguousarray(col_pts, np.int32)
+        out = np.zeros((len(row_pts), len(cp)))
+        lib().tco_bops_block(ctypes.byref(self.c), ctypes.c_int(len(rc)), rc.ctypes.data_as(ctypes.c_void_p),
+                             rinv.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(len(row_pts)), ctypes.c_int(len(cp)),
+                             cp.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(direction), out.ctypes.data_as(ctypes.c_void_p))
+        return out
+
     def cell_basis(self):
         """Per-cell list of (dof0, E vector): vertex DOFs + signed hole DOFs (A.3 of SURVEY)."""
         out = []
