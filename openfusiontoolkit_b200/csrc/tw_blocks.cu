@@ -41,7 +41,7 @@ struct RowSlot {
   double area;
   double nh[3];    // unit normal as tw_compute_phipot forms it
   double nrm[3];   // mesh normal (B operator: on-surface offset direction)
-  double pts[kSwPts * 3];
+  double pts[kSwPts * 4];  // x, y, z, weight
 };
 
 struct SweepSmem {
@@ -66,6 +66,12 @@ struct SweepArgs {
   const double* J;             // mode 1: [nrc][kMfQ][3]
   double* F;                   // mode 1: [gridDim.y][ncc][kMfQ][3]
   unsigned long long* counts;  // optional [3]: pairs per class (mode 1) / far, near (mode 0, 2)
+  // modes 0 / 2: near pairs are not evaluated by the sweep but appended here (row-list index, column index) and handed
+  // to a second kernel that spreads them over the whole device (they cluster in the few CTAs whose columns touch the
+  // staged rows); beyond near_cap the sweep evaluates them itself
+  int2* near_list;
+  unsigned int* near_count;
+  unsigned int near_cap;
 };
 
 // ---- classification of tw_compute_Lmat_MF (thin_wall.F90:1243-1288) --------------------------------------------
@@ -151,7 +157,7 @@ __device__ __forceinline__ int mf_class(const double* Pi, const double* Pj) {
 // (rule `o` of the row cell) and the column points formed on the fly (thin_wall.F90:1069-1083)
 __device__ __forceinline__ double far_inline(const RowSlot& R, const double* Pj, int o) {
   const int n = c_qnp[o], off = c_qoff[o];
-  const double* tab = R.pts + 3 * (off - kSwOff);
+  const double* tab = R.pts + 4 * (off - kSwOff);
   double acc = 0.0;
   for (int jj = 0; jj < n; jj++) {
     const double* b = g_qpts + 3 * (off + jj);
@@ -159,17 +165,19 @@ __device__ __forceinline__ double far_inline(const RowSlot& R, const double* Pj,
     const double x = xquad(b0, b1, b2, Pj[0], Pj[3], Pj[6]), y = xquad(b0, b1, b2, Pj[1], Pj[4], Pj[7]),
                  z = xquad(b0, b1, b2, Pj[2], Pj[5], Pj[8]);
     double s = 0.0;
+#pragma unroll 2
     for (int ii = 0; ii < n; ii++) {
-      const double dx = tab[3 * ii] - x, dy = tab[3 * ii + 1] - y, dz = tab[3 * ii + 2] - z;
-      s = fma(g_qwts[off + ii], rsqrt_fast(fma(dz, dz, fma(dy, dy, dx * dx))), s);
+      const double2 xy = *reinterpret_cast<const double2*>(tab + 4 * ii), zw = *reinterpret_cast<const double2*>(tab + 4 * ii + 2);
+      const double dx = xy.x - x, dy = xy.y - y, dz = zw.x - z;
+      s = fma(zw.y, rsqrt_fast(fma(dz, dz, fma(dy, dy, dx * dx))), s);
     }
-    acc = fma(g_qwts[off + jj], s, acc);
+    acc = fma(tab[4 * jj + 3], s, acc);
   }
   return acc;
 }
 
 // near pair, whole warp: sum_q w_q phipot(row triangle, x_q(column cell)) with rule o (thin_wall.F90:1061-1068)
-__device__ __forceinline__ double near_warp(const RowSlot& R, const double* Pj, int o, int lane) {
+__device__ __forceinline__ double near_warp(const double* Pi, const double* nhi, const double* Pj, int o, int lane) {
   const int n = c_qnp[o], off = c_qoff[o];
   double acc = 0.0;
   for (int base = 0; base < n; base += 32) {
@@ -180,7 +188,7 @@ __device__ __forceinline__ double near_warp(const RowSlot& R, const double* Pj, 
       const double b0 = b[0], b1 = b[1], b2 = b[2];
       const double x = xquad(b0, b1, b2, Pj[0], Pj[3], Pj[6]), y = xquad(b0, b1, b2, Pj[1], Pj[4], Pj[7]),
                    z = xquad(b0, b1, b2, Pj[2], Pj[5], Pj[8]);
-      v = g_qwts[off + q] * phipot(R.P, R.nh, x, y, z);
+      v = g_qwts[off + q] * phipot(Pi, nhi, x, y, z);
     }
     acc += warp_sum(v);
   }
@@ -203,9 +211,10 @@ __device__ __forceinline__ void stage_rows(SweepSmem& S, const SweepArgs& A, int
     const int s = k / kSwPts, q = k - s * kSwPts;
     const double* b = g_qpts + 3 * (kSwOff + q);
     const double* P = S.row[s].P;
-    S.row[s].pts[3 * q] = xquad(b[0], b[1], b[2], P[0], P[3], P[6]);
-    S.row[s].pts[3 * q + 1] = xquad(b[0], b[1], b[2], P[1], P[4], P[7]);
-    S.row[s].pts[3 * q + 2] = xquad(b[0], b[1], b[2], P[2], P[5], P[8]);
+    S.row[s].pts[4 * q] = xquad(b[0], b[1], b[2], P[0], P[3], P[6]);
+    S.row[s].pts[4 * q + 1] = xquad(b[0], b[1], b[2], P[1], P[4], P[7]);
+    S.row[s].pts[4 * q + 2] = xquad(b[0], b[1], b[2], P[2], P[5], P[8]);
+    S.row[s].pts[4 * q + 3] = g_qwts[kSwOff + q];
   }
   __syncthreads();
 }
@@ -213,7 +222,7 @@ __device__ __forceinline__ void stage_rows(SweepSmem& S, const SweepArgs& A, int
 // MODE 0: T(i,j) with the order rule of tw_compute_Lmatblock/-Hole (= tw_compute_LmatDirect's), stored
 // MODE 1: tw_compute_Lmat_MF's classes, consumed at once: F_j[q] += T(i,j) J_i[q]
 template <int MODE>
-__global__ void __launch_bounds__(kSwT) pair_sweep_kernel(const SweepArgs A) {
+__global__ void __launch_bounds__(kSwT, 2) pair_sweep_kernel(const SweepArgs A) {
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   SweepSmem& S = *reinterpret_cast<SweepSmem*>(sweep_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -273,7 +282,22 @@ __global__ void __launch_bounds__(kSwT) pair_sweep_kernel(const SweepArgs A) {
         }
       }
       const unsigned m = __ballot_sync(0xffffffffu, near);
-      if (near) S.list[warp][nlist + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(s << 5 | lane);
+      if (m == 0) continue;
+      const int rank = __popc(m & ((1u << lane) - 1u));
+      if (MODE == 0 && A.near_list) {  // hand the pair to the near kernel (one atomic per warp)
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(A.near_count, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (near && base + rank < A.near_cap) {
+          A.near_list[base + rank] = make_int2(r0 + s, jx);
+          near = false;
+        }
+        const unsigned m2 = __ballot_sync(0xffffffffu, near);  // what did not fit is evaluated here
+        if (near) S.list[warp][nlist + __popc(m2 & ((1u << lane) - 1u))] = (uint16_t)(s << 5 | lane);
+        nlist += __popc(m2);
+        continue;
+      }
+      if (near) S.list[warp][nlist + rank] = (uint16_t)(s << 5 | lane);
       nlist += __popc(m);
     }
     __syncwarp();
@@ -289,7 +313,7 @@ __global__ void __launch_bounds__(kSwT) pair_sweep_kernel(const SweepArgs A) {
         const double aj = __shfl_sync(0xffffffffu, area_j, owner);
         o = iquad_exact(R.P, Po, 3, 3, fmax(R.area, aj) * 2.0);
       }
-      const double T = near_warp(S.row[s], Po, o, lane) * __shfl_sync(0xffffffffu, area_j, owner);
+      const double T = near_warp(S.row[s].P, S.row[s].nh, Po, o, lane) * __shfl_sync(0xffffffffu, area_j, owner);
       if (lane == owner) {
         nnear++;
         if (MODE == 0) A.T[(size_t)(r0 - A.row0 + s) * A.ldT + jx] = T;
@@ -314,6 +338,78 @@ __global__ void __launch_bounds__(kSwT) pair_sweep_kernel(const SweepArgs A) {
       atomicAdd(A.counts + 1, (unsigned long long)nclose);
       atomicAdd(A.counts + 2, (unsigned long long)nnear);
     }
+  }
+}
+
+// near pairs of a stored-T sweep, one warp per pair over the whole device (thin_wall.F90:1061-1068)
+__global__ void __launch_bounds__(256) near_pairs_kernel(const SweepArgs A) {
+  const int lane = threadIdx.x & 31;
+  const unsigned n = min(*A.near_count, A.near_cap);
+  for (unsigned e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n; e += gridDim.x * 8) {
+    const int2 ent = A.near_list[e];
+    const int ci = A.row_cells ? A.row_cells[ent.x] : ent.x, cj = A.col_items ? A.col_items[ent.y] : ent.y;
+    double Pi[9], Pj[9], nh[3];
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+      Pi[q] = A.Pr[9 * (size_t)ci + q];
+      Pj[q] = A.Pc[9 * (size_t)cj + q];
+    }
+    tri_normal(Pi, nh);
+    const double ai = A.Ar[ci], aj = A.Ac[cj];
+    const int o = iquad_exact(Pi, Pj, 3, 3, fmax(ai, aj) * 2.0);
+    const double T = near_warp(Pi, nh, Pj, o, lane) * aj;
+    if (lane == 0) A.T[(size_t)(ent.x - A.row0) * A.ldT + ent.y] = T;
+  }
+}
+
+// central differences of the analytic potential around a vertex (thin_wall.F90:2049-2075), D = grad phi
+__device__ __forceinline__ void bops_near(const double* P, const double* nh, const double* nrm, const double* X, bool nb, double* D) {
+  const double B_dx = 1.e-6;
+  double pt[3] = {X[0], X[1], X[2]}, diff[3] = {0.0, 0.0, 0.0};
+  if (nb)
+    for (int d = 0; d < 3; d++) pt[d] = xsub(pt[d], xmul(xmul(nrm[d], 10.0), B_dx));
+  for (int ik = 1; ik <= 2; ik++) {
+    if (ik == 2)
+      for (int d = 0; d < 3; d++) pt[d] = xadd(pt[d], xmul(xmul(nrm[d], 20.0), B_dx));
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) {
+      pt[jj] = xadd(pt[jj], B_dx);
+      double tmp = phipot(P, nh, pt[0], pt[1], pt[2]);
+      diff[jj] = xadd(diff[jj], __ddiv_rn(tmp, 2.0 * B_dx));
+      pt[jj] = xsub(pt[jj], 2.0 * B_dx);
+      tmp = phipot(P, nh, pt[0], pt[1], pt[2]);
+      diff[jj] = xsub(diff[jj], __ddiv_rn(tmp, 2.0 * B_dx));
+      pt[jj] = xadd(pt[jj], B_dx);
+    }
+    if (!nb) break;
+  }
+  if (nb)
+    for (int d = 0; d < 3; d++) diff[d] = diff[d] / 2.0;
+  D[0] = diff[0];
+  D[1] = diff[1];
+  D[2] = diff[2];
+}
+// near (cell, vertex) pairs of a B sweep, one thread per pair over the whole device; ent.y bit 30 = on-surface vertex
+__global__ void __launch_bounds__(128) bops_near_kernel(const SweepArgs A) {
+  const unsigned n = min(*A.near_count, A.near_cap);
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int2 ent = A.near_list[e];
+    const int jy = ent.y & 0x3fffffff;
+    const bool nb = (ent.y >> 30) & 1;
+    const int ci = A.row_cells ? A.row_cells[ent.x] : ent.x, p = A.col_items ? A.col_items[jy] : jy;
+    double Pi[9], nh[3], nrm[3], X[3], D[3];
+#pragma unroll
+    for (int q = 0; q < 9; q++) Pi[q] = A.Pr[9 * (size_t)ci + q];
+    tri_normal(Pi, nh);
+    for (int d = 0; d < 3; d++) {
+      nrm[d] = A.Nr[3 * (size_t)ci + d];
+      X[d] = A.rc[3 * (size_t)p + d];
+    }
+    bops_near(Pi, nh, nrm, X, nb, D);
+    double* o = A.T + ((size_t)(ent.x - A.row0) * A.ldT + jy) * 3;
+    o[0] = D[0];
+    o[1] = D[1];
+    o[2] = D[2];
   }
 }
 

@@ -6,7 +6,7 @@ the largest entry of the block (|x| > 1e-6 max), 1e-10 of the largest entry else
 import os
 import numpy as np
 import pytest
-from helpers import MU0, load_mesh, split_nodesets, ref_circle, ref_floop
+from helpers import MU0, load_mesh, mutual_abs_sum, split_nodesets, ref_circle, ref_floop
 from oracle import tw_oracle as tw
 
 pytestmark = pytest.mark.gpu
@@ -72,14 +72,19 @@ def test_lmatblock_vs_oracle(env, name, js):
     assert np.array_equal(T.compute_Lmatblock(rows, cols), Bg)
 
 
-def test_lmatblock_two_models_and_chunked_rows(env):
-    """row and column blocks from different models (tw_compute_Lmatblock(row_obj, col_obj, ...)); a row block large
-    enough to be swept in several row-list chunks is exercised on the ports example mesh."""
+def test_lmatblock_two_models(env):
+    """row and column blocks from different models (tw_compute_Lmatblock(row_obj, col_obj, ...))"""
     O1, T1 = make(env, 'plate')
     O2, T2 = make(env, 'cyl', 2)
-    rows = np.arange(0, O1.np_, 3, dtype=np.int32)
-    cols = np.arange(0, O2.np_, 2, dtype=np.int32)
-    close(T1.compute_Lmatblock(rows, cols, col_model=T2), O1.lmat_block(rows, cols, other=O2))
+    rows = np.nonzero(O1.pmap > 0)[0][::3].astype(np.int32)
+    cols = np.nonzero(O2.pmap > 0)[0][::2].astype(np.int32)
+    Bg, Bo = T1.compute_Lmatblock(rows, cols, col_model=T2), O1.lmat_block(rows, cols, other=O2)
+    # entries of a mutual matrix of unrelated meshes are sums with cancellation: judged against the magnitude of their
+    # terms as in test_gpu_coupling.py::test_cross_coupling (the reference's own atomics move them by ~eps * A)
+    A = mutual_abs_sum(O1, O2)[np.ix_(O1.pmap[rows] - 1, O2.pmap[cols] - 1)]
+    assert (np.abs(Bg - Bo) <= 1e-10 * np.abs(Bo) + 64 * np.finfo(float).eps * A).all()
+    well = np.abs(Bo) > 1e-4 * A
+    assert (np.abs(Bg - Bo)[well] <= 1e-10 * np.abs(Bo)[well]).all()
 
 
 def test_lmatblock_strip_ports_scale(env):
@@ -110,12 +115,16 @@ def test_bops_block_vs_oracle(env, name, js):
     rows = np.sort(rng.permutation(O.np_)[:120]).astype(np.int32)
     cols = rng.permutation(O.np_)[:300].astype(np.int32)  # includes vertices of the row block's own cells (on-surface)
     Ball = T.compute_Bops_block(rows, cols)  # all three components in one sweep
+    Bos = [O.bops_block(rows, cols, d) for d in range(3)]
+    sc = max(np.abs(Bo).max() for Bo in Bos)  # one scale for the vector (the flat plate has pure rounding noise in x, y)
     for d in range(3):
-        Bo = O.bops_block(rows, cols, d)
+        Bo = Bos[d]
         Bd = T.compute_Bops_block(rows, cols, direction=d)
-        # near entries are central differences of the analytic potential with h = 1e-6: rounding in phi (1e-16 relative to
-        # phi ~ area/r) is amplified by 1/h, so they carry ~1e-9 of the largest entry on both sides
-        close(Bd, Bo, tol=2e-8, small=1e-3)
+        # same criterion as test_gpu_coupling.py::test_bmat: near entries are central differences of the analytic
+        # potential with h = 1e-6, which amplify last-digit differences of log/atan2 by ~1e6 (SURVEY hard part 8)
+        assert np.abs(Bd - Bo).max() / sc < 1e-8
+        far = np.abs(Bo) < 1e-2 * sc
+        assert np.abs(Bd - Bo)[far].max() / sc < 1e-9
         assert np.array_equal(Ball[d], Bd)
 
 
@@ -128,15 +137,18 @@ def test_cross_eval_vs_oracle(env):
     bo = O1.cross_eval(O2, a, co)
     bg = T1.cross_eval(T2, a, counts=cg)
     assert np.array_equal(co, cg), (co, cg)  # identical quadrature decisions for every cell pair
-    close(bg, bo)
-    close(T1.cross_eval(T2, a[:1]), bo[:1])  # through the reference-named entry point
+    # b = M a with random signs in a: entries are sums with cancellation, judged against the largest entry of each field
+    # (1e-10) and against themselves at 1e-9
+    vclose = lambda x, y: (close(x, y, tol=1e-10, small=10.0), close(x, y, tol=1e-9, small=1e-6))
+    vclose(bg, bo)
+    vclose(T1.cross_eval(T2, a[:1]), bo[:1])  # through the reference-named entry point
     # a model against itself: coincident cells and shared vertices (all three classes), holes on both sides
     O3, T3 = make(env, 'torus')
     a3 = rng.standard_normal((2, O3.nelems))
     bo3 = O3.cross_eval(O3, a3, co)
     bg3 = T3.cross_eval(T3, a3, counts=cg)
     assert np.array_equal(co, cg) and (co > 0).all(), (co, cg)
-    close(bg3, bo3)
+    vclose(bg3, bo3)
     with pytest.raises(IndexError):
         T1.cross_eval(T2, a[:, :-1])
 
