@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -128,6 +129,50 @@ std::string replan(Model& m, int nshards) {
   if (m.plan && m.plan->nshards_hint == std::max(1, nshards)) return "";
   m.plan.reset();
   return ensure_plan(m, nshards);
+}
+
+// Banded plan of the streamed single-device build (lmat_stream_host): the vertex DOFs are cut into B equal ranges of
+// reference ids, every range gets patches of its own.  Band b evaluates its rows against itself and all later bands; with
+// uniform cost per entry a band holding the rows [F0,F1) (fractions of N) carries the share (1-F0)^2 - (1-F1)^2 of the work
+// AND of the bytes that can leave the device when it is done (its rows from its own columns on, plus its columns of all
+// later rows), so the copies keep pace with the evaluation; what stays exposed is the copy of the last band, 1/B^2 of the
+// matrix.  B <= 10, and few enough bands that a range of reference ids (on a structured mesh: a strip of grid lines) is
+// not narrower than a patch: sqrt(nv / (1.1 P)).  Empty result: no streaming (small or V-coil models).
+static std::vector<int> stream_ref_cuts(const Model& m, int P) {
+  const int nv = m.np_active;
+  int B = 0;
+  if (const char* e = std::getenv("THINCURR_B200_STREAM_BANDS")) B = std::atoi(e);
+  else if (m.nelems >= 12000 && m.n_vcoils == 0) B = std::min(10, (int)std::sqrt(nv / (1.125 * std::max(P, 1))));
+  if (B < 2 || nv < 64 * B || m.n_vcoils > 0) return {};
+  B = std::min(B, 32);
+  std::vector<int> cuts{0};
+  for (int b = 1; b < B; b++) {
+    const int c = std::min((int)std::lround((double)nv * b / B / 32.0) * 32, nv - 32);
+    if (c > cuts.back()) cuts.push_back(c);
+  }
+  cuts.push_back(nv);
+  return cuts.size() >= 3 ? cuts : std::vector<int>{};
+}
+// (re)plan for the streamed build; false: this model is built the ordinary way
+static bool ensure_banded_plan(Model& m, std::string& err) {
+  err.clear();
+  int P = 0;
+  if (const char* e = std::getenv("THINCURR_B200_PATCH")) P = std::atoi(e);
+  if (m.plan && !m.plan->band_ref_ptr.empty() && (P <= 0 || m.plan->patch_size == P)) return true;
+  if (P <= 0) P = auto_patch_size(m.np_active, 4);  // (100k-vertex vessel: 600 -> 1.98 s, 850 -> 1.93 s, 1200 -> 2.17 s end to end)
+  const std::vector<int> cuts = stream_ref_cuts(m, P);
+  if (cuts.empty()) return false;
+  auto pl = std::make_shared<Plan>();
+  err = build_patches(m, P, pl->ps, 1, &cuts, &pl->band_patch_ptr);
+  if (!err.empty()) return false;
+  pl->band_ref_ptr = cuts;
+  pl->band_ref_ptr.back() = m.np_active + m.nholes;  // the hole DOFs (reference ids after the vertices) and their patches
+  pl->band_patch_ptr.back() = pl->ps.npatch;         // belong to the last band
+  pl->nshards_hint = 1;
+  pl->patch_size = P;
+  pl->serial = ++g_plan_serial;
+  m.plan = pl;
+  return true;
 }
 
 std::string ensure_device(Model& m, int device, std::shared_ptr<DeviceState>& out) {
@@ -534,6 +579,157 @@ static std::string scratch_rows(DeviceState& ds, size_t bytes, double** out) {
   return "";
 }
 
+// Streamed single-device build into a page-locked host matrix (banded plan, see stream_ref_cuts).  The device holds the
+// matrix in the reference layout and ONE launch of the tile kernel works through the tiles band by band (rows of a band
+// against this and all later bands).  As soon as the tiles of a band are done the kernel's own CTAs run its mirror pass
+// between two tiles and raise the band's flag in mapped host memory; this thread then hands the band's L-shaped part of
+// the matrix -- its rows from its first column on, and its columns of all later rows -- to the copy engine as two
+// strided copies, while the later bands are evaluated.  Every entry crosses the link exactly once and leaves as soon as
+// the band that evaluated it (or its transposed twin) is done, so the link works in step with the evaluation from the
+// first band on.  (A build whose rows may only leave complete -- all columns -- cannot start copying before its most
+// expensive rows are finished and ends link-bound; separate launches per band end on their longest tile each.)
+static std::string lmat_stream_host(Model& m, double* dst, bool trace) {
+  const auto tr0 = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+  const Plan& pl = *m.plan;
+  const PatchSet& ps = pl.ps;
+  const size_t N = (size_t)m.nelems;
+  const int nb = (int)pl.band_ref_ptr.size() - 1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return "No CUDA device available (the B200 backend has no CPU fallback)";
+  std::shared_ptr<DeviceState> ds;
+  std::string err = ensure_device(m, dev, ds);
+  if (!err.empty()) return err;
+  if (trace) std::fprintf(stderr, "[lmat_stream_host] ensure_device at %.1f ms\n", since(tr0));
+  err = ds->ps.upload_from(ps);  // the call's inputs: host model -> device, every call
+  if (trace) std::fprintf(stderr, "[lmat_stream_host] upload done at %.1f ms\n", since(tr0));
+  if (!err.empty()) return err;
+  ds->plan_serial = pl.serial;
+  double* d = nullptr;
+  err = scratch_rows(*ds, N * N * 8, &d);
+  if (trace) std::fprintf(stderr, "[lmat_stream_host] scratch done at %.1f ms\n", since(tr0));
+  if (!err.empty()) return err;
+  cudaStream_t s = nullptr, cs = nullptr;
+  int* d_ref_patch = nullptr;
+  int* flags = nullptr;
+  auto ck = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && err.empty()) err = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaSuccess;
+  };
+  ck(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+  ck(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "cudaStreamCreate");
+  {  // band flags: a small mapped page-locked buffer kept for the life of the process (allocating and freeing page-locked
+     // memory synchronises the device)
+    static int* g_flags = nullptr;
+    static std::mutex g_flags_mu;
+    std::lock_guard<std::mutex> lk(g_flags_mu);
+    if (!g_flags && !ck(cudaHostAlloc((void**)&g_flags, 64 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc")) g_flags = nullptr;
+    flags = g_flags;
+  }
+  if (nb > 64) err = "Internal error: too many bands";
+  if (trace) std::fprintf(stderr, "[lmat_stream_host] streams+flags done at %.1f ms\n", since(tr0));
+  std::vector<int> ref_patch(N, 0), row_out(ps.ndof, -1);
+  for (int p = 0; p < ps.npatch; p++)
+    for (int i = ps.patch_dof_ptr[p]; i < ps.patch_dof_ptr[p + 1]; i++) ref_patch[ps.dof_orig[i]] = p;
+  for (int i = 0; i < ps.ndof; i++) row_out[i] = ps.dof_orig[i];  // output row = reference id
+  StreamBands sb;
+  std::vector<Tile> tiles;
+  std::vector<int> tile_band, band_ntiles(nb, 0);
+  {
+    // Queue order: latest start time first.  Band b should be complete when the work of the bands up to b is done
+    // (deadline = that work spread over the SMs, in units of the tile cost model); a tile must start its own cost before
+    // the deadline of its band, so the long tiles of a band (its near-field diagonal blocks) start ahead of the cheap tiles
+    // of the band before, and the queue ends on cheap tiles.
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    std::vector<Tile> bt;
+    std::vector<double> key;
+    double done = 0.0;
+    for (int b = 0; b < nb; b++) {
+      build_self_tiles(ps, pl.band_patch_ptr[b], pl.band_patch_ptr[b + 1], bt, false, b > 0 ? 0 : -1);
+      double w = 0.0;
+      for (const Tile& t : bt) w += t.cost;
+      done += w / nsm;
+      for (const Tile& t : bt) {
+        tiles.push_back(t);
+        tile_band.push_back(b);
+        key.push_back(done - t.cost);
+      }
+      band_ntiles[b] = (int)bt.size();
+    }
+    std::vector<int> order(tiles.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return key[a] < key[c]; });
+    std::vector<Tile> t2(tiles.size());
+    std::vector<int> b2(tiles.size());
+    for (size_t i = 0; i < order.size(); i++) {
+      t2[i] = tiles[order[i]];
+      b2[i] = tile_band[order[i]];
+    }
+    tiles.swap(t2);
+    tile_band.swap(b2);
+  }
+  sb.nbands = nb;
+  sb.N = (int)N;
+  sb.flags = flags;
+  if (trace) std::fprintf(stderr, "[lmat_stream_host] tiles built at %.1f ms\n", since(tr0));
+  if (err.empty()) {
+    std::memset(flags, 0, (size_t)nb * sizeof(int));
+    std::vector<int> hb(2 * nb + 1);  // band arrays of the kernel: tiles per band [nb], reference ids [nb+1], then 3 nb counters
+    for (int b = 0; b < nb; b++) hb[b] = band_ntiles[b];
+    for (int b = 0; b <= nb; b++) hb[nb + b] = pl.band_ref_ptr[b];
+    const size_t nt = tiles.size();
+    ck(cudaMallocAsync((void**)&d_ref_patch, (N + nt + 5 * (size_t)nb + 1) * sizeof(int), s), "cudaMallocAsync");
+    ck(cudaMemcpyAsync(d_ref_patch, ref_patch.data(), N * sizeof(int), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync");
+    ck(cudaMemcpyAsync(d_ref_patch + N, tile_band.data(), nt * sizeof(int), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync");
+    ck(cudaMemcpyAsync(d_ref_patch + N + nt, hb.data(), hb.size() * sizeof(int), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync");
+    ck(cudaMemsetAsync(d_ref_patch + N + nt + 2 * nb + 1, 0, (size_t)3 * nb * sizeof(int), s), "cudaMemsetAsync");
+    ck(cudaStreamSynchronize(s), "cudaStreamSynchronize");  // (host vectors are locals; nothing large is queued yet)
+  if (trace) std::fprintf(stderr, "[lmat_stream_host] small uploads done at %.1f ms\n", since(tr0));
+    ck(cudaMemsetAsync(d, 0, N * N * 8, s), "cudaMemsetAsync");
+    sb.d_ref_patch = d_ref_patch;
+    sb.d_tile_band = d_ref_patch + N;
+    sb.d_bands = d_ref_patch + N + nt;
+  }
+  if (err.empty()) err = gpu_lmat_tiles(ds->ps, ds->ps, tiles, row_out, true, d, (long long)N, s, nullptr, nullptr, false, &sb);
+  if (trace) std::fprintf(stderr, "[lmat_stream_host] %d bands, %zu tiles, launched at %.1f ms\n", nb, tiles.size(), since(tr0));
+  // hand the finished bands to the copy engine
+  volatile int* vf = flags;
+  for (int b = 0; b < nb && err.empty(); b++) {
+    while (!vf[b]) {
+      const cudaError_t q = cudaStreamQuery(s);
+      if (q == cudaErrorNotReady) {
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+        continue;
+      }
+      if (q != cudaSuccess) ck(q, "Kernel execution failed");
+      else if (!vf[b]) err = "Internal error: the streamed build ended without finishing its bands";
+      break;
+    }
+    if (!err.empty()) break;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const int R0 = pl.band_ref_ptr[b], R1 = pl.band_ref_ptr[b + 1];
+    const size_t o0 = (size_t)R0 * N + R0, o1 = (size_t)R1 * N + R0;
+    ck(cudaMemcpy2DAsync(dst + o0, N * 8, d + o0, N * 8, (N - R0) * 8, (size_t)(R1 - R0), cudaMemcpyDeviceToHost, cs), "Device->host copy");
+    if ((size_t)R1 < N)
+      ck(cudaMemcpy2DAsync(dst + o1, N * 8, d + o1, N * 8, (size_t)(R1 - R0) * 8, N - R1, cudaMemcpyDeviceToHost, cs), "Device->host copy");
+    if (trace) std::fprintf(stderr, "[lmat_stream_host] band %d (rows [%d,%d), %d tiles) final at %.1f ms\n", b, R0, R1, band_ntiles[b], since(tr0));
+  }
+  if (s) {
+    if (d_ref_patch) cudaFreeAsync(d_ref_patch, s);
+    cudaError_t ce = cudaStreamSynchronize(s);
+    if (trace) std::fprintf(stderr, "[lmat_stream_host] build stream done at %.1f ms\n", since(tr0));
+    if (ce == cudaSuccess && cs) ce = cudaStreamSynchronize(cs);
+    if (trace) std::fprintf(stderr, "[lmat_stream_host] copies done at %.1f ms\n", since(tr0));
+    if (ce != cudaSuccess && err.empty()) err = std::string("Kernel execution failed: ") + cudaGetErrorString(ce);
+  }
+  if (s) cudaStreamDestroy(s);
+  if (cs) cudaStreamDestroy(cs);
+  cudaGetLastError();
+  if (trace) std::fprintf(stderr, "[lmat_stream_host] returning at %.1f ms\n", since(tr0));
+  return err;
+}
+
 // full self-inductance matrix into host memory dst[nelems][nelems] (reference layout), rows sharded
 // over the usable devices, each shard copied straight to its place.  One device: the matrix is built in row bands and
 // the rows of a finished band go to the host (copy engine) while the next band is evaluated.  Several devices that can
@@ -548,9 +744,20 @@ static std::string lmat_full_host(Model& m, double* dst) {
   DeviceGuard guard;
   std::vector<int> devs_ids = build_devices();
   if (devs_ids.empty()) return "No CUDA device available (the B200 backend has no CPU fallback)";
-  // one device: the rows leave band by band and every band needs enough tiles for all SMs: patches as for 8 shards
-  std::string err = replan(m, devs_ids.size() == 1 ? 8 : (int)devs_ids.size());
-  if (!err.empty()) return err;
+  std::string err;
+  if (devs_ids.size() == 1 && m.n_vcoils == 0 && ensure_banded_plan(m, err)) {
+    // one device, large model: banded plan; a page-locked destination is served by the streamed build, a pageable one by
+    // the row bands below on the same patches (same bits)
+    if (is_pinned(dst)) {
+      if (cudaSetDevice(devs_ids[0]) != cudaSuccess) return "cudaSetDevice failed";
+      return lmat_stream_host(m, dst, trace);
+    }
+  } else {
+    if (!err.empty()) return err;
+    // one device: the rows leave band by band and every band needs enough tiles for all SMs: patches as for 8 shards
+    err = replan(m, devs_ids.size() == 1 ? 8 : (int)devs_ids.size());
+    if (!err.empty()) return err;
+  }
   const PatchSet& ps = m.plan->ps;
   int ndev = std::min((int)devs_ids.size(), std::max(1, ps.npatch));
   devs_ids.resize(ndev);

@@ -21,6 +21,8 @@ struct DevicePatchSet {
   int *patch_chunk_ptr = nullptr, *dof_orig = nullptr;
   int* dof_patch = nullptr;  // [ndof] patch of every internal DOF
   size_t bytes = 0;  // host->device bytes of the last upload
+  size_t cap[11] = {0};  // allocated bytes per array: a re-upload of a plan of the same size only copies (the reference-facing
+                         // builds upload the model on every call; a dozen cudaFree/cudaMalloc pairs cost more than the copies)
   std::string upload_from(const PatchSet& ps);
   void release();
   ~DevicePatchSet() { release(); }
@@ -46,9 +48,23 @@ long long launch_count();
 // of the owned diagonal block afterwards (self builds whose tiles defer them, Tile.flags bit 3).
 // Run the tile kernel: out[row_out[internal row]][ld] += (1/4pi) sum ... ; out must be zeroed.
 // h_stats (optional, 8 x u64) forces a stream sync: far pairs, near T evals, 1/r evals, phipot evals.
+// sb (streamed single-device build, tw_capi.cu): every tile belongs to a band of rows, the output is the whole matrix in the
+// reference layout (row_out = reference id); the kernel itself runs the mirror pass of every band as soon as the band's
+// tiles are done and then sets flags[b] in mapped host memory: the band's rows from its first column on and its columns
+// of all later rows are final and may leave the device while the later bands are evaluated.
+struct StreamBands {
+  int nbands;
+  const int* d_tile_band;     // device, [ntiles]: band of every tile (the queue order is the caller's)
+  const int* d_ref_patch;     // device, [N]: patch of a reference DOF id
+  int* d_bands;               // device, [5 nbands + 1]: tiles per band, reference ids of the bands' rows (nbands + 1), then
+                              // 3 nbands zeroed counters
+  int N;
+  int* flags;                 // mapped page-locked host memory, [nbands], zeroed by the caller
+};
 std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, const std::vector<Tile>& tiles,
                            const std::vector<int>& row_out, bool self, double* d_out, long long ld, cudaStream_t stream,
-                           unsigned long long* h_stats, const int* d_col_map = nullptr, bool symmetrize = true);
+                           unsigned long long* h_stats, const int* d_col_map = nullptr, bool symmetrize = true,
+                           const StreamBands* sb = nullptr);
 
 // dst[i-i0][orig(j)] = src[j-j0][orig(i)] for internal DOFs i in [i0,i1), j in [j0,j1): the transposed block of another
 // shard or band (src may be peer memory of another device); A = patch set mirror on the device that runs the kernel.

@@ -89,7 +89,17 @@ struct LmatArgs {
   int debug_skip;                     // test build only: bit0 skip near-field evaluation, bit1 skip far-field evaluation,
                                       // bit2 skip the contraction
   unsigned long long* stats;          // [0] far pairs, [1] near T evaluations, [2] 1/r evaluations, [3] phipot evals
+  // streamed build (one launch, matrix in the reference layout, tiles ordered band by band; nbands = 0 otherwise):
+  int nbands;
+  const int* tile_band;               // [ntiles] band of a tile (the queue order is free: latest start time first)
+  const int* band_ntiles;             // [nbands] tiles per band
+  const int* band_ref;                // [nbands+1] reference DOF ids of the band's rows
+  const int* ref_patch;               // [N] patch of a reference DOF id
+  int N;
+  int* band_state;                    // [3][nbands]: tiles finished, next mirror task, mirror tasks finished
+  volatile int* host_flags;           // [nbands] (mapped host memory) set when the band's part of the matrix is final
 };
+constexpr int kMirKC = 256;           // 32-column blocks per mirror task
 
 // one staged chunk (row or column side): SoA geometry record + index record + output rows, each
 // filled by one bulk async copy
@@ -129,9 +139,12 @@ struct Smem {
   float vfI[9 * CI], vfJ[9 * kCH];    // vertices relative to the row chunk's centre, FP32 (order screening)
   float flI[CI], flJ[kCH];            // 2 * area
   float4 cenI[CI], cenJ[kCH];         // centroid (same frame) and the radius covering the vertices
-  int tile_id;
+  int item[5];                        // [0] tile (-1: exit, -2: mirror task [1] of band [2]), [3], [4]: see fetch_banded
 };
 static_assert(sizeof(Smem) <= 232448, "shared memory of one CTA");
+static_assert(offsetof(Smem, tabI) == offsetof(Smem, T) + sizeof(double) * CI * TS && offsetof(Smem, u) == offsetof(Smem, tabI) + sizeof(double2) * kTabPts * 2 * CI &&
+                  sizeof(double) * CI * TS + 2 * sizeof(double2) * kTabPts * 2 * CI >= NW * 32 * 33 * sizeof(double),
+              "T, tabI and tabJ form the contiguous scratch of the mirror tasks (one 32 x 33 block per warp)");
 template <int N> struct ShowSize;
 #ifdef TW_SHOW_SMEM
 ShowSize<sizeof(Smem)> show_smem_size;
@@ -1101,6 +1114,95 @@ __device__ __forceinline__ void drain_pass(Smem& S, const LmatArgs& A, const Chu
   }
 }
 
+// ---- streamed build: mirror tasks and band bookkeeping ---------------------------------------------------------------
+// The matrix lies in the reference layout (out[row DOF][column DOF], both reference ids); a band owns the rows [R0,R1) and
+// its tiles filled, of every pair {i,k} with i in the band and k >= R0, the entry [i][k] iff patch(i) < patch(k), or the
+// patches are equal and i <= k -- else [k][i] (then k lies in the band too).  The other entry of the pair is its copy
+// (thin_wall.F90:1146-1151): afterwards the rows of the band are final from column R0 on, and so are the columns [R0,R1)
+// of all later rows -- the L-shaped part of the matrix that leaves for the host while the later bands are evaluated.
+// One 32 x 32 block of that pass, handled by one warp through its own 32 x 33 scratch (coalesced both ways): rows
+// i = ib.., columns k = kb..
+__device__ __forceinline__ void mirror_block(double* __restrict__ buf, int R1, int N, int ib, int kb, bool diag, const int* __restrict__ ref_patch,  // @region mirror_task
+                                             double* __restrict__ out, long long ld, int lane) {
+  const int pi = ib + lane < R1 ? ref_patch[ib + lane] : -1, pk = kb + lane < N ? ref_patch[kb + lane] : -1;
+#pragma unroll 8
+  for (int ii = 0; ii < 32; ii++)  // A[ii][kk] = out[i][k], lanes over k
+    if (ib + ii < R1 && kb + lane < N) buf[ii * 33 + lane] = __ldcg(out + (long long)(ib + ii) * ld + kb + lane);
+  __syncwarp();
+#pragma unroll 8
+  for (int kk = 0; kk < 32; kk++) {  // out[k][i] = out[i][k] where [i][k] was evaluated, lanes over i
+    const int k = kb + kk, i = ib + lane, pkk = __shfl_sync(0xffffffffu, pk, kk);
+    if (k < N && i < R1 && i != k && (pi < pkk || (pi == pkk && i < k))) out[(long long)k * ld + i] = buf[lane * 33 + kk];
+  }
+  if (!diag && kb < R1) {  // rows k of the band: entries they hold may belong to the rows i
+    __syncwarp();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; kk++)  // Bt[kk][ii] = out[k][i], lanes over i
+      if (kb + kk < R1 && ib + lane < R1) buf[kk * 33 + lane] = __ldcg(out + (long long)(kb + kk) * ld + ib + lane);
+    __syncwarp();
+#pragma unroll 8
+    for (int ii = 0; ii < 32; ii++) {  // out[i][k] = out[k][i] where [k][i] was evaluated, lanes over k
+      const int i = ib + ii, k = kb + lane, pii = __shfl_sync(0xffffffffu, pi, ii);
+      if (i < R1 && k < R1 && (pk < pii || (pk == pii && k < i))) out[(long long)i * ld + k] = buf[lane * 33 + ii];
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ int mirror_task_count(int R0, int R1, int N) {
+  return ((R1 - R0 + 31) / 32) * (((N - R0 + 31) / 32 + kMirKC - 1) / kMirKC);
+}
+// mirror task `task` of the band with rows [R0,R1): 32 rows of the band against kMirKC column blocks, one block per warp at
+// a time (scalar arguments: a reference to the kernel's parameter block would force a local copy of it)
+__device__ __noinline__ void mirror_task(double* __restrict__ scratch, int R0, int R1, int N, const int* __restrict__ ref_patch, double* __restrict__ out,
+                                         long long ld, int task, int tid) {
+  const int nbk = (N - R0 + 31) / 32, nkc = (nbk + kMirKC - 1) / kMirKC;
+  const int bx = task / nkc, kc = task - bx * nkc;
+  double* buf = scratch + (tid >> 5) * (32 * 33);
+  const int by1 = min(nbk, (kc + 1) * kMirKC);
+  for (int by = max(bx, kc * kMirKC) + (tid >> 5); by < by1; by += NW)
+    mirror_block(buf, R1, N, R0 + 32 * bx, R0 + 32 * by, by == bx, ref_patch, out, ld, tid & 31);
+}
+// next work item of a streamed build (one thread): a mirror task of a band whose tiles are all done, else the next tile;
+// when the tiles are used up, the remaining bands are waited for (their tiles are running on other CTAs).
+// item[0]: tile, -1: exit, -2: mirror task item[1] of band item[2]; item[3]: cursor over the bands, item[4]: band of the
+// tile this CTA just finished (or -1)
+__device__ __noinline__ void fetch_banded(int* __restrict__ item, int* tile_counter, int ntiles, int nbands, const int* __restrict__ tile_band,
+                                          const int* __restrict__ band_ntiles, const int* __restrict__ band_ref, int N, int* band_state) {
+  int* tiles_done = band_state;
+  int* mir_next = band_state + nbands;
+  if (item[4] >= 0) atomicAdd(&tiles_done[item[4]], 1);  // (all threads fenced their stores before the barrier)
+  item[4] = -1;
+  bool tiles_left = true;
+  for (;;) {
+    for (int b = item[3]; b < nbands; b++) {
+      if (*(volatile int*)&tiles_done[b] < band_ntiles[b]) break;  // bands hand out their mirror tasks in order
+      const int k = atomicAdd(&mir_next[b], 1);
+      if (k < mirror_task_count(band_ref[b], band_ref[b + 1], N)) {
+        __threadfence();  // the tile stores of the other CTAs (released by their fences) before this task's loads
+        item[0] = -2;
+        item[1] = k;
+        item[2] = b;
+        return;
+      }
+      item[3] = b + 1;
+    }
+    if (item[3] >= nbands) {
+      item[0] = -1;
+      return;
+    }
+    if (tiles_left) {
+      const int t = atomicAdd(tile_counter, 1);
+      if (t < ntiles) {
+        item[4] = tile_band[t];
+        item[0] = t;
+        return;
+      }
+      tiles_left = false;
+    }
+    __nanosleep(2000);
+  }
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {  // @region kernel_head
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1121,12 +1223,35 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {  /
     A.stats[6] = t0;
   }
 
+  if (tid == 0) {
+    S.item[3] = 0;
+    S.item[4] = -1;
+  }
   for (;;) {
+    if (A.nbands) __threadfence();  // streamed build: this tile's stores before its band's count
     __syncthreads();  // the previous tile is drained (chunk slots, T and the scratch are free)
-    if (tid == 0) S.tile_id = atomicAdd(A.tile_counter, 1);
+    if (tid == 0) {
+      if (A.nbands) fetch_banded(S.item, A.tile_counter, A.ntiles, A.nbands, A.tile_band, A.band_ntiles, A.band_ref, A.N, A.band_state);
+      else S.item[0] = atomicAdd(A.tile_counter, 1);
+    }
     __syncthreads();
-    const int t = S.tile_id;
-    if (t >= A.ntiles) break;
+    const int t = S.item[0];
+    if (t >= A.ntiles || t == -1) break;
+    if (t == -2) {  // mirror task of a finished band
+      const int b = S.item[2], R0 = A.band_ref[b], R1 = A.band_ref[b + 1];
+      mirror_task(S.T, R0, R1, A.N, A.ref_patch, A.out, A.ld, S.item[1], tid);
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) {
+        int* mir_done = A.band_state + 2 * A.nbands;
+        if (atomicAdd(&mir_done[b], 1) == mirror_task_count(R0, R1, A.N) - 1) {  // the band's part of the matrix is final
+          __threadfence_system();
+          A.host_flags[b] = 1;
+          __threadfence_system();
+        }
+      }
+      continue;
+    }
     const tw::Tile tile = A.tiles[t];
     const int flags = tile.flags;
     const int ci0 = A.patch_chunk_ptrA[tile.pa], ci1 = A.patch_chunk_ptrA[tile.pa + 1];
@@ -1346,10 +1471,15 @@ void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(); }
 
 template <class T>
-static std::string upload(const std::vector<T>& h, T** d) {
-  *d = nullptr;
-  size_t n = std::max<size_t>(h.size(), 1);
-  CK(cudaMalloc((void**)d, n * sizeof(T)));
+static std::string upload(const std::vector<T>& h, T** d, size_t* cap = nullptr) {
+  const size_t n = std::max<size_t>(h.size(), 1) * sizeof(T);
+  if (!(cap && *d && *cap >= n)) {
+    if (cap && *d) cudaFree(*d);
+    *d = nullptr;
+    if (cap) *cap = 0;
+    CK(cudaMalloc((void**)d, n));
+    if (cap) *cap = n;
+  }
   if (!h.empty()) CK(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
   return "";
 }
@@ -1406,22 +1536,21 @@ std::string gpu_init_constants() {
 }
 
 std::string DevicePatchSet::upload_from(const PatchSet& ps) {
-  release();
   std::string e;
-  if (!(e = upload(ps.chunks, &chunks)).empty()) return e;
-  if (!(e = upload(ps.geom, &geom)).empty()) return e;
-  if (!(e = upload(ps.cell_dmin, &dmin)).empty()) return e;
-  if (!(e = upload(ps.cell_dmax, &dmax)).empty()) return e;
-  if (!(e = upload(ps.chunk_dof, &chunk_dof)).empty()) return e;
-  if (!(e = upload(ps.chunk_inc_ptr, &inc_ptr)).empty()) return e;
-  if (!(e = upload(ps.inc, &inc)).empty()) return e;
-  if (!(e = upload(ps.patch_chunk_ptr, &patch_chunk_ptr)).empty()) return e;
-  if (!(e = upload(ps.dof_orig, &dof_orig)).empty()) return e;
+  if (!(e = upload(ps.chunks, &chunks, &cap[0])).empty()) return e;
+  if (!(e = upload(ps.geom, &geom, &cap[1])).empty()) return e;
+  if (!(e = upload(ps.cell_dmin, &dmin, &cap[2])).empty()) return e;
+  if (!(e = upload(ps.cell_dmax, &dmax, &cap[3])).empty()) return e;
+  if (!(e = upload(ps.chunk_dof, &chunk_dof, &cap[4])).empty()) return e;
+  if (!(e = upload(ps.chunk_inc_ptr, &inc_ptr, &cap[5])).empty()) return e;
+  if (!(e = upload(ps.inc, &inc, &cap[6])).empty()) return e;
+  if (!(e = upload(ps.patch_chunk_ptr, &patch_chunk_ptr, &cap[7])).empty()) return e;
+  if (!(e = upload(ps.dof_orig, &dof_orig, &cap[8])).empty()) return e;
   {
     std::vector<int> dp(ps.ndof, 0);
     for (int p = 0; p < ps.npatch; p++)
       for (int i = ps.patch_dof_ptr[p]; i < ps.patch_dof_ptr[p + 1]; i++) dp[i] = p;
-    if (!(e = upload(dp, &dof_patch)).empty()) return e;
+    if (!(e = upload(dp, &dof_patch, &cap[9])).empty()) return e;
   }
   {
     std::vector<ChunkAux> ax(ps.nchunk);
@@ -1444,7 +1573,7 @@ std::string DevicePatchSet::upload_from(const PatchSet& ps) {
           if ((hm >> h) & 1u) x.act[h][x.nact[h]++] = (unsigned char)i;
       }
     }
-    if (!(e = upload(ax, &aux)).empty()) return e;
+    if (!(e = upload(ax, &aux, &cap[10])).empty()) return e;
     nchunk = ps.nchunk;
   }
   bytes = ps.chunks.size() * sizeof(ChunkMeta) + ps.geom.size() * 8 + (ps.cell_dmin.size() + ps.cell_dmax.size()) * 4 +
@@ -1452,6 +1581,7 @@ std::string DevicePatchSet::upload_from(const PatchSet& ps) {
   return "";
 }
 void DevicePatchSet::release() {
+  for (size_t& c : cap) c = 0;
   cudaFree(chunks);
   cudaFree(geom);
   cudaFree(dmin);
@@ -1483,7 +1613,7 @@ std::string gpu_symmetrize_cross(const DevicePatchSet& A, int i0, int i1, int j0
 
 std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, const std::vector<Tile>& tiles,
                            const std::vector<int>& row_out, bool self, double* d_out, long long ld, cudaStream_t stream,
-                           unsigned long long* h_stats, const int* d_col_map, bool symmetrize) {
+                           unsigned long long* h_stats, const int* d_col_map, bool symmetrize, const StreamBands* sb) {
   std::string e = gpu_init_constants();
   if (!e.empty()) return e;
   if (tiles.empty()) return "";
@@ -1526,6 +1656,24 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
   a.debug_skip = std::getenv("THINCURR_B200_DEBUG_SKIP") ? std::atoi(std::getenv("THINCURR_B200_DEBUG_SKIP")) : 0;
 #endif
   a.stats = d_stats;
+  a.nbands = 0;
+  a.tile_band = a.band_ntiles = a.band_ref = a.ref_patch = nullptr;
+  a.band_state = nullptr;
+  a.host_flags = nullptr;
+  a.N = 0;
+  if (sb && sb->nbands > 0) {
+    const int nb = sb->nbands;
+    int* d_flags = nullptr;
+    CK(cudaHostGetDevicePointer((void**)&d_flags, sb->flags, 0));
+    a.nbands = nb;
+    a.band_ntiles = sb->d_bands;
+    a.band_ref = sb->d_bands + nb;
+    a.band_state = sb->d_bands + 2 * nb + 1;
+    a.tile_band = sb->d_tile_band;
+    a.ref_patch = sb->d_ref_patch;
+    a.N = sb->N;
+    a.host_flags = d_flags;
+  }
   int dev = 0, nsm = 148;
   CK(cudaGetDevice(&dev));
   CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));

@@ -37,11 +37,9 @@ void rcb(std::vector<int>& idx, int lo, int hi, const std::vector<double>& xyz, 
 }
 }  // namespace
 
-std::string build_patches(const Model& m, int P, PatchSet& ps, int nshards) {
-  const int nv = m.np_active, nh = m.nholes;
-  ps = PatchSet();
-  ps.ndof = nv + nh;
-  if (P <= 0) {
+int auto_patch_size(int nv, int nshards) {
+  int P;
+  {
     // Large patches keep the halo (cells shared by neighbouring patches are evaluated once per patch) small, but the tile
     // count must fill the 148 SMs of every device many times over (>= ~1750 tiles per device of the upper triangle):
     // P = nv / (59 sqrt(nshards)), between 300 and 1200 DOFs.  Measured with the round-2 kernel on the 100k-vertex vessel,
@@ -52,6 +50,14 @@ std::string build_patches(const Model& m, int P, PatchSet& ps, int nshards) {
     while (P > 32 && ((long)((nv + P - 1) / P) * ((nv + P - 1) / P)) / 2 < 1500) P = P * 3 / 4;
     P = std::max(P, 32);
   }
+  return P;
+}
+
+std::string build_patches(const Model& m, int P, PatchSet& ps, int nshards, const std::vector<int>* ref_cuts, std::vector<int>* band_patch_ptr) {
+  const int nv = m.np_active, nh = m.nholes;
+  ps = PatchSet();
+  ps.ndof = nv + nh;
+  if (P <= 0) P = auto_patch_size(nv, nshards);
   // dof -> vertices (periodic meshes map several vertices to one DOF)
   std::vector<int> kdv(nv + 1, 0), ldv;
   for (int v = 0; v < m.np; v++)
@@ -70,7 +76,17 @@ std::string build_patches(const Model& m, int P, PatchSet& ps, int nshards) {
     for (int k = 0; k < 3; k++) xyz[3 * (size_t)d + k] = m.r[3 * (size_t)ldv[kdv[d]] + k];
   std::vector<int> idx(nv), cuts;
   std::iota(idx.begin(), idx.end(), 0);
-  if (nv > 0) rcb(idx, 0, nv, xyz, std::max(1, (nv + P - 1) / P), cuts);
+  if (ref_cuts && ref_cuts->size() >= 2 && ref_cuts->front() == 0 && ref_cuts->back() == nv) {
+    // patches per range of reference ids (idx is the identity here: a range of idx is a range of reference ids)
+    for (size_t b = 0; b + 1 < ref_cuts->size(); b++) {
+      const int lo = (*ref_cuts)[b], hi = (*ref_cuts)[b + 1];
+      if (band_patch_ptr) band_patch_ptr->push_back((int)cuts.size());
+      if (hi > lo) rcb(idx, lo, hi, xyz, std::max(1, (hi - lo + P / 2) / P), cuts);
+    }
+    if (band_patch_ptr) band_patch_ptr->push_back((int)cuts.size());
+  } else if (nv > 0) {
+    rcb(idx, 0, nv, xyz, std::max(1, (nv + P - 1) / P), cuts);
+  }
   cuts.push_back(nv);
   ps.nvert_patch = (int)cuts.size() - 1;
   ps.npatch = ps.nvert_patch + nh;

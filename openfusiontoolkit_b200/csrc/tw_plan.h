@@ -75,11 +75,19 @@ struct Plan {
   int patch_size = 0;
   int nshards_hint = 1;  // shard count the patch size was chosen for
   int serial = 0;        // distinguishes successive plans of a model (device mirrors are re-uploaded when it changes)
+  // banded plan (streamed single-device build, tw_capi.cu): band b = reference DOF ids [band_ref_ptr[b], band_ref_ptr[b+1])
+  // = patches [band_patch_ptr[b], band_patch_ptr[b+1]) (the hole patches belong to the last band); empty otherwise
+  std::vector<int> band_ref_ptr, band_patch_ptr;
   PatchSet ps;
 };
 
-// Build the patch decomposition of a model; P = target DOFs per patch (0 = choose automatically)
-std::string build_patches(const Model& m, int P, PatchSet& out, int nshards = 1);
+// Patch size (DOFs) chosen for a model with nv vertex DOFs whose rows are spread over nshards pieces of work
+int auto_patch_size(int nv, int nshards);
+// Build the patch decomposition of a model; P = target DOFs per patch (0 = choose automatically).
+// ref_cuts (optional, ascending, first 0, last np_active): the vertex DOFs are first cut into these ranges of reference ids
+// and every range gets patches of its own, in range order (band_patch_ptr: first vertex patch of every range + total)
+std::string build_patches(const Model& m, int P, PatchSet& out, int nshards = 1, const std::vector<int>* ref_cuts = nullptr,
+                          std::vector<int>* band_patch_ptr = nullptr);
 // Unit normal of a triangle exactly as tw_compute_phipot evaluates it (thin_wall.F90:1942-1943): IEEE operations
 // in the reference's order, no contraction (the device reads these values instead of recomputing them).
 void phipot_normal(const double* P /*[3][3]*/, double* n);

@@ -60,11 +60,14 @@ ref = res['one']
 assert np.array_equal(ref, ref.T)
 for k, v in res.items():
     assert np.array_equal(v, v.T), k
-    if k.startswith('full') or k.startswith('one'):
-        assert np.array_equal(v, ref), k          # full-row shards keep the single-device orientation of every tile
+    if k.startswith('one'):
+        assert np.array_equal(v, ref), k          # streamed (page-locked) and banded (pageable) builds share their patches
     else:
-        assert np.abs(v - ref).max() <= 1e-13 * np.abs(ref).max(), k   # symmetric shards: to rounding (summation order)
+        # other patches (the one-device build of a model this size plans its patches band by band) or another tile
+        # orientation (symmetric shards): equal to rounding of the summation order
+        assert np.abs(v - ref).max() <= 1e-13 * np.abs(ref).max(), k
 assert np.array_equal(res['sym'], res['sym_pageable'])
+assert np.array_equal(res['full'], res['full_pageable'])
 print('INPROC_OK')
 """
 

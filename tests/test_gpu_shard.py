@@ -126,9 +126,14 @@ def test_vessel_mesh_rows_and_stats(env):
     O = tw.OracleModel(m['r'], m['lc'], None, nodesets=m['nodesets'], closures=m['closures'])
     rng = np.random.default_rng(9)
     rows = np.concatenate([rng.choice(O.np_active, 24, replace=False), np.arange(O.np_active, O.nelems)]).astype(np.int32)
-    Ro = O.lmat_rows(rows)
-    err = entry_err(np.array(L[rows]), Ro, np.abs(np.diag(L)).max())
-    assert err < ENTRY_TOL, 'max rel entry error %.3e' % err
+    Ro, A = O.lmat_rows(rows, with_abs=True)
+    got = np.array(L[rows])
+    # criterion of tests/test_gpu_scale.py: 1e-10 relative on every entry plus the summation-order noise of an entry that
+    # cancels to a small fraction of its terms (A = sum of their magnitudes; the reference's atomics reorder them from run
+    # to run); plain 1e-10 where fewer than 3 digits are lost
+    assert (np.abs(got - Ro) <= 1e-10 * np.abs(Ro) + 64 * np.finfo(float).eps * A).all()
+    well = np.abs(Ro) > 1e-3 * A
+    assert (np.abs(got - Ro)[well] / np.abs(Ro)[well]).max() < ENTRY_TOL
     for r in rows[:12]:
         assert np.array_equal(L[r, :], L[:, r])
     hist, visited = T.pair_stats()
@@ -183,3 +188,35 @@ def test_dense_block_evaluator(env):
         assert (np.abs(got[:, :len(cols)] - ref)[big] / np.abs(ref)[big]).max() < 1e-10
     with pytest.raises(Exception):
         T.compute_Lmat_block([0, 0], [1], torch.empty((2, 1), dtype=torch.float64, device='cuda'))
+
+
+@pytest.mark.parametrize('name,bands', [('torus', '3'), ('ex_torus', '6')])
+def test_streamed_single_device_build(env, monkeypatch, name, bands):
+    """The reference-facing build of a large model on one device (thincurr_Lmat -> lmat_stream_host): banded plan over ranges
+    of reference ids, the matrix in the reference layout on the device, every band followed by its mirror pass and two
+    strided device->host copies.  Forced onto small meshes here (holes, closure, periodic torus): entries vs the oracle,
+    exact symmetry, the same bits from the device-resident shard builds of the same plan and from the pageable-destination
+    path (row bands over the same patches)."""
+    import torch
+    from openfusiontoolkit_b200 import _interface as I
+    from openfusiontoolkit_b200.ThinCurr import ThinCurr
+    monkeypatch.setenv('THINCURR_B200_STREAM_BANDS', bands)
+    m = load_mesh(name)
+    T = ThinCurr(env)
+    T.setup_model(r=m['r'], lc=m['lc'], reg=m['reg'], nodesets=m['nodesets'], closures=m['sidesets'][0])
+    T.compute_Lmat()
+    L = np.array(T.Lmat)
+    assert np.array_equal(L, L.T)
+    O = tw.OracleModel(m['r'], m['lc'], m['reg'], nodesets=m['nodesets'], closures=m['sidesets'][0])
+    Lo = O.compute_Lmat()
+    err = entry_err(L, Lo, np.abs(np.diag(Lo)).max())
+    assert err < ENTRY_TOL, 'max rel entry error %.3e' % err
+    for s in range(2):
+        rows = T.shard_rows(2, s)
+        out = torch.empty((len(rows), T.nelems), dtype=torch.float64, device='cuda')
+        T.compute_Lmat_shard(2, s, out)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), L[rows]), 'shard %d differs from the streamed build' % s
+    P = np.full((T.nelems, T.nelems), np.nan)   # pageable caller memory
+    assert I.b200_Lmat_host(T.tw_obj, P) == 0, I.b200_last_error()
+    assert np.array_equal(P, L)
