@@ -362,57 +362,6 @@ __global__ void __launch_bounds__(256) near_pairs_kernel(const SweepArgs A) {
   }
 }
 
-// central differences of the analytic potential around a vertex (thin_wall.F90:2049-2075), D = grad phi
-__device__ __forceinline__ void bops_near(const double* P, const double* nh, const double* nrm, const double* X, bool nb, double* D) {
-  const double B_dx = 1.e-6;
-  double pt[3] = {X[0], X[1], X[2]}, diff[3] = {0.0, 0.0, 0.0};
-  if (nb)
-    for (int d = 0; d < 3; d++) pt[d] = xsub(pt[d], xmul(xmul(nrm[d], 10.0), B_dx));
-  for (int ik = 1; ik <= 2; ik++) {
-    if (ik == 2)
-      for (int d = 0; d < 3; d++) pt[d] = xadd(pt[d], xmul(xmul(nrm[d], 20.0), B_dx));
-#pragma unroll
-    for (int jj = 0; jj < 3; jj++) {
-      pt[jj] = xadd(pt[jj], B_dx);
-      double tmp = phipot(P, nh, pt[0], pt[1], pt[2]);
-      diff[jj] = xadd(diff[jj], __ddiv_rn(tmp, 2.0 * B_dx));
-      pt[jj] = xsub(pt[jj], 2.0 * B_dx);
-      tmp = phipot(P, nh, pt[0], pt[1], pt[2]);
-      diff[jj] = xsub(diff[jj], __ddiv_rn(tmp, 2.0 * B_dx));
-      pt[jj] = xadd(pt[jj], B_dx);
-    }
-    if (!nb) break;
-  }
-  if (nb)
-    for (int d = 0; d < 3; d++) diff[d] = diff[d] / 2.0;
-  D[0] = diff[0];
-  D[1] = diff[1];
-  D[2] = diff[2];
-}
-// near (cell, vertex) pairs of a B sweep, one thread per pair over the whole device; ent.y bit 30 = on-surface vertex
-__global__ void __launch_bounds__(128) bops_near_kernel(const SweepArgs A) {
-  const unsigned n = min(*A.near_count, A.near_cap);
-  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const int2 ent = A.near_list[e];
-    const int jy = ent.y & 0x3fffffff;
-    const bool nb = (ent.y >> 30) & 1;
-    const int ci = A.row_cells ? A.row_cells[ent.x] : ent.x, p = A.col_items ? A.col_items[jy] : jy;
-    double Pi[9], nh[3], nrm[3], X[3], D[3];
-#pragma unroll
-    for (int q = 0; q < 9; q++) Pi[q] = A.Pr[9 * (size_t)ci + q];
-    tri_normal(Pi, nh);
-    for (int d = 0; d < 3; d++) {
-      nrm[d] = A.Nr[3 * (size_t)ci + d];
-      X[d] = A.rc[3 * (size_t)p + d];
-    }
-    bops_near(Pi, nh, nrm, X, nb, D);
-    double* o = A.T + ((size_t)(ent.x - A.row0) * A.ldT + jy) * 3;
-    o[0] = D[0];
-    o[1] = D[1];
-    o[2] = D[2];
-  }
-}
-
 // MODE 2 of the sweep: B operator of a row cell at a mesh vertex (thin_wall_hodlr.F90:612-676 = thin_wall.F90:2030-2088).
 // D(i,p) such that the contribution of vertex k of cell i is D x qbasis(:,k,i):
 //   far : D = -area_i sum_q w_q d_q/|d_q|^3, d_q = r_p - x_q      near: D = grad phi by central differences
@@ -458,12 +407,12 @@ __global__ void __launch_bounds__(kSwT) bops_sweep_kernel(const SweepArgs A) {
           continue;
         }
         const int n = c_qnp[o], off = c_qoff[o];
-        const double* tab = R.pts + 3 * (off - kSwOff);
+        const double* tab = R.pts + 4 * (off - kSwOff);
         double h0 = 0.0, h1 = 0.0, h2 = 0.0;
         for (int q = 0; q < n; q++) {
-          const double dx = X[0] - tab[3 * q], dy = X[1] - tab[3 * q + 1], dz = X[2] - tab[3 * q + 2];
+          const double dx = X[0] - tab[4 * q], dy = X[1] - tab[4 * q + 1], dz = X[2] - tab[4 * q + 2];
           const double ri = rsqrt_fast(fma(dz, dz, fma(dy, dy, dx * dx)));
-          const double w3 = g_qwts[off + q] * (ri * ri * ri);
+          const double w3 = tab[4 * q + 3] * (ri * ri * ri);
           h0 = fma(w3, dx, h0);
           h1 = fma(w3, dy, h1);
           h2 = fma(w3, dz, h2);
@@ -804,10 +753,25 @@ static std::string stored_sweep(BlockCtx& R, BlockCtx& C, const DBuf<int>* row_c
   const int chunk = (int)std::max<long long>(twk::kSwR, std::min<long long>(nrc, ((256ll << 20) / 8) / std::max<long long>(ldT, 1)));
   double* T = nullptr;
   CKO(cudaMallocAsync((void**)&T, (size_t)chunk * ldT * 8, stream));
+  // near pairs of a chunk: listed by the sweep, evaluated by a second kernel over the whole device
+  const unsigned near_cap = 1u << 21;
+  int2* near_list = nullptr;
+  unsigned* near_count = nullptr;
+  CKO(cudaMallocAsync((void**)&near_list, (size_t)near_cap * sizeof(int2) + sizeof(unsigned), stream));
+  near_count = reinterpret_cast<unsigned*>(near_list + near_cap);
+  int nsm = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  }
   for (int r0 = 0, it = 0; r0 < std::max(nrc, 1); r0 += chunk, it++) {
     const int r1 = std::min(nrc, r0 + chunk);
     if (r1 > r0) {
       twk::SweepArgs a{};
+      a.near_list = near_list;
+      a.near_count = near_count;
+      a.near_cap = near_cap;
+      CKO(cudaMemsetAsync(near_count, 0, sizeof(unsigned), stream));
       a.Pr = R.P.p; a.Ar = R.A.p; a.Nr = R.N.p;
       a.Pc = C.P.p; a.Ac = C.A.p;
       a.row_cells = row_cells ? row_cells->p : nullptr;
@@ -817,6 +781,9 @@ static std::string stored_sweep(BlockCtx& R, BlockCtx& C, const DBuf<int>* row_c
       dim3 grid;
       sweep_grid(ncc, r1 - r0, grid, a.rows_per_y);
       twk::pair_sweep_kernel<0><<<grid, twk::kSwT, sizeof(twk::SweepSmem), stream>>>(a);
+      CKO(cudaGetLastError());
+      note_launch();
+      twk::near_pairs_kernel<<<4 * nsm, 256, 0, stream>>>(a);
       CKO(cudaGetLastError());
       note_launch();
     }
@@ -833,6 +800,7 @@ static std::string stored_sweep(BlockCtx& R, BlockCtx& C, const DBuf<int>* row_c
     note_launch();
   }
   CKO(cudaFreeAsync(T, stream));
+  CKO(cudaFreeAsync(near_list, stream));
   return "";
 }
 
