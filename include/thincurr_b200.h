@@ -166,6 +166,14 @@ int thincurr_b200_shard_rows(void* tw_ptr, int nshards, int shard, int* row_ids)
 /* info[8]: patch size, patches, chunks, sum of patch cells (halo included), self tiles, chunk pairs,
  * cell pairs of those tiles (diagonal tiles counted in full), vertex patches */
 int thincurr_b200_plan_info(void* tw_ptr, int64_t* info);
+/* Banded plan of the streamed single-device build behind thincurr_Lmat (large models, one device, page-locked host
+ * matrix; replaces the blocking row-by-row fill of thincurr_f.F90:545-581): the vertex DOFs are cut into *nbands ranges of
+ * reference ids [band_ref_ptr[b], band_ref_ptr[b+1]) whose patches are [band_patch_ptr[b], band_patch_ptr[b+1]); band b
+ * leaves the device as rows [R0,R1) x columns [R0,N) and rows [R1,N) x columns [R0,R1) while the later bands are
+ * evaluated.  *nbands = 0: this model is built the ordinary way (small, V-coils, or a reference numbering without
+ * locality).  Arrays hold up to 33 entries (may be NULL).  Host-only call (plans, launches nothing); the model keeps
+ * the plan. */
+int thincurr_b200_stream_plan(void* tw_ptr, int* nbands, int* band_ref_ptr, int* band_patch_ptr);
 /* introspection: patch_chunk_ptr[npatch+1]; chunk_info[nchunk][6] = centre xyz, bounding radius, longest edge, cells */
 int thincurr_b200_plan_chunks(void* tw_ptr, int* patch_chunk_ptr, double* chunk_info);
 /* host->device bytes of one upload of the model (plan mirror) to a device; 0 before the first build */

@@ -459,6 +459,18 @@ class ThinCurr():
         sptr = c_void_p(stream) if stream else c_void_p()
         _check(b200_Bel_shard(self.tw_obj, nshards, shard, c_void_p(out.data_ptr()), sptr))
 
+    def stream_plan(self):
+        '''! Banded plan of the streamed single-device build behind `compute_Lmat()` (thincurr_b200_stream_plan): returns
+        `(band_ref_ptr, band_patch_ptr)` -- band b = reference DOF ids `[band_ref_ptr[b], band_ref_ptr[b+1])` = patches
+        `[band_patch_ptr[b], band_patch_ptr[b+1])` -- or `None` when this model is built the ordinary way.'''
+        from .._interface import b200_stream_plan
+        nb = c_int()
+        ref, pat = numpy.zeros(33, dtype=numpy.int32), numpy.zeros(33, dtype=numpy.int32)
+        _check(b200_stream_plan(self.tw_obj, ctypes.byref(nb), ref.ctypes.data_as(c_void_p), pat.ctypes.data_as(c_void_p)))
+        if nb.value == 0:
+            return None
+        return ref[:nb.value + 1].copy(), pat[:nb.value + 1].copy()
+
     def plan_info(self):
         '''! Patch/chunk/tile counts of the owner-computes plan (see thincurr_b200_plan_info).'''
         from .._interface import b200_plan_info

@@ -80,6 +80,7 @@ b200_set_sensors = ctypes_subroutine(oftpy_lib.thincurr_b200_set_sensors,
      c_void_ptr_ptr], c_int)
 b200_msensor = ctypes_subroutine(oftpy_lib.thincurr_b200_msensor, [c_void_p, c_void_p, c_void_ptr_ptr, c_void_ptr_ptr], c_int)
 b200_plan = ctypes_subroutine(oftpy_lib.thincurr_b200_plan, [c_void_p, c_int, c_int, c_int_ptr], c_int)
+b200_stream_plan = ctypes_subroutine(oftpy_lib.thincurr_b200_stream_plan, [c_void_p, c_int_ptr, c_void_p, c_void_p], c_int)
 b200_shard_rows = ctypes_subroutine(oftpy_lib.thincurr_b200_shard_rows, [c_void_p, c_int, c_int, ctypes_numpy_array(int32, 1)], c_int)
 b200_Lmat_shard = ctypes_subroutine(oftpy_lib.thincurr_b200_Lmat_shard,
     [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p], c_int)

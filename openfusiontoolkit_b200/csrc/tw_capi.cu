@@ -159,12 +159,24 @@ static bool ensure_banded_plan(Model& m, std::string& err) {
   int P = 0;
   if (const char* e = std::getenv("THINCURR_B200_PATCH")) P = std::atoi(e);
   if (m.plan && !m.plan->band_ref_ptr.empty() && (P <= 0 || m.plan->patch_size == P)) return true;
+  if (m.no_stream_plan) return false;
   if (P <= 0) P = auto_patch_size(m.np_active, 4);  // (100k-vertex vessel: 600 -> 1.98 s, 850 -> 1.93 s, 1200 -> 2.17 s end to end)
   const std::vector<int> cuts = stream_ref_cuts(m, P);
   if (cuts.empty()) return false;
   auto pl = std::make_shared<Plan>();
   err = build_patches(m, P, pl->ps, 1, &cuts, &pl->band_patch_ptr);
   if (!err.empty()) return false;
+  {
+    // A range of reference ids must be a compact piece of the surface for its patches to be compact: with a numbering
+    // without locality (a permuted mesh) the one-ring halos of the patches multiply the cells, hence the pair work.
+    // Compact patches of >= 300 DOFs carry 1.1-1.3 x nc cells in total.
+    double cells = 0.0;
+    for (int p = 0; p < pl->ps.nvert_patch; p++) cells += pl->ps.patch_ncell[p];
+    if (cells > 1.6 * std::max(m.nc, 1) && !std::getenv("THINCURR_B200_STREAM_BANDS")) {
+      m.no_stream_plan = true;
+      return false;
+    }
+  }
   pl->band_ref_ptr = cuts;
   pl->band_ref_ptr.back() = m.np_active + m.nholes;  // the hole DOFs (reference ids after the vertices) and their patches
   pl->band_patch_ptr.back() = pl->ps.npatch;         // belong to the last band
@@ -618,14 +630,13 @@ static std::string lmat_stream_host(Model& m, double* dst, bool trace) {
   };
   ck(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
   ck(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "cudaStreamCreate");
-  {  // band flags: a small mapped page-locked buffer kept for the life of the process (allocating and freeing page-locked
-     // memory synchronises the device)
-    static int* g_flags = nullptr;
-    static std::mutex g_flags_mu;
-    std::lock_guard<std::mutex> lk(g_flags_mu);
-    if (!g_flags && !ck(cudaHostAlloc((void**)&g_flags, 64 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc")) g_flags = nullptr;
-    flags = g_flags;
-  }
+  // band flags: a small mapped page-locked buffer kept for the life of the process (allocating and freeing page-locked
+  // memory synchronises the device); streamed builds of one process take turns
+  static int* g_flags = nullptr;
+  static std::mutex g_stream_mu;
+  std::lock_guard<std::mutex> stream_lock(g_stream_mu);
+  if (!g_flags && !ck(cudaHostAlloc((void**)&g_flags, 64 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc")) g_flags = nullptr;
+  flags = g_flags;
   if (nb > 64) err = "Internal error: too many bands";
   if (trace) std::fprintf(stderr, "[lmat_stream_host] streams+flags done at %.1f ms\n", since(tr0));
   std::vector<int> ref_patch(N, 0), row_out(ps.ndof, -1);
@@ -1268,6 +1279,20 @@ int thincurr_b200_plan(void* tw_ptr, int nshards, int shard, int* nrows) {
   std::vector<int> rows;
   shard_rows(m, nshards, shard, p0, p1, rows);
   *nrows = (int)rows.size();
+  return 0;
+}
+
+int thincurr_b200_stream_plan(void* tw_ptr, int* nbands, int* band_ref_ptr, int* band_patch_ptr) {
+  Model& m = *(Model*)tw_ptr;
+  std::string err;
+  *nbands = 0;
+  if (!ensure_banded_plan(m, err)) return err.empty() ? 0 : fail(err);
+  const Plan& pl = *m.plan;
+  *nbands = (int)pl.band_ref_ptr.size() - 1;
+  for (size_t b = 0; b < pl.band_ref_ptr.size(); b++) {
+    if (band_ref_ptr) band_ref_ptr[b] = pl.band_ref_ptr[b];
+    if (band_patch_ptr) band_patch_ptr[b] = pl.band_patch_ptr[b];
+  }
   return 0;
 }
 

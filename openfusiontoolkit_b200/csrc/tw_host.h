@@ -108,6 +108,7 @@ struct Model {
   std::vector<double> R_val;
   // ---- device side ----
   std::shared_ptr<Plan> plan;
+  bool no_stream_plan = false;  // the banded plan of the streamed build was tried and rejected (reference numbering without locality)
   std::vector<std::shared_ptr<DeviceState>> dev;  // one per CUDA device used
   std::shared_ptr<void> block_ctx;                // plain cell arrays on the device for the list sweeps (tw_blocks.cu)
   bool verbose = true;

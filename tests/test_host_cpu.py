@@ -179,3 +179,39 @@ def test_h5_writer_roundtrip(tmp_path):
     assert struct.unpack_from('<Q', raw, 40)[0] == len(raw) and struct.unpack_from('<I', raw, 72)[0] == 1
     bt, heap = struct.unpack_from('<QQ', raw, 80)
     assert raw[bt:bt + 4] == b'TREE' and raw[heap:heap + 4] == b'HEAP' and heap - bt == 544
+
+
+def test_stream_plan_bands(env, monkeypatch):
+    """Banded plan of the streamed single-device build (thincurr_b200_stream_plan, host-only): equal ranges of reference
+    ids, every band's patches hold exactly the DOFs of its range (the hole DOFs in the last band), small models and a
+    reference numbering without locality are built the ordinary way."""
+    import bench
+    from openfusiontoolkit_b200.ThinCurr import ThinCurr
+    from openfusiontoolkit_b200.ThinCurr.meshing import build_torus_vessel
+    from openfusiontoolkit_b200 import _interface as I
+    m = load_mesh('ex_torus')
+    T = ThinCurr(env)
+    T.setup_model(r=m['r'], lc=m['lc'], reg=m['reg'], nodesets=m['nodesets'], closures=m['sidesets'][0])
+    assert T.stream_plan() is None   # 2 395 DOFs: one launch, one copy
+    m = bench.make_mesh('vessel20k')
+    T = ThinCurr(env)
+    T.setup_model(r=m['r'], lc=m['lc'], nodesets=m['nodesets'], closures=m['closures'])
+    ref, pat = T.stream_plan()
+    nb = len(ref) - 1
+    assert 2 <= nb <= 10 and ref[0] == 0 and ref[-1] == T.nelems and pat[0] == 0
+    assert (np.diff(ref) > 0).all() and (np.diff(pat) > 0).all()
+    widths = np.diff(ref[:-1])
+    assert widths.max() - widths.min() <= 64   # equal ranges (cut at multiples of 32)
+    patch_of = np.zeros(T.nelems, dtype=np.int32)
+    assert I.b200_dof_patches(T.tw_obj, 1, patch_of) == 0
+    for b in range(nb):
+        p = patch_of[ref[b]:ref[b + 1]]
+        assert p.min() >= pat[b] and p.max() < pat[b + 1], 'band %d: patches outside its range' % b
+    assert pat[-1] == T.plan_info()['npatch']
+    assert (patch_of[T.np_active:] >= pat[-2]).all()   # hole patches belong to the last band
+    # the same vessel with a random vertex numbering: ranges of reference ids are scattered over the surface
+    nt, nphi = bench.WORKLOADS['vessel20k']
+    mp = build_torus_vessel(nt, nphi, nports=10, permute_seed=3)
+    T = ThinCurr(env)
+    T.setup_model(r=mp['r'], lc=mp['lc'], nodesets=mp['nodesets'], closures=mp['closures'])
+    assert T.stream_plan() is None
