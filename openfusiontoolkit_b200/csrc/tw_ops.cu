@@ -250,7 +250,8 @@ __global__ void vcoil_fill_kernel(int nrows, const int* __restrict__ row_ids, in
 constexpr int BNT = 512;
 struct BelSmem {
   double g[tw::kGeomRows * tw::kCH];
-  double H[3][tw::kCH * tw::kCH];  // [comp][c][p]
+  double H[3][tw::kCH * (tw::kCH + 1)];  // [comp][c][p], row stride kCH+1: the contraction reads one vertex p for the cells of 32
+                                         // different DOFs at once (stride kCH would put them all in one bank)
   double vx[tw::kCH], vy[tw::kCH], vz[tw::kCH], vva[tw::kCH];
   unsigned int near_list[tw::kCH * tw::kCH];
   int dof[tw::kMaxChunkDof];
@@ -402,9 +403,9 @@ __global__ void __launch_bounds__(BNT, 1) bel_tile_kernel(const BelArgs A) {
               h2 *= area;
             }
           }
-          S.H[0][c * CH + p] = h0;
-          S.H[1][c * CH + p] = h1;
-          S.H[2][c * CH + p] = h2;
+          S.H[0][c * (CH + 1) + p] = h0;
+          S.H[1][c * (CH + 1) + p] = h1;
+          S.H[2][c * (CH + 1) + p] = h2;
         }
       }
       __syncthreads();
@@ -420,9 +421,9 @@ __global__ void __launch_bounds__(BNT, 1) bel_tile_kernel(const BelArgs A) {
         nrm[1] = S.g[23 * CH + c];
         nrm[2] = S.g[24 * CH + c];
         bel_near(P, nh, nrm, S.vx[p], S.vy[p], S.vz[p], (e & 4096u) != 0, Hn);
-        S.H[0][c * CH + p] = Hn[0];
-        S.H[1][c * CH + p] = Hn[1];
-        S.H[2][c * CH + p] = Hn[2];
+        S.H[0][c * (CH + 1) + p] = Hn[0];
+        S.H[1][c * (CH + 1) + p] = Hn[1];
+        S.H[2][c * (CH + 1) + p] = Hn[2];
       }
       __syncthreads();
       // ---- phase 3: contraction, entry = (dof in chunk, vertex)
@@ -432,12 +433,15 @@ __global__ void __launch_bounds__(BNT, 1) bel_tile_kernel(const BelArgs A) {
           const int p = e / cm.ndof, ia = e - p * cm.ndof;  // dof fastest: contiguous-ish writes in e
           const int row = A.row_out[S.dof[ia]];
           if (row < 0) continue;
+          // (old values first: their latency overlaps the contraction)
+          const size_t o = (size_t)(pbase + p) * A.nrows + row, cs = (size_t)A.np * A.nrows;
+          const double o0 = __ldcg(A.out + o), o1 = __ldcg(A.out + cs + o), o2 = __ldcg(A.out + 2 * cs + o);
           double b0 = 0.0, b1 = 0.0, b2 = 0.0;
           for (int i1 = S.iptr[ia]; i1 < S.iptr[ia + 1]; i1++) {
             const unsigned w1 = S.inc[i1];
             const int c = w1 & 63, k1 = (w1 >> 6) & 3;
             const double ex = S.g[(10 + 3 * k1) * CH + c], ey = S.g[(11 + 3 * k1) * CH + c], ez = S.g[(12 + 3 * k1) * CH + c];
-            const double hx = S.H[0][c * CH + p], hy = S.H[1][c * CH + p], hz = S.H[2][c * CH + p];
+            const double hx = S.H[0][c * (CH + 1) + p], hy = S.H[1][c * (CH + 1) + p], hz = S.H[2][c * (CH + 1) + p];
             double c0 = ey * hz - ez * hy, c1 = ez * hx - ex * hz, c2 = ex * hy - ey * hx;
             if (w1 & 256) {
               c0 = -c0;
@@ -448,10 +452,9 @@ __global__ void __launch_bounds__(BNT, 1) bel_tile_kernel(const BelArgs A) {
             b1 += c1;
             b2 += c2;
           }
-          const size_t o = (size_t)(pbase + p) * A.nrows + row;
-          A.out[o] += b0 * A.scale;
-          A.out[(size_t)A.np * A.nrows + o] += b1 * A.scale;
-          A.out[2 * (size_t)A.np * A.nrows + o] += b2 * A.scale;
+          __stcg(A.out + o, o0 + b0 * A.scale);
+          __stcg(A.out + cs + o, o1 + b1 * A.scale);
+          __stcg(A.out + 2 * cs + o, o2 + b2 * A.scale);
         }
       }
     }
