@@ -138,11 +138,14 @@ std::string replan(Model& m, int nshards) {
 // later rows), so the copies keep pace with the evaluation; what stays exposed is the copy of the last band, 1/B^2 of the
 // matrix.  B <= 10, and few enough bands that a range of reference ids (on a structured mesh: a strip of grid lines) is
 // not narrower than a patch: sqrt(nv / (1.1 P)).  Empty result: no streaming (small or V-coil models).
-static std::vector<int> stream_ref_cuts(const Model& m, int P) {
+static std::vector<int> stream_ref_cuts(const Model& m, int P, int ndev) {
   const int nv = m.np_active;
   int B = 0;
   if (const char* e = std::getenv("THINCURR_B200_STREAM_BANDS")) B = std::atoi(e);
   else if (m.nelems >= 12000 && m.n_vcoils == 0) B = std::min(10, (int)std::sqrt(nv / (1.125 * std::max(P, 1))));
+  // several devices: the bands are dealt out to the devices (a band needs nothing from any other band), at least four
+  // per device so that their unequal costs balance (narrower ranges: more halo, paid for by the second link)
+  if (ndev > 1 && B >= 2) B = std::max(B, 4 * ndev);
   if (B < 2 || nv < 64 * B || m.n_vcoils > 0) return {};
   B = std::min(B, 32);
   std::vector<int> cuts{0};
@@ -154,14 +157,15 @@ static std::vector<int> stream_ref_cuts(const Model& m, int P) {
   return cuts.size() >= 3 ? cuts : std::vector<int>{};
 }
 // (re)plan for the streamed build; false: this model is built the ordinary way
-static bool ensure_banded_plan(Model& m, std::string& err) {
+static bool ensure_banded_plan(Model& m, std::string& err, int ndev = 1) {
   err.clear();
   int P = 0;
   if (const char* e = std::getenv("THINCURR_B200_PATCH")) P = std::atoi(e);
-  if (m.plan && !m.plan->band_ref_ptr.empty() && (P <= 0 || m.plan->patch_size == P)) return true;
+  if (m.plan && !m.plan->band_ref_ptr.empty() && (P <= 0 || m.plan->patch_size == P) && m.plan->band_ndev == ndev) return true;
   if (m.no_stream_plan) return false;
-  if (P <= 0) P = auto_patch_size(m.np_active, 4);  // (100k-vertex vessel: 600 -> 1.98 s, 850 -> 1.93 s, 1200 -> 2.17 s end to end)
-  const std::vector<int> cuts = stream_ref_cuts(m, P);
+  // (one device, 100k-vertex vessel: 600 -> 1.98 s, 850 -> 1.93 s, 1200 -> 2.17 s end to end)
+  if (P <= 0) P = auto_patch_size(m.np_active, 4 * ndev);
+  const std::vector<int> cuts = stream_ref_cuts(m, P, ndev);
   if (cuts.empty()) return false;
   auto pl = std::make_shared<Plan>();
   err = build_patches(m, P, pl->ps, 1, &cuts, &pl->band_patch_ptr);
@@ -180,7 +184,8 @@ static bool ensure_banded_plan(Model& m, std::string& err) {
   pl->band_ref_ptr = cuts;
   pl->band_ref_ptr.back() = m.np_active + m.nholes;  // the hole DOFs (reference ids after the vertices) and their patches
   pl->band_patch_ptr.back() = pl->ps.npatch;         // belong to the last band
-  pl->nshards_hint = 1;
+  pl->nshards_hint = ndev;
+  pl->band_ndev = ndev;
   pl->patch_size = P;
   pl->serial = ++g_plan_serial;
   m.plan = pl;
@@ -591,151 +596,219 @@ static std::string scratch_rows(DeviceState& ds, size_t bytes, double** out) {
   return "";
 }
 
-// Streamed single-device build into a page-locked host matrix (banded plan, see stream_ref_cuts).  The device holds the
-// matrix in the reference layout and ONE launch of the tile kernel works through the tiles band by band (rows of a band
-// against this and all later bands).  As soon as the tiles of a band are done the kernel's own CTAs run its mirror pass
-// between two tiles and raise the band's flag in mapped host memory; this thread then hands the band's L-shaped part of
-// the matrix -- its rows from its first column on, and its columns of all later rows -- to the copy engine as two
-// strided copies, while the later bands are evaluated.  Every entry crosses the link exactly once and leaves as soon as
-// the band that evaluated it (or its transposed twin) is done, so the link works in step with the evaluation from the
-// first band on.  (A build whose rows may only leave complete -- all columns -- cannot start copying before its most
-// expensive rows are finished and ends link-bound; separate launches per band end on their longest tile each.)
-static std::string lmat_stream_host(Model& m, double* dst, bool trace) {
+// several devices stream a build only if every one of them can hold the whole matrix next to what it holds already
+static bool stream_devices_ok(const std::vector<int>& devs_ids, size_t bytes) {
+  if (std::getenv("THINCURR_B200_NO_MULTI_STREAM")) return false;
+  DeviceGuard guard;
+  for (int d : devs_ids) {
+    size_t fr = 0, tot = 0;
+    if (cudaSetDevice(d) != cudaSuccess || cudaMemGetInfo(&fr, &tot) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    if (tot < bytes + ((size_t)8 << 30)) return false;  // (the row-block scratch of an earlier call is reused or replaced)
+  }
+  return true;
+}
+
+// Streamed build into a page-locked host matrix (banded plan, see stream_ref_cuts).  A device holds the matrix in the
+// reference layout and ONE launch of the tile kernel works through its bands (rows of a band against this and all later
+// bands).  As soon as the tiles of a band are done the kernel's own CTAs run its mirror pass between two tiles and raise
+// the band's flag in mapped host memory; this thread then hands the band's L-shaped part of the matrix -- its rows from
+// its first column on, and its columns of all later rows -- to the copy engine as two strided copies, while the later
+// bands are evaluated.  Every entry crosses the link exactly once and leaves as soon as the band that evaluated it (or
+// its transposed twin) is done, so the link works in step with the evaluation from the first band on.  (A build whose
+// rows may only leave complete -- all columns -- cannot start copying before its most expensive rows are finished and
+// ends link-bound; separate launches per band end on their longest tile each.)
+// Several devices: a band needs nothing from any other band, so the bands are dealt out to the devices by cost (no
+// exchange, no peer access; every pair integral is still evaluated once) and every device streams its bands over its own
+// link.
+static std::string lmat_stream_host(Model& m, double* dst, const std::vector<int>& devs_ids, bool trace) {
   const auto tr0 = std::chrono::steady_clock::now();
   auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
   const Plan& pl = *m.plan;
   const PatchSet& ps = pl.ps;
   const size_t N = (size_t)m.nelems;
-  const int nb = (int)pl.band_ref_ptr.size() - 1;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return "No CUDA device available (the B200 backend has no CPU fallback)";
-  std::shared_ptr<DeviceState> ds;
-  std::string err = ensure_device(m, dev, ds);
-  if (!err.empty()) return err;
-  if (trace) std::fprintf(stderr, "[lmat_stream_host] ensure_device at %.1f ms\n", since(tr0));
-  err = ds->ps.upload_from(ps);  // the call's inputs: host model -> device, every call
-  if (trace) std::fprintf(stderr, "[lmat_stream_host] upload done at %.1f ms\n", since(tr0));
-  if (!err.empty()) return err;
-  ds->plan_serial = pl.serial;
-  double* d = nullptr;
-  err = scratch_rows(*ds, N * N * 8, &d);
-  if (trace) std::fprintf(stderr, "[lmat_stream_host] scratch done at %.1f ms\n", since(tr0));
-  if (!err.empty()) return err;
-  cudaStream_t s = nullptr, cs = nullptr;
-  int* d_ref_patch = nullptr;
-  int* flags = nullptr;
+  const int nb = (int)pl.band_ref_ptr.size() - 1, ndev = (int)devs_ids.size();
+  std::string err;
   auto ck = [&](cudaError_t e, const char* what) {
     if (e != cudaSuccess && err.empty()) err = std::string(what) + ": " + cudaGetErrorString(e);
     return e == cudaSuccess;
   };
-  ck(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
-  ck(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "cudaStreamCreate");
   // band flags: a small mapped page-locked buffer kept for the life of the process (allocating and freeing page-locked
-  // memory synchronises the device); streamed builds of one process take turns
+  // memory synchronises the devices); streamed builds of one process take turns
+  constexpr int kMaxBands = 256;
   static int* g_flags = nullptr;
   static std::mutex g_stream_mu;
   std::lock_guard<std::mutex> stream_lock(g_stream_mu);
-  if (!g_flags && !ck(cudaHostAlloc((void**)&g_flags, 64 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc")) g_flags = nullptr;
-  flags = g_flags;
-  if (nb > 64) err = "Internal error: too many bands";
-  if (trace) std::fprintf(stderr, "[lmat_stream_host] streams+flags done at %.1f ms\n", since(tr0));
+  if (!g_flags && !ck(cudaHostAlloc((void**)&g_flags, kMaxBands * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc")) g_flags = nullptr;
+  if (nb > kMaxBands) err = "Internal error: too many bands";
+  if (!err.empty()) return err;
+  std::memset(g_flags, 0, (size_t)nb * sizeof(int));
+
+  // tiles of every band (most expensive first) and the bands of every device: greedy by cost, most expensive band first
+  std::vector<std::vector<Tile>> band_tiles(nb);
+  std::vector<double> band_cost(nb, 0.0);
+  for (int b = 0; b < nb; b++) {
+    build_self_tiles(ps, pl.band_patch_ptr[b], pl.band_patch_ptr[b + 1], band_tiles[b], false, b > 0 ? 0 : -1);
+    for (const Tile& t : band_tiles[b]) band_cost[b] += t.cost;
+  }
+  std::vector<std::vector<int>> dev_bands(ndev);
+  {
+    std::vector<int> order(nb);
+    for (int b = 0; b < nb; b++) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return band_cost[a] > band_cost[c]; });
+    std::vector<double> load(ndev, 0.0);
+    for (int b : order) {
+      int g = 0;
+      for (int k = 1; k < ndev; k++)
+        if (load[k] < load[g]) g = k;
+      dev_bands[g].push_back(b);
+      load[g] += band_cost[b];
+    }
+    for (auto& v : dev_bands) std::sort(v.begin(), v.end());
+  }
   std::vector<int> ref_patch(N, 0), row_out(ps.ndof, -1);
   for (int p = 0; p < ps.npatch; p++)
     for (int i = ps.patch_dof_ptr[p]; i < ps.patch_dof_ptr[p + 1]; i++) ref_patch[ps.dof_orig[i]] = p;
   for (int i = 0; i < ps.ndof; i++) row_out[i] = ps.dof_orig[i];  // output row = reference id
-  StreamBands sb;
-  std::vector<Tile> tiles;
-  std::vector<int> tile_band, band_ntiles(nb, 0);
-  {
-    // Queue order: latest start time first.  Band b should be complete when the work of the bands up to b is done
-    // (deadline = that work spread over the SMs, in units of the tile cost model); a tile must start its own cost before
-    // the deadline of its band, so the long tiles of a band (its near-field diagonal blocks) start ahead of the cheap tiles
-    // of the band before, and the queue ends on cheap tiles.
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    std::vector<Tile> bt;
-    std::vector<double> key;
-    double done = 0.0;
-    for (int b = 0; b < nb; b++) {
-      build_self_tiles(ps, pl.band_patch_ptr[b], pl.band_patch_ptr[b + 1], bt, false, b > 0 ? 0 : -1);
-      double w = 0.0;
-      for (const Tile& t : bt) w += t.cost;
-      done += w / nsm;
-      for (const Tile& t : bt) {
-        tiles.push_back(t);
-        tile_band.push_back(b);
-        key.push_back(done - t.cost);
-      }
-      band_ntiles[b] = (int)bt.size();
+  if (trace) std::fprintf(stderr, "[lmat_stream_host] %d device(s), %d bands, tiles built at %.1f ms\n", ndev, nb, since(tr0));
+
+  struct Dev {
+    std::shared_ptr<DeviceState> ds;
+    double* d = nullptr;
+    cudaStream_t s = nullptr, cs = nullptr;
+    int* d_ints = nullptr;
+    int* flags = nullptr;  // this device's slice of the flag buffer (local band index)
+    size_t next = 0;       // next band to hand to the copy engine
+    bool done = false;
+  };
+  std::vector<Dev> devs(ndev);
+  int flag_off = 0;
+  // ---- every device: model upload, matrix, launch
+  for (int g = 0; g < ndev && err.empty(); g++) {
+    Dev& D = devs[g];
+    const std::vector<int>& mine = dev_bands[g];
+    const int nbl = (int)mine.size();
+    D.flags = g_flags + flag_off;
+    flag_off += nbl;
+    if (nbl == 0) {
+      D.done = true;
+      continue;
     }
-    std::vector<int> order(tiles.size());
-    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return key[a] < key[c]; });
-    std::vector<Tile> t2(tiles.size());
-    std::vector<int> b2(tiles.size());
-    for (size_t i = 0; i < order.size(); i++) {
-      t2[i] = tiles[order[i]];
-      b2[i] = tile_band[order[i]];
-    }
-    tiles.swap(t2);
-    tile_band.swap(b2);
-  }
-  sb.nbands = nb;
-  sb.N = (int)N;
-  sb.flags = flags;
-  if (trace) std::fprintf(stderr, "[lmat_stream_host] tiles built at %.1f ms\n", since(tr0));
-  if (err.empty()) {
-    std::memset(flags, 0, (size_t)nb * sizeof(int));
-    std::vector<int> hb(2 * nb + 1);  // band arrays of the kernel: tiles per band [nb], reference ids [nb+1], then 3 nb counters
-    for (int b = 0; b < nb; b++) hb[b] = band_ntiles[b];
-    for (int b = 0; b <= nb; b++) hb[nb + b] = pl.band_ref_ptr[b];
-    const size_t nt = tiles.size();
-    ck(cudaMallocAsync((void**)&d_ref_patch, (N + nt + 5 * (size_t)nb + 1) * sizeof(int), s), "cudaMallocAsync");
-    ck(cudaMemcpyAsync(d_ref_patch, ref_patch.data(), N * sizeof(int), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync");
-    ck(cudaMemcpyAsync(d_ref_patch + N, tile_band.data(), nt * sizeof(int), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync");
-    ck(cudaMemcpyAsync(d_ref_patch + N + nt, hb.data(), hb.size() * sizeof(int), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync");
-    ck(cudaMemsetAsync(d_ref_patch + N + nt + 2 * nb + 1, 0, (size_t)3 * nb * sizeof(int), s), "cudaMemsetAsync");
-    ck(cudaStreamSynchronize(s), "cudaStreamSynchronize");  // (host vectors are locals; nothing large is queued yet)
-  if (trace) std::fprintf(stderr, "[lmat_stream_host] small uploads done at %.1f ms\n", since(tr0));
-    ck(cudaMemsetAsync(d, 0, N * N * 8, s), "cudaMemsetAsync");
-    sb.d_ref_patch = d_ref_patch;
-    sb.d_tile_band = d_ref_patch + N;
-    sb.d_bands = d_ref_patch + N + nt;
-  }
-  if (err.empty()) err = gpu_lmat_tiles(ds->ps, ds->ps, tiles, row_out, true, d, (long long)N, s, nullptr, nullptr, false, &sb);
-  if (trace) std::fprintf(stderr, "[lmat_stream_host] %d bands, %zu tiles, launched at %.1f ms\n", nb, tiles.size(), since(tr0));
-  // hand the finished bands to the copy engine
-  volatile int* vf = flags;
-  for (int b = 0; b < nb && err.empty(); b++) {
-    while (!vf[b]) {
-      const cudaError_t q = cudaStreamQuery(s);
-      if (q == cudaErrorNotReady) {
-        std::this_thread::sleep_for(std::chrono::microseconds(50));
-        continue;
-      }
-      if (q != cudaSuccess) ck(q, "Kernel execution failed");
-      else if (!vf[b]) err = "Internal error: the streamed build ended without finishing its bands";
-      break;
-    }
+    if (!ck(cudaSetDevice(devs_ids[g]), "cudaSetDevice")) break;
+    err = ensure_device(m, devs_ids[g], D.ds);
     if (!err.empty()) break;
-    std::atomic_thread_fence(std::memory_order_acquire);
-    const int R0 = pl.band_ref_ptr[b], R1 = pl.band_ref_ptr[b + 1];
-    const size_t o0 = (size_t)R0 * N + R0, o1 = (size_t)R1 * N + R0;
-    ck(cudaMemcpy2DAsync(dst + o0, N * 8, d + o0, N * 8, (N - R0) * 8, (size_t)(R1 - R0), cudaMemcpyDeviceToHost, cs), "Device->host copy");
-    if ((size_t)R1 < N)
-      ck(cudaMemcpy2DAsync(dst + o1, N * 8, d + o1, N * 8, (size_t)(R1 - R0) * 8, N - R1, cudaMemcpyDeviceToHost, cs), "Device->host copy");
-    if (trace) std::fprintf(stderr, "[lmat_stream_host] band %d (rows [%d,%d), %d tiles) final at %.1f ms\n", b, R0, R1, band_ntiles[b], since(tr0));
+    err = D.ds->ps.upload_from(ps);  // the call's inputs: host model -> device, every call
+    if (!err.empty()) break;
+    D.ds->plan_serial = pl.serial;
+    err = scratch_rows(*D.ds, N * N * 8, &D.d);
+    if (!err.empty()) break;
+    if (!ck(cudaStreamCreateWithFlags(&D.s, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !ck(cudaStreamCreateWithFlags(&D.cs, cudaStreamNonBlocking), "cudaStreamCreate"))
+      break;
+    // Queue order: latest start time first.  A band should be complete when the work of this device's bands up to it is
+    // done (deadline = that work spread over the SMs, in units of the tile cost model); a tile must start its own cost
+    // before the deadline of its band, so the long tiles of a band (its near-field diagonal blocks) start ahead of the
+    // cheap tiles of the band before, and the queue ends on cheap tiles.
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, devs_ids[g]);
+    std::vector<Tile> tiles;
+    std::vector<int> tile_band;
+    std::vector<double> key;
+    double deadline = 0.0;
+    for (int l = 0; l < nbl; l++) {
+      const int b = mine[l];
+      deadline += band_cost[b] / nsm;
+      for (const Tile& t : band_tiles[b]) {
+        tiles.push_back(t);
+        tile_band.push_back(l);
+        key.push_back(deadline - t.cost);
+      }
+    }
+    {
+      std::vector<int> order(tiles.size());
+      for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return key[a] < key[c]; });
+      std::vector<Tile> t2(tiles.size());
+      std::vector<int> b2(tiles.size());
+      for (size_t i = 0; i < order.size(); i++) {
+        t2[i] = tiles[order[i]];
+        b2[i] = tile_band[order[i]];
+      }
+      tiles.swap(t2);
+      tile_band.swap(b2);
+    }
+    // band arrays of the kernel: tiles per band [nbl], first / one-past-last reference id of the rows [2 nbl], then 3 nbl counters
+    std::vector<int> hb(3 * nbl);
+    for (int l = 0; l < nbl; l++) {
+      hb[l] = (int)band_tiles[mine[l]].size();
+      hb[nbl + 2 * l] = pl.band_ref_ptr[mine[l]];
+      hb[nbl + 2 * l + 1] = pl.band_ref_ptr[mine[l] + 1];
+    }
+    const size_t nt = tiles.size();
+    ck(cudaMallocAsync((void**)&D.d_ints, (N + nt + 6 * (size_t)nbl) * sizeof(int), D.s), "cudaMallocAsync");
+    ck(cudaMemcpyAsync(D.d_ints, ref_patch.data(), N * sizeof(int), cudaMemcpyHostToDevice, D.s), "cudaMemcpyAsync");
+    ck(cudaMemcpyAsync(D.d_ints + N, tile_band.data(), nt * sizeof(int), cudaMemcpyHostToDevice, D.s), "cudaMemcpyAsync");
+    ck(cudaMemcpyAsync(D.d_ints + N + nt, hb.data(), hb.size() * sizeof(int), cudaMemcpyHostToDevice, D.s), "cudaMemcpyAsync");
+    ck(cudaMemsetAsync(D.d_ints + N + nt + 3 * nbl, 0, (size_t)3 * nbl * sizeof(int), D.s), "cudaMemsetAsync");
+    ck(cudaStreamSynchronize(D.s), "cudaStreamSynchronize");  // (host vectors are locals; nothing large is queued yet)
+    ck(cudaMemsetAsync(D.d, 0, N * N * 8, D.s), "cudaMemsetAsync");
+    if (!err.empty()) break;
+    StreamBands sb;
+    sb.nbands = nbl;
+    sb.N = (int)N;
+    sb.flags = D.flags;
+    sb.d_ref_patch = D.d_ints;
+    sb.d_tile_band = D.d_ints + N;
+    sb.d_bands = D.d_ints + N + nt;
+    err = gpu_lmat_tiles(D.ds->ps, D.ds->ps, tiles, row_out, true, D.d, (long long)N, D.s, nullptr, nullptr, false, &sb);
+    if (trace) std::fprintf(stderr, "[lmat_stream_host] device %d: %d bands, %zu tiles, launched at %.1f ms\n", devs_ids[g], nbl, tiles.size(), since(tr0));
   }
-  if (s) {
-    if (d_ref_patch) cudaFreeAsync(d_ref_patch, s);
-    cudaError_t ce = cudaStreamSynchronize(s);
-    if (trace) std::fprintf(stderr, "[lmat_stream_host] build stream done at %.1f ms\n", since(tr0));
-    if (ce == cudaSuccess && cs) ce = cudaStreamSynchronize(cs);
-    if (trace) std::fprintf(stderr, "[lmat_stream_host] copies done at %.1f ms\n", since(tr0));
+  // ---- hand the finished bands to the copy engines
+  for (bool pending = err.empty(); pending && err.empty();) {
+    pending = false;
+    bool progress = false;
+    for (int g = 0; g < ndev && err.empty(); g++) {
+      Dev& D = devs[g];
+      if (D.done) continue;
+      pending = true;
+      volatile int* vf = D.flags;
+      if (!vf[D.next]) {
+        if (!ck(cudaSetDevice(devs_ids[g]), "cudaSetDevice")) break;
+        const cudaError_t q = cudaStreamQuery(D.s);
+        if (q == cudaErrorNotReady) continue;
+        if (q != cudaSuccess) ck(q, "Kernel execution failed");
+        else if (!vf[D.next]) err = "Internal error: the streamed build ended without finishing its bands";
+        if (!err.empty()) break;
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      const int b = dev_bands[g][D.next];
+      const int R0 = pl.band_ref_ptr[b], R1 = pl.band_ref_ptr[b + 1];
+      const size_t o0 = (size_t)R0 * N + R0, o1 = (size_t)R1 * N + R0;
+      if (!ck(cudaSetDevice(devs_ids[g]), "cudaSetDevice")) break;
+      ck(cudaMemcpy2DAsync(dst + o0, N * 8, D.d + o0, N * 8, (N - R0) * 8, (size_t)(R1 - R0), cudaMemcpyDeviceToHost, D.cs), "Device->host copy");
+      if ((size_t)R1 < N)
+        ck(cudaMemcpy2DAsync(dst + o1, N * 8, D.d + o1, N * 8, (size_t)(R1 - R0) * 8, N - R1, cudaMemcpyDeviceToHost, D.cs), "Device->host copy");
+      if (trace) std::fprintf(stderr, "[lmat_stream_host] device %d: band %d (rows [%d,%d), %zu tiles) final at %.1f ms\n", devs_ids[g], b, R0, R1, band_tiles[b].size(), since(tr0));
+      progress = true;
+      if (++D.next == dev_bands[g].size()) D.done = true;
+    }
+    if (pending && !progress && err.empty()) std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
+  for (int g = 0; g < ndev; g++) {
+    Dev& D = devs[g];
+    if (!D.s) continue;
+    cudaSetDevice(devs_ids[g]);
+    if (D.d_ints) cudaFreeAsync(D.d_ints, D.s);
+    cudaError_t ce = cudaStreamSynchronize(D.s);
+    if (trace) std::fprintf(stderr, "[lmat_stream_host] device %d: build stream done at %.1f ms\n", devs_ids[g], since(tr0));
+    if (ce == cudaSuccess && D.cs) ce = cudaStreamSynchronize(D.cs);
+    if (trace) std::fprintf(stderr, "[lmat_stream_host] device %d: copies done at %.1f ms\n", devs_ids[g], since(tr0));
     if (ce != cudaSuccess && err.empty()) err = std::string("Kernel execution failed: ") + cudaGetErrorString(ce);
+    cudaStreamDestroy(D.s);
+    if (D.cs) cudaStreamDestroy(D.cs);
   }
-  if (s) cudaStreamDestroy(s);
-  if (cs) cudaStreamDestroy(cs);
   cudaGetLastError();
   if (trace) std::fprintf(stderr, "[lmat_stream_host] returning at %.1f ms\n", since(tr0));
   return err;
@@ -756,13 +829,14 @@ static std::string lmat_full_host(Model& m, double* dst) {
   std::vector<int> devs_ids = build_devices();
   if (devs_ids.empty()) return "No CUDA device available (the B200 backend has no CPU fallback)";
   std::string err;
-  if (devs_ids.size() == 1 && m.n_vcoils == 0 && ensure_banded_plan(m, err)) {
-    // one device, large model: banded plan; a page-locked destination is served by the streamed build, a pageable one by
-    // the row bands below on the same patches (same bits)
-    if (is_pinned(dst)) {
-      if (cudaSetDevice(devs_ids[0]) != cudaSuccess) return "cudaSetDevice failed";
-      return lmat_stream_host(m, dst, trace);
-    }
+  const bool pinned_dst = is_pinned(dst);
+  bool banded = false;
+  if (m.n_vcoils == 0 && !std::getenv("THINCURR_B200_FULL_ROWS") && (devs_ids.size() == 1 || (pinned_dst && stream_devices_ok(devs_ids, N * N * 8))))
+    banded = ensure_banded_plan(m, err, (int)devs_ids.size());
+  if (banded) {
+    // large model: banded plan; a page-locked destination is served by the streamed build (bands dealt out to the devices),
+    // a pageable one (one device) by the row bands below on the same patches (same bits)
+    if (pinned_dst) return lmat_stream_host(m, dst, devs_ids, trace);
   } else {
     if (!err.empty()) return err;
     // one device: the rows leave band by band and every band needs enough tiles for all SMs: patches as for 8 shards

@@ -56,8 +56,8 @@ struct StreamBands {
   int nbands;
   const int* d_tile_band;     // device, [ntiles]: band of every tile (the queue order is the caller's)
   const int* d_ref_patch;     // device, [N]: patch of a reference DOF id
-  int* d_bands;               // device, [5 nbands + 1]: tiles per band, reference ids of the bands' rows (nbands + 1), then
-                              // 3 nbands zeroed counters
+  int* d_bands;               // device, [6 nbands]: tiles per band, first / one-past-last reference id of every band's rows
+                              // (2 nbands), then 3 nbands zeroed counters
   int N;
   int* flags;                 // mapped page-locked host memory, [nbands], zeroed by the caller
 };

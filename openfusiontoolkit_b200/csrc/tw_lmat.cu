@@ -93,7 +93,7 @@ struct LmatArgs {
   int nbands;
   const int* tile_band;               // [ntiles] band of a tile (the queue order is free: latest start time first)
   const int* band_ntiles;             // [nbands] tiles per band
-  const int* band_ref;                // [nbands+1] reference DOF ids of the band's rows
+  const int* band_ref;                // [nbands][2] first / one-past-last reference DOF id of the band's rows
   const int* ref_patch;               // [N] patch of a reference DOF id
   int N;
   int* band_state;                    // [3][nbands]: tiles finished, next mirror task, mirror tasks finished
@@ -1184,7 +1184,7 @@ __device__ __noinline__ void fetch_banded(int* __restrict__ item, int* tile_coun
     for (int b = item[3]; b < nbands; b++) {
       if (*(volatile int*)&tiles_done[b] < band_ntiles[b]) break;  // bands hand out their mirror tasks in order
       const int k = atomicAdd(&mir_next[b], 1);
-      if (k < mirror_task_count(band_ref[b], band_ref[b + 1], N)) {
+      if (k < mirror_task_count(band_ref[2 * b], band_ref[2 * b + 1], N)) {
         __threadfence();  // the tile stores of the other CTAs (released by their fences) before this task's loads
         item[0] = -2;
         item[1] = k;
@@ -1245,7 +1245,7 @@ __global__ void __launch_bounds__(NT, 1) lmat_tile_kernel(const LmatArgs A) {  /
     const int t = S.item[0];
     if (t >= A.ntiles || t == -1) break;
     if (t == -2) {  // mirror task of a finished band
-      const int b = S.item[2], R0 = A.band_ref[b], R1 = A.band_ref[b + 1];
+      const int b = S.item[2], R0 = A.band_ref[2 * b], R1 = A.band_ref[2 * b + 1];
       mirror_task(S.T, R0, R1, A.N, A.ref_patch, A.out, A.ld, S.item[1], tid);
       __threadfence_system();
       __syncthreads();
@@ -1675,7 +1675,7 @@ std::string gpu_lmat_tiles(const DevicePatchSet& A, const DevicePatchSet& B, con
     a.nbands = nb;
     a.band_ntiles = sb->d_bands;
     a.band_ref = sb->d_bands + nb;
-    a.band_state = sb->d_bands + 2 * nb + 1;
+    a.band_state = sb->d_bands + 3 * nb;
     a.tile_band = sb->d_tile_band;
     a.ref_patch = sb->d_ref_patch;
     a.N = sb->N;

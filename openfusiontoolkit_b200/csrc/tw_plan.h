@@ -78,6 +78,7 @@ struct Plan {
   // banded plan (streamed single-device build, tw_capi.cu): band b = reference DOF ids [band_ref_ptr[b], band_ref_ptr[b+1])
   // = patches [band_patch_ptr[b], band_patch_ptr[b+1]) (the hole patches belong to the last band); empty otherwise
   std::vector<int> band_ref_ptr, band_patch_ptr;
+  int band_ndev = 0;     // devices the bands were sized for
   PatchSet ps;
 };
 

@@ -66,7 +66,8 @@ for k, v in res.items():
         # other patches (the one-device build of a model this size plans its patches band by band) or another tile
         # orientation (symmetric shards): equal to rounding of the summation order
         assert np.abs(v - ref).max() <= 1e-13 * np.abs(ref).max(), k
-assert np.array_equal(res['sym'], res['sym_pageable'])
+# ('sym': page-locked destination = streamed build, bands dealt out to the devices; 'sym_pageable': symmetric shards +
+#  peer reads; 'full*': full-row shards, one path for both destinations)
 assert np.array_equal(res['full'], res['full_pageable'])
 print('INPROC_OK')
 """
