@@ -120,13 +120,25 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def _lazy_zeros(n):
+    """n x n float64 zeros whose pages are committed on first touch (the CPU sample fills a slab of rows of a matrix
+    that need not fit the host): calloc where the kernel's overcommit heuristic allows it, else an anonymous
+    MAP_NORESERVE mapping."""
+    try:
+        return np.zeros((n, n))
+    except MemoryError:
+        import mmap
+        buf = mmap.mmap(-1, n * n * 8, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS | getattr(mmap, 'MAP_NORESERVE', 0x4000))
+        return np.frombuffer(buf, dtype=np.float64).reshape(n, n)
+
+
 def cpu_sample(mesh, nthreads, variant=None, seconds=8.0, O=None):
     """Oracle C/OpenMP loop (reference schedule) over a bounded slab of row cells in the middle of the mesh, sized from a
     short probe so that it takes about `seconds`; returns (pairs/s, description, model)."""
     from oracle import tw_oracle as tw
     if O is None:
         O = tw.OracleModel(mesh['r'], mesh['lc'], None, nodesets=mesh['nodesets'], closures=mesh['closures'])
-    out = np.zeros((O.nelems, O.nelems))  # calloc-backed: only the rows the sample touches are ever committed
+    out = _lazy_zeros(O.nelems)  # only the rows the sample touches are ever committed
     mid = O.nc // 2
     probe = min(O.nc, 100 * nthreads)  # one schedule(dynamic,100) chunk per thread
     t0 = time.perf_counter()
@@ -176,7 +188,7 @@ def run_reference(args, rank, world):
     line = {'impl': 'reference', 'metric': 'L-matrix pair-integrals/s', 'value': value, 'unit': 'pairs/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': None,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload_name(mesh), 'np': int(mesh['r'].shape[0]), 'nc': nc, 'nc2_pairs': nc * nc},
+            'config': {'workload': workload_name(mesh), 'np': int(mesh['r'].shape[0]), 'nc': nc, 'nelems': int(O.nelems), 'nc2_pairs': nc * nc},
             'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': vals[-1][1]},
             'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
