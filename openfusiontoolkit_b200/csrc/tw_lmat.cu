@@ -327,56 +327,61 @@ __device__ __noinline__ double far_group_dispatch(const double* gI, int c1, cons
 // 10 FP64-pipe instructions per 1/r: 1 add + 3 fma (d^2), 5 (rsqrt correction), 1 fma (weighted sum).
 // The QB evaluations of one row point are advanced stage by stage so that QB independent
 // dependency chains are in flight (DFMA latency is 8 cycles, the pipe takes one warp every 2).
-template <int N, int OFF>  // @region far_tab
+// one block of QB column points (q0 .. q0+QB-1, all valid) against all N row points; `total` carries the weighted sum
+template <int N, int OFF, int QB>  // @region far_tab
+__device__ __forceinline__ double far_tab_block(const double2* __restrict__ tabI, const double2* __restrict__ tabJ, int c1, int c2, int q0, double total) {
+  const double* bw = c_qwts + OFF;  // OFF = TCQ_OFF[iquad]: weights become constant-bank operands
+  double xj[QB], yj[QB], zj[QB], sj[QB], acc[QB];
+#pragma unroll
+  for (int q = 0; q < QB; q++) {
+    const double2 u = tabJ[((q0 + q) * 2) * kCH + c2], v = tabJ[((q0 + q) * 2 + 1) * kCH + c2];
+    xj[q] = u.x;
+    yj[q] = u.y;
+    zj[q] = v.x;
+    sj[q] = v.y;
+    acc[q] = 0.0;
+  }
+  double2 an = tabI[c1], bn = tabI[CI + c1];  // row point p+1 is loaded while point p is evaluated
+#pragma unroll(N <= 7 ? N : 2)
+  for (int p = 0; p < N; p++) {
+    const double2 a = an, b = bn;
+    if (p + 1 < N) {
+      an = tabI[((p + 1) * 2) * CI + c1];
+      bn = tabI[((p + 1) * 2 + 1) * CI + c1];
+    }
+    const double wp = bw[p];
+    double d2[QB], y0[QB], e[QB], h[QB];
+#pragma unroll
+    for (int q = 0; q < QB; q++) d2[q] = fma(a.x, xj[q], fma(a.y, yj[q], fma(b.x, zj[q], b.y + sj[q])));
+#pragma unroll
+    for (int q = 0; q < QB; q++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[q]) : "d"(d2[q]));
+#pragma unroll
+    for (int q = 0; q < QB; q++) h[q] = d2[q] * y0[q];
+#pragma unroll
+    for (int q = 0; q < QB; q++) e[q] = fma(-h[q], y0[q], 1.0);
+#pragma unroll
+    for (int q = 0; q < QB; q++) h[q] = fma(0.375, e[q], 0.5);
+#pragma unroll
+    for (int q = 0; q < QB; q++) e[q] = e[q] * y0[q];
+#pragma unroll
+    for (int q = 0; q < QB; q++) y0[q] = fma(e[q], h[q], y0[q]);
+#pragma unroll
+    for (int q = 0; q < QB; q++) acc[q] = fma(wp, y0[q], acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < QB; q++) total = fma(bw[q0 + q], acc[q], total);
+  return total;
+}
+// N column points in blocks of QB held in registers, the remainder (7 = 4 + 3, 19 = 4 x 4 + 3) as a block of its own size
+template <int N, int OFF>
 __device__ __forceinline__ double far_tab(const double2* __restrict__ tabI, const double2* __restrict__ tabJ, int c1, int c2) {
   // c1: row cell within the pass (stride CI), c2: column cell (stride kCH)
-  const double* bw = c_qwts + OFF;  // OFF = TCQ_OFF[iquad]: weights become constant-bank operands
-  constexpr int QB = (N == 6) ? 3 : ((N == 15 || N == 25) ? 5 : 4);  // j-side points held in registers
+  constexpr int QB = (N == 6) ? 3 : ((N == 15 || N == 25) ? 5 : 4);
+  constexpr int NFULL = N / QB, REM = N - NFULL * QB;
   double total = 0.0;
 #pragma unroll 1
-  for (int q0 = 0; q0 < N; q0 += QB) {
-    double xj[QB], yj[QB], zj[QB], sj[QB], acc[QB];
-#pragma unroll
-    for (int q = 0; q < QB; q++) {
-      const int qq = (q0 + q < N) ? q0 + q : N - 1;
-      const double2 u = tabJ[(qq * 2) * kCH + c2], v = tabJ[(qq * 2 + 1) * kCH + c2];
-      xj[q] = u.x;
-      yj[q] = u.y;
-      zj[q] = v.x;
-      sj[q] = v.y;
-      acc[q] = 0.0;
-    }
-    double2 an = tabI[c1], bn = tabI[CI + c1];  // row point p+1 is loaded while point p is evaluated
-#pragma unroll(N <= 7 ? N : 2)
-    for (int p = 0; p < N; p++) {
-      const double2 a = an, b = bn;
-      if (p + 1 < N) {
-        an = tabI[((p + 1) * 2) * CI + c1];
-        bn = tabI[((p + 1) * 2 + 1) * CI + c1];
-      }
-      const double wp = bw[p];
-      double d2[QB], y0[QB], e[QB], h[QB];
-#pragma unroll
-      for (int q = 0; q < QB; q++) d2[q] = fma(a.x, xj[q], fma(a.y, yj[q], fma(b.x, zj[q], b.y + sj[q])));
-#pragma unroll
-      for (int q = 0; q < QB; q++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[q]) : "d"(d2[q]));
-#pragma unroll
-      for (int q = 0; q < QB; q++) h[q] = d2[q] * y0[q];
-#pragma unroll
-      for (int q = 0; q < QB; q++) e[q] = fma(-h[q], y0[q], 1.0);
-#pragma unroll
-      for (int q = 0; q < QB; q++) h[q] = fma(0.375, e[q], 0.5);
-#pragma unroll
-      for (int q = 0; q < QB; q++) e[q] = e[q] * y0[q];
-#pragma unroll
-      for (int q = 0; q < QB; q++) y0[q] = fma(e[q], h[q], y0[q]);
-#pragma unroll
-      for (int q = 0; q < QB; q++) acc[q] = fma(wp, y0[q], acc[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < QB; q++)
-      if (q0 + q < N) total = fma(bw[q0 + q], acc[q], total);
-  }
+  for (int q0 = 0; q0 < NFULL * QB; q0 += QB) total = far_tab_block<N, OFF, QB>(tabI, tabJ, c1, c2, q0, total);
+  if (REM > 0) total = far_tab_block<N, OFF, (REM > 0 ? REM : 1)>(tabI, tabJ, c1, c2, NFULL * QB, total);
   return total;
 }
 
