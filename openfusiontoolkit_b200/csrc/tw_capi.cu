@@ -814,12 +814,13 @@ static std::string lmat_stream_host(Model& m, double* dst, const std::vector<int
   return err;
 }
 
-// full self-inductance matrix into host memory dst[nelems][nelems] (reference layout), rows sharded
-// over the usable devices, each shard copied straight to its place.  One device: the matrix is built in row bands and
-// the rows of a finished band go to the host (copy engine) while the next band is evaluated.  Several devices that can
-// read each other's memory: symmetric shards (upper trapezoid per device, no pair integral evaluated twice); all builds
-// are launched first, then every device fetches the transposed blocks of the earlier shards over NVLink
-// (symmetrize_cross_kernel on peer memory) and sends its rows to the host.
+// full self-inductance matrix into host memory dst[nelems][nelems] (reference layout).  Large models without V-coils and
+// with a page-locked destination: the streamed build above (lmat_stream_host).  Otherwise the rows are sharded over the
+// usable devices, each shard copied straight to its place.  One device: the matrix is built in row bands (separate
+// launches) and the rows of a finished band go to the host (copy engine, or the staging thread of a pageable
+// destination) while the next band is evaluated.  Several devices that can read each other's memory: symmetric shards
+// (no pair integral evaluated twice); all builds are launched first, then every device fetches the transposed blocks of
+// the other shards over NVLink (symmetrize_cross_kernel on peer memory) and sends its rows to the host.
 static std::string lmat_full_host(Model& m, double* dst) {
   const size_t N = (size_t)m.nelems;
   const bool trace = std::getenv("THINCURR_B200_TRACE") != nullptr;
