@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -874,9 +875,18 @@ std::string gpu_bmat(Model& m) {
   m.Bdr.alloc(3 * np * std::max(m.n_icoils, 1));
   if (!m.Bel.p) return "Host allocation of the B-field operator failed";
   if (!(e = ensure_plan(m)).empty()) return e;
-  int ndev = std::min(visible_devices(), std::max(1, m.plan->ps.npatch));
+  // devices: all visible ones, or only the caller's current device when the process is one rank of a one-process-per-GPU
+  // job (as thincurr_Lmat does); the caller's device is current again on return
+  int cur = 0;
+  CKO(cudaGetDevice(&cur));
+  std::vector<int> devs;
+  if (std::getenv("THINCURR_B200_ONE_DEVICE") || (std::getenv("LOCAL_RANK") && !std::getenv("THINCURR_B200_NDEV"))) devs.push_back(cur);
+  else
+    for (int g = 0; g < visible_devices(); g++) devs.push_back(g);
+  if (devs.empty()) devs.push_back(cur);
+  const int ndev = std::min((int)devs.size(), std::max(1, m.plan->ps.npatch));
   for (int g = 0; g < ndev; g++) {
-    CKO(cudaSetDevice(g));
+    CKO(cudaSetDevice(devs[g]));
     int p0, p1;
     std::vector<int> rows;
     shard_rows(m, ndev, g, p0, p1, rows);
@@ -890,7 +900,7 @@ std::string gpu_bmat(Model& m) {
     for (size_t cp = 0; cp < 3 * np; cp++)
       for (size_t r = 0; r < rows.size(); r++) m.Bel.p[cp * N + rows[r]] = h[cp * rows.size() + r];
   }
-  CKO(cudaSetDevice(0));
+  CKO(cudaSetDevice(cur));
   // Bdr(np, n_icoils, 3) = mu0/4pi * Biot-Savart of the I-coils
   if (m.n_icoils > 0) {
     FlatCoils ic;
@@ -915,10 +925,12 @@ std::string gpu_bmat(Model& m) {
 std::string gpu_cross_coupling(Model& m1, Model& m2, double* Mmat_host) {
   std::string e = need_gpu();
   if (!e.empty()) return e;
-  CKO(cudaSetDevice(0));
+  int cur = 0;  // the caller's current device
+  CKO(cudaGetDevice(&cur));
   std::shared_ptr<DeviceState> d1, d2;
-  if (!(e = ensure_device(m1, 0, d1)).empty()) return e;
-  if (!(e = ensure_device(m2, 0, d2)).empty()) return e;
+  if (!(e = ensure_device(m1, cur, d1)).empty()) return e;
+  if (!(e = ensure_device(m2, cur, d2)).empty()) return e;
+  CKO(cudaSetDevice(cur));
   const PatchSet &p1 = m1.plan->ps, &p2 = m2.plan->ps;
   const size_t N1 = (size_t)m1.nelems, N2 = (size_t)m2.nelems;
   std::vector<Tile> tiles;
