@@ -435,25 +435,33 @@ def main():
             dist.barrier(group=host_group)
         if rank == 0:
             os.environ['THINCURR_B200_NDEV'] = str(world)
-            dt = None
-            try:
-                with _c_stdout_to_stderr():   # (the library reports like the reference: "Building ... Time = ..." on stdout)
-                    T.compute_Lmat()  # allocates + pins the library-owned host matrix, device scratch, peer mappings
-                    T.compute_Lmat()
-                    nrep = 2
-                    t0 = time.perf_counter()
-                    for _ in range(nrep):
+            dt, e2e_note = None, None
+            for attempt in range(2):
+                try:
+                    with _c_stdout_to_stderr():   # (the library reports like the reference: "Building ... Time = ..." on stdout)
+                        T.compute_Lmat()  # allocates + pins the library-owned host matrix, device scratch, peer mappings
                         T.compute_Lmat()
-                    dt = (time.perf_counter() - t0) / nrep
-            except Exception as ex:   # the device-timed line above stands on its own
-                e2e = {'error': str(ex)[:300]}
+                        nrep = 2
+                        t0 = time.perf_counter()
+                        for _ in range(nrep):
+                            T.compute_Lmat()
+                        dt = (time.perf_counter() - t0) / nrep
+                    break
+                except Exception as ex:   # the device-timed line above stands on its own
+                    e2e = {'error': str(ex)[:300]}
+                    if attempt == 0 and world > 1:
+                        # (every device holds the whole matrix in the streamed build; retry with row shards + peer reads)
+                        os.environ['THINCURR_B200_NO_MULTI_STREAM'] = '1'
+                        e2e_note = 'streamed multi-device build failed (%s); symmetric shards + peer reads instead' % str(ex)[:200]
+                    else:
+                        break
         if rank == 0 and dt is not None:
             pi = T.plan_info()
             e2e = {'value': visited / dt, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(pi.get('model_bytes', 0)) * world,
                    'd2h_bytes_per_step': int(N) * int(N) * 8, 'ms_per_step': dt * 1e3,
                    'api': 'ThinCurr.compute_Lmat() -> thincurr_Lmat: host mesh -> %d device(s) of one process -> library-owned pinned host matrix (reference layout)' % world
                           + '; streamed build (one launch per device over its row bands, every band leaves as two strided copies while later bands are evaluated)',
-                   'plan': pi,
+                   'plan': pi, 'note': e2e_note,
                    'sym_check': float(np.abs(T.Lmat[:2048, :2048] - T.Lmat[:2048, :2048].T).max())}
         if world > 1:
             dist.barrier(group=host_group)
